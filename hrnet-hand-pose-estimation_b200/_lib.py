@@ -1,0 +1,114 @@
+"""ctypes binding of libhrnb.so (include/hrnb.h).
+
+There is NO fallback: if the library cannot be loaded every product entry point raises.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhrnb.so")
+
+_lib = None
+_lock = threading.Lock()
+
+HRNB_CONV_RELU = 1
+HRNB_CONV_OUT_NCHW = 2
+HRNB_CONV_GATHER = 4
+
+
+def guard_lead(Wp):
+    return ((Wp + 2) + 7) // 8 * 8
+
+
+def guard_tail(Wp):
+    return ((Wp + 2) + 7) // 8 * 8 + 512
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("inp", C.c_void_p), ("in_ps", C.c_int64),
+        ("wpk", C.c_void_p), ("bias", C.c_void_p),
+        ("res", C.c_void_p), ("res_ps", C.c_int64),
+        ("out", C.c_void_p), ("out_ps", C.c_int64),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("in_H", C.c_int32), ("in_W", C.c_int32),
+        ("cin", C.c_int32), ("cout", C.c_int32), ("taps", C.c_int32), ("stride", C.c_int32),
+        ("KC", C.c_int32), ("BN", C.c_int32), ("MB", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
+class FuseParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * 4), ("src_ps", C.c_int64 * 4), ("shift", C.c_int32 * 4),
+        ("nsrc", C.c_int32),
+        ("out", C.c_void_p), ("out_ps", C.c_int64),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("relu", C.c_int32),
+    ]
+
+
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+_SIGS = {
+    "hrnb_conv": (C.c_int, [C.POINTER(ConvParams), _vp]),
+    "hrnb_conv_smem_bytes": (_i64, [C.POINTER(ConvParams)]),
+    "hrnb_pack_conv_weights": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hrnb_stem_conv1": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "hrnb_fuse_sum": (C.c_int, [C.POINTER(FuseParams), _vp]),
+    "hrnb_bilinear_up": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "hrnb_pf8_to_nchw_f32": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hrnb_nchw_f32_to_pf8": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "hrnb_decode_argmax": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "hrnb_softmax_softargmax": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hrnb_softargmax": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "hrnb_softmax_softargmax_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hrnb_final_preds": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "hrnb_loss_heatmap": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hrnb_loss_pose2d": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "hrnb_last_error": (C.c_char_p, []),
+    "hrnb_abi_version": (C.c_int, []),
+    "hrnb_launch_count": (_i64, []),
+    "hrnb_debug_set": (C.c_int, [C.c_int, C.c_int]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+class HrnbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if libhrnb.so is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise HrnbError(
+                "libhrnb.so not found at %s - run `python hrnet-hand-pose-estimation_b200/build.py` "
+                "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(h, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if h.hrnb_abi_version() != 1:
+            raise HrnbError("libhrnb.so ABI version mismatch")
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().hrnb_last_error()
+        raise HrnbError("libhrnb call failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(lib().hrnb_launch_count())

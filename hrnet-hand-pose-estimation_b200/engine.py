@@ -1,0 +1,346 @@
+"""Inference engine: turns a reference-layout state_dict into packed bf16 weights + a launch plan.
+
+Host side of the hot path.  Everything numerical happens in libhrnb.so; this file only decides which
+kernel runs on which buffer and stream:
+
+  * BN (eval) is folded: scale into the bf16 weights, shift into the fp32 epilogue bias
+    (BatchNorm2d eps 1e-5: lib/models/pose_hrnet.py:36 et al.).
+  * every conv is one launch with bias / residual / ReLU fused (BasicBlock :43-59, Bottleneck :80-100).
+  * a fuse layer = low-resolution 1x1 convs + stride-2 chains + ONE sum kernel per output that applies the
+    nearest up-sampling on the fly and the ReLU (HighResolutionModule.forward :247-266) - up-sampled
+    tensors are never materialised.
+  * the head writes branch 0 straight into the concat buffer and bilinearly up-samples branches 1-3 into
+    it (:560-565 / pose_hrnet_softmax.py:499-504).
+  * branches of a module run on separate CUDA streams; the whole plan is replayed as one CUDA graph.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib, arch as A
+from .ops import ConvLayer, PF8
+from ._lib import FuseParams
+
+EPS = 1e-5
+
+
+def _fold(sd, bn_key, conv_bias=None):
+    g, b = sd[bn_key + ".weight"].float(), sd[bn_key + ".bias"].float()
+    m, v = sd[bn_key + ".running_mean"].float(), sd[bn_key + ".running_var"].float()
+    scale = g / torch.sqrt(v + EPS)
+    shift = b - m * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.float() * scale
+    return scale, shift
+
+
+class _Step:
+    __slots__ = ("kind", "sid", "fn", "other", "name")
+
+    def __init__(self, kind, sid, fn=None, other=None, name=""):
+        self.kind, self.sid, self.fn, self.other, self.name = kind, sid, fn, other, name
+
+
+class Plan:
+    """Buffers + ordered launch list for one (batch, H, W)."""
+
+    def __init__(self, engine, B, H, W):
+        self.engine, self.B, self.H, self.W = engine, B, H, W
+        self.steps = []
+        self.keep = []          # keeps ctypes structs / tensors alive
+        self.graph = None
+        self.n_launch = 0
+        dev = engine.device
+        self.x = torch.zeros((B, 3, H, W), dtype=torch.float32, device=dev)
+        self.out = {}
+        self._build()
+
+    # ---- step recording ---------------------------------------------------------------------------
+    def _op(self, sid, fn, name):
+        self.steps.append(_Step("op", sid, fn, name=name))
+        self.n_launch += 1
+
+    def _wait(self, sid, other):
+        if sid != other:
+            self.steps.append(_Step("wait", sid, other=other))
+
+    def _buf(self, C_, H, W):
+        t = PF8(self.B, C_, H, W, device=self.engine.device)
+        self.keep.append(t)
+        return t
+
+    def _conv(self, sid, layer, x, out, res=None, name=""):
+        p = layer.params(x, out, res)
+        self.keep.append(p)
+        lib = _lib.lib()
+        ref = C.byref(p)
+
+        def fn(lib=lib, ref=ref):
+            _lib.check(lib.hrnb_conv(ref, _lib.stream_ptr()))
+        self._op(sid, fn, name)
+        return out
+
+    def _fuse(self, sid, srcs, shifts, out, name=""):
+        p = FuseParams()
+        for i, (s, sh) in enumerate(zip(srcs, shifts)):
+            p.src[i], p.src_ps[i], p.shift[i] = s.ptr, s.ps, sh
+        p.nsrc = len(srcs)
+        p.out, p.out_ps = out.ptr, out.ps
+        p.N, p.H, p.W, p.C, p.relu = out.N, out.H, out.W, out.C, 1
+        self.keep.append(p)
+        lib = _lib.lib()
+        ref = C.byref(p)
+
+        def fn(lib=lib, ref=ref):
+            _lib.check(lib.hrnb_fuse_sum(ref, _lib.stream_ptr()))
+        self._op(sid, fn, name)
+        return out
+
+    # ---- the network -------------------------------------------------------------------------------
+    def _build(self):
+        e, L, B = self.engine, self.engine.layers, self.B
+        arch, lib = e.arch, _lib.lib()
+        ch = arch.channels
+        H2, W2, H4, W4 = self.H // 2, self.W // 2, self.H // 4, self.W // 4
+        if self.H % 32 or self.W % 32:
+            raise ValueError("input H and W must be multiples of 32 (four resolutions, each halving)")
+
+        # stem
+        t1 = self._buf(64, H2, W2)
+        x, w27, b1 = self.x, e.stem_w, e.stem_b
+
+        def stem(lib=lib, x=x, w27=w27, b1=b1, t1=t1, B=B, H=self.H, W=self.W):
+            _lib.check(lib.hrnb_stem_conv1(x.data_ptr(), w27.data_ptr(), b1.data_ptr(), t1.ptr, t1.ps, B, H, W,
+                                           _lib.stream_ptr()))
+        self._op(0, stem, "conv1")
+        cur = self._conv(0, L["conv2"], t1, self._buf(64, H4, W4), name="conv2")
+
+        # layer1: 4 bottlenecks
+        for b in range(4):
+            pre = "layer1.%d" % b
+            c1 = self._conv(0, L[pre + ".conv1"], cur, self._buf(64, H4, W4), name=pre + ".conv1")
+            c2 = self._conv(0, L[pre + ".conv2"], c1, self._buf(64, H4, W4), name=pre + ".conv2")
+            res = cur
+            if b == 0:
+                res = self._conv(0, L[pre + ".downsample.0"], cur, self._buf(256, H4, W4), name=pre + ".downsample")
+            cur = self._conv(0, L[pre + ".conv3"], c2, self._buf(256, H4, W4), res=res, name=pre + ".conv3")
+
+        # transition1
+        res_hw = [(H4 >> i, W4 >> i) for i in range(4)]
+        xs = [self._conv(0, L["transition1.0.0"], cur, self._buf(ch[0], *res_hw[0]), name="transition1.0")]
+        self._wait(1, 0)
+        xs.append(self._conv(1, L["transition1.1.0.0"], cur, self._buf(ch[1], *res_hw[1]), name="transition1.1"))
+
+        cat = None
+        stage3_b0 = None
+        for s, nmod in zip((2, 3, 4), arch.modules):
+            nb = s
+            if s > 2:
+                self._wait(nb - 1, nb - 2)
+                key = "transition%d.%d.0.0" % (s - 1, nb - 1)
+                xs.append(self._conv(nb - 1, L[key], xs[-1], self._buf(ch[nb - 1], *res_hw[nb - 1]), name=key))
+            for m in range(nmod):
+                pre = "stage%d.%d" % (s, m)
+                last_module = (s == 4 and m == nmod - 1)
+                # branches: 4 BasicBlocks each, branch i on stream i
+                for i in range(nb):
+                    for b in range(arch.blocks):
+                        bp = "%s.branches.%d.%d" % (pre, i, b)
+                        y = self._conv(i, L[bp + ".conv1"], xs[i], self._buf(ch[i], *res_hw[i]), name=bp + ".conv1")
+                        xs[i] = self._conv(i, L[bp + ".conv2"], y, self._buf(ch[i], *res_hw[i]), res=xs[i],
+                                           name=bp + ".conv2")
+                # every fuse output needs every branch
+                for i in range(nb):
+                    for j in range(nb):
+                        self._wait(i, j)
+                outs = []
+                for i in range(nb):
+                    srcs, shifts = [], []
+                    for j in range(nb):
+                        if j == i:
+                            srcs.append(xs[j]); shifts.append(0)
+                        elif j > i:
+                            fp = "%s.fuse_layers.%d.%d.0" % (pre, i, j)
+                            z = self._conv(i, L[fp], xs[j], self._buf(ch[i], *res_hw[j]), name=fp)
+                            srcs.append(z); shifts.append(j - i)
+                        else:
+                            t = xs[j]
+                            for k in range(i - j):
+                                fp = "%s.fuse_layers.%d.%d.%d.0" % (pre, i, j, k)
+                                co = ch[i] if k == i - j - 1 else ch[j]
+                                t = self._conv(i, L[fp], t, self._buf(co, *res_hw[j + k + 1]), name=fp)
+                            srcs.append(t); shifts.append(0)
+                    if last_module and i == 0:
+                        cat = self._buf(arch.head_channels, *res_hw[0])
+                        dst = cat.view_planes(0, ch[0] // 8)
+                    else:
+                        dst = self._buf(ch[i], *res_hw[i])
+                    outs.append(self._fuse(i, srcs, shifts, dst, name="%s.fuse.%d" % (pre, i)))
+                # the next module's branch j reads outs[j], produced on stream j: no extra sync needed;
+                # the fuse kernels of other streams still read the old xs, which are distinct buffers.
+                xs = outs
+            if s == 3:
+                stage3_b0 = xs[0]
+
+        # head: bilinear up-sample branches 1..3 into the concat buffer, each on its own stream
+        align = 1 if e.variant == "softmax" else 0
+        plane0 = ch[0] // 8
+        for i in range(1, 4):
+            dst = cat.view_planes(plane0, ch[i] // 8)
+            plane0 += ch[i] // 8
+            src = xs[i]
+
+            def up(lib=lib, src=src, dst=dst, align=align):
+                _lib.check(lib.hrnb_bilinear_up(src.ptr, src.ps, src.N, src.C, src.H, src.W, dst.ptr, dst.ps, dst.H,
+                                                dst.W, align, _lib.stream_ptr()))
+            self._op(i, up, "head.bilinear.%d" % i)
+        for i in range(1, 4):
+            self._wait(0, i)
+        hid = self._conv(0, L["last_layer.0"], cat, self._buf(arch.head_channels, *res_hw[0]), name="last_layer.0")
+        J = arch.num_joints
+        logits = torch.empty((B, J, H4, W4), dtype=torch.float32, device=e.device)
+        self._conv(0, L["last_layer.3"], hid, logits, name="last_layer.3")
+        self.out["logits"] = logits
+        self.cat, self.stage3_b0 = cat, stage3_b0
+
+        if e.variant == "softmax":
+            heat = torch.empty_like(logits)
+            coords = torch.empty((B, J, 2), dtype=torch.float32, device=e.device)
+            temp = e.temp
+
+            def sm(lib=lib, logits=logits, temp=temp, heat=heat, coords=coords, BJ=B * J, h=H4, w=W4):
+                _lib.check(lib.hrnb_softmax_softargmax(logits.data_ptr(), temp.data_ptr(), BJ, h, w, heat.data_ptr(),
+                                                       coords.data_ptr(), _lib.stream_ptr()))
+            self._op(0, sm, "softmax_softargmax")
+            self.out["heatmap"], self.out["coords"] = heat, coords
+        else:
+            preds = torch.empty((B, J, 2), dtype=torch.float32, device=e.device)
+            maxvals = torch.empty((B, J, 1), dtype=torch.float32, device=e.device)
+
+            def am(lib=lib, logits=logits, preds=preds, maxvals=maxvals, BJ=B * J, h=H4, w=W4):
+                _lib.check(lib.hrnb_decode_argmax(logits.data_ptr(), BJ, h, w, 0, 1, preds.data_ptr(),
+                                                  maxvals.data_ptr(), None, _lib.stream_ptr()))
+            self._op(0, am, "decode_argmax")
+            self.out["preds"], self.out["maxvals"] = preds, maxvals
+
+        # optional feature output (NCHW fp32, as the reference returns it)
+        feat_src = cat if e.variant == "softmax" else stage3_b0
+        feat = torch.empty((B, feat_src.C, feat_src.H, feat_src.W), dtype=torch.float32, device=e.device)
+
+        def tofeat(lib=lib, s=feat_src, feat=feat):
+            _lib.check(lib.hrnb_pf8_to_nchw_f32(s.ptr, s.ps, s.N, s.C, s.H, s.W, feat.data_ptr(), _lib.stream_ptr()))
+        self.feat_step = _Step("op", 0, tofeat, name="features_to_nchw")
+        self.out["features"] = feat
+
+    # ---- execution ----------------------------------------------------------------------------------
+    def _run_steps(self, want_features):
+        main = torch.cuda.current_stream()
+        side = self.engine.side_streams
+        streams = [main] + side
+        for sd_ in side:
+            sd_.wait_stream(main)
+        for st in self.steps:
+            if st.kind == "op":
+                if st.sid == 0:
+                    st.fn()
+                else:
+                    with torch.cuda.stream(streams[st.sid]):
+                        st.fn()
+            else:
+                streams[st.sid].wait_stream(streams[st.other])
+        for sd_ in side:
+            main.wait_stream(sd_)
+        if want_features:
+            self.feat_step.fn()
+
+    def launches(self, want_features):
+        return self.n_launch + (1 if want_features else 0)
+
+    def run(self, want_features=True, use_graph=True):
+        if not use_graph:
+            self._run_steps(want_features)
+            return self.out
+        key = bool(want_features)
+        if self.graph is None:
+            self.graph = {}
+        if key not in self.graph:
+            # warm-up outside capture (sets function attributes, loads modules), then capture
+            self._run_steps(want_features)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_steps(want_features)
+            self.graph[key] = g
+        self.graph[key].replay()
+        return self.out
+
+
+class HRNetEngine:
+    def __init__(self, sd, arch, variant, device):
+        self.arch, self.variant, self.device = arch, variant, torch.device(device)
+        self.layers = {}
+        self.plans = {}
+        self.use_graph = os.environ.get("HRNB_NO_GRAPH", "0") != "1"
+        with torch.cuda.device(self.device):
+            self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+            self._pack(sd)
+
+    def _pack(self, sd):
+        specs = A.layer_specs(self.arch)
+        bn_after = {}
+        for a, b in zip(specs[:-1], specs[1:]):
+            if isinstance(a, A.Conv) and isinstance(b, A.BN):
+                bn_after[a.key] = b.key
+        relu_less = set()   # convs whose BN output feeds a sum (no ReLU): block conv2/conv3, downsample, fuse finals
+        for sp in specs:
+            if not isinstance(sp, A.Conv):
+                continue
+            k = sp.key
+            leaf = k.rsplit(".", 1)[-1]
+            if ".fuse_layers." in k:
+                parts = k.split(".")          # stageS.M.fuse_layers.I.J[.K].0
+                i, j = int(parts[3]), int(parts[4])
+                if j > i or int(parts[5]) == i - j - 1:
+                    relu_less.add(k)
+            elif ".downsample." in k:
+                relu_less.add(k)
+        for sp in specs:
+            if not isinstance(sp, A.Conv):
+                continue
+            k = sp.key
+            w = sd[k + ".weight"].float().contiguous()
+            cb = sd.get(k + ".bias")
+            if k in bn_after:
+                scale, shift = _fold(sd, bn_after[k], cb)
+            else:
+                scale, shift = None, (cb.float() if cb is not None else None)
+            if k == "conv1":
+                self.stem_w = (w.reshape(64, 27) * scale[:, None]).contiguous()
+                self.stem_b = shift.contiguous()
+                continue
+            leaf = k.rsplit(".", 1)[-1]
+            # residual convs (block conv2 / bottleneck conv3) apply ReLU after the add -> flag set
+            relu = k not in relu_less and k != "last_layer.3"
+            self.layers[k] = ConvLayer(w, scale, shift, stride=sp.stride, relu=relu, out_nchw=(k == "last_layer.3"))
+        if self.variant == "softmax":
+            self.temp = sd["trainable_temp"].detach().float().reshape(1).clone()
+        torch.cuda.synchronize(self.device)
+
+    def plan(self, B, H, W):
+        key = (B, H, W)
+        if key not in self.plans:
+            with torch.cuda.device(self.device):
+                self.plans[key] = Plan(self, B, H, W)
+        return self.plans[key]
+
+    def forward(self, x, want_features=True):
+        """x: [B,3,H,W] float32 CUDA NCHW.  Returns the plan's static output tensors (overwritten by the next
+        call with the same shape - clone to keep)."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected input [B, 3, H, W]")
+        B, _, H, W = x.shape
+        p = self.plan(B, H, W)
+        with torch.cuda.device(self.device):
+            p.x.copy_(x, non_blocking=True)
+            return p.run(want_features, self.use_graph)

@@ -1,0 +1,77 @@
+"""PF8 activation buffers: the HBM layout every conv of the path reads and writes.
+
+Logical [N, C, H, W]  ->  C/8 planes x P positions x 8 bf16, P = N*(H+1)*(W+1), position
+p = (n*(H+1) + y+1)*(W+1) + x+1 ; row 0 / column 0 of every image are shared zero padding.
+Each plane carries zero guard bands so the conv's halo loads never leave the allocation.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class PF8:
+    __slots__ = ("buf", "N", "C", "H", "W", "Hp", "Wp", "P", "planes", "ps", "lead", "_ptr")
+
+    def __init__(self, N, C_, H, W, device="cuda", buf=None, plane_offset=0, planes_total=None):
+        assert C_ % 8 == 0, "PF8 needs channels % 8 == 0"
+        self.N, self.C, self.H, self.W = N, C_, H, W
+        self.Hp, self.Wp = H + 1, W + 1
+        self.P = N * self.Hp * self.Wp
+        self.planes = C_ // 8
+        self.lead = _lib.guard_lead(self.Wp)
+        tail = _lib.guard_tail(self.Wp)
+        self.ps = self.lead + (self.P + 7) // 8 * 8 + tail
+        if buf is None:
+            buf = torch.zeros((planes_total or self.planes, self.ps, 8), dtype=torch.bfloat16, device=device)
+        self.buf = buf
+        self._ptr = buf.data_ptr() + (plane_offset * self.ps + self.lead) * 16
+
+    @property
+    def ptr(self):
+        """device address of position 0 of plane 0"""
+        return self._ptr
+
+    def view_planes(self, plane0, nplanes):
+        """A PF8 tensor aliasing planes [plane0, plane0+nplanes) of this buffer (used for the concat)."""
+        v = PF8.__new__(PF8)
+        for s in ("N", "H", "W", "Hp", "Wp", "P", "ps", "lead", "buf"):
+            setattr(v, s, getattr(self, s))
+        v.C = nplanes * 8
+        v.planes = nplanes
+        v._ptr = self._ptr + plane0 * self.ps * 16
+        return v
+
+    # ---- conversions through the CUDA kernels --------------------------------------------------
+    def to_nchw(self):
+        out = torch.empty((self.N, self.C, self.H, self.W), dtype=torch.float32, device=self.buf.device)
+        _lib.check(_lib.lib().hrnb_pf8_to_nchw_f32(self.ptr, self.ps, self.N, self.C, self.H, self.W,
+                                                   out.data_ptr(), _lib.stream_ptr()))
+        return out
+
+    @staticmethod
+    def from_nchw(x):
+        x = x.contiguous().float()
+        N, C_, H, W = x.shape
+        Cp = (C_ + 7) // 8 * 8
+        t = PF8(N, Cp, H, W, device=x.device)
+        _lib.check(_lib.lib().hrnb_nchw_f32_to_pf8(x.data_ptr(), N, C_, H, W, t.ptr, t.ps, _lib.stream_ptr()))
+        return t
+
+    # ---- pure-torch views (tests only; no kernels) ------------------------------------------------
+    def torch_interior(self):
+        """[N, C, H, W] float32 gathered with torch indexing (test helper)."""
+        body = self.buf[:, self.lead:self.lead + self.P, :]  # (planes_total?, P, 8)
+        base_plane = (self._ptr - self.buf.data_ptr()) // 16 // self.ps
+        body = self.buf[base_plane:base_plane + self.planes, self.lead:self.lead + self.P, :]
+        t = body.reshape(self.planes, self.N, self.Hp, self.Wp, 8)[:, :, 1:, 1:, :]
+        return t.permute(1, 0, 4, 2, 3).reshape(self.N, self.C, self.H, self.W).float()
+
+    def padding_is_zero(self):
+        base_plane = (self._ptr - self.buf.data_ptr()) // 16 // self.ps
+        pl = self.buf[base_plane:base_plane + self.planes]
+        body = pl[:, self.lead:self.lead + self.P, :].reshape(self.planes, self.N, self.Hp, self.Wp, 8)
+        ok = bool((body[:, :, 0, :, :] == 0).all()) and bool((body[:, :, :, 0, :] == 0).all())
+        ok = ok and bool((pl[:, :self.lead] == 0).all()) and bool((pl[:, self.lead + self.P:] == 0).all())
+        return ok

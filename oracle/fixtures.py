@@ -1,0 +1,57 @@
+"""Deterministic synthetic inputs / weight perturbations shared by make_golden.py, tests and bench.  TEST INFRA.
+
+Synthetic data follows SURVEY.md §8(d): images ~ N(0,1) (post-Normalize statistics), GT heat maps are
+peak-1 Gaussians sigma=2 at uniform joint coordinates (lib/dataset/target_generators.py:15-53).
+"""
+import numpy as np
+import torch
+
+
+def perturb_state_dict(sd, seed=123):
+    """Make BN statistics / affine parameters non-trivial (default init is mean 0, var 1, gamma 1, beta 0,
+    which would leave BN folding untested).  Operates in place, in key order, with its own generator."""
+    g = torch.Generator().manual_seed(seed)
+    for k in sd:
+        v = sd[k]
+        if k.endswith("running_mean"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+        elif k.endswith("running_var"):
+            v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+        elif ".bn" in k or k.startswith("bn") or _is_bn_affine(k, sd):
+            if k.endswith(".weight"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+            elif k.endswith(".bias"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+    return sd
+
+
+def _is_bn_affine(k, sd):
+    stem = k.rsplit(".", 1)[0]
+    return (stem + ".running_mean") in sd
+
+
+def sharpen_head(sd, factor=50.0):
+    """Second weight set with peaky heat maps (default-init logits are nearly flat)."""
+    sd["last_layer.3.weight"].mul_(factor)
+    return sd
+
+
+def images(B, H=256, W=256, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 3, H, W, generator=g)
+
+
+def targets(B, J=21, h=64, w=64, seed=2, sigma=2.0):
+    """(gt_heatmaps [B,J,h,w], pose2d_gt [B,J,2], visibility [B,J])"""
+    g = torch.Generator().manual_seed(seed)
+    xy = torch.rand(B, J, 2, generator=g) * torch.tensor([w - 1.0, h - 1.0])
+    vis = (torch.rand(B, J, generator=g) < 0.9).float()
+    ys = torch.arange(h, dtype=torch.float32).view(1, 1, h, 1)
+    xs = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w)
+    mu = xy.round()
+    hm = torch.exp(-((xs - mu[..., 0, None, None]) ** 2 + (ys - mu[..., 1, None, None]) ** 2) / (2 * sigma ** 2))
+    return hm, xy, vis
+
+
+def tensor_checksums(sd, keys):
+    return {k: float(sd[k].double().abs().sum()) for k in keys}

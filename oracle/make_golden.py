@@ -1,0 +1,175 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference).
+
+Run in the authoring container only:   python oracle/make_golden.py
+The fixtures pin (a) the oracle restatements and (b) the product's seeded parameter initialisation
+against the reference itself; tests/test_oracle_golden.py re-checks them without needing the reference.
+TEST INFRASTRUCTURE.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, fixtures, hrnet_oracle, decode_oracle, loss_oracle  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CHECK_KEYS = ["conv1.weight", "layer1.0.downsample.0.weight", "layer1.3.conv3.weight", "transition1.1.0.0.weight",
+              "stage2.0.fuse_layers.1.0.0.0.weight", "stage3.2.branches.2.1.conv2.weight",
+              "stage4.2.fuse_layers.3.0.2.0.weight", "stage4.1.fuse_layers.0.3.0.weight", "last_layer.0.weight",
+              "last_layer.0.bias", "last_layer.3.weight", "last_layer.3.bias"]
+
+
+def sub(t, cs=1, ss=2):
+    return t[:, ::cs, ::ss, ::ss].contiguous().numpy()
+
+
+def net_fixture(name, yaml_rel, variant, width_override=None, H=256, W=256, B=1, sharpen=False):
+    pose_hrnet, pose_hrnet_softmax, *_ = ref_shim.modules()
+    cfg = ref_shim.load_cfg(yaml_rel)
+    if width_override:
+        for s, nb in ((2, 2), (3, 3), (4, 4)):
+            cfg.MODEL.EXTRA["STAGE%d" % s]["NUM_CHANNELS"] = [width_override * 2 ** i for i in range(nb)]
+    mod = pose_hrnet_softmax if variant == "softmax" else pose_hrnet
+    torch.manual_seed(0)
+    ref = mod.get_pose_net(cfg, is_train=False).eval()
+    sd0 = ref.state_dict()
+    init_sums = fixtures.tensor_checksums(sd0, CHECK_KEYS)
+    total_abs = float(sum(v.double().abs().sum() for k, v in sd0.items() if v.dtype.is_floating_point))
+    fixtures.perturb_state_dict(sd0)
+    if sharpen:
+        fixtures.sharpen_head(sd0)
+    if variant == "softmax":
+        sd0["trainable_temp"].fill_(1.7)
+    ref.load_state_dict(sd0)
+    x = fixtures.images(B, H, W)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        out = ref(x)
+    arch = hrnet_oracle.Arch.from_cfg(cfg)
+    o = hrnet_oracle.forward(ref.state_dict(), x, arch, variant)
+    rec = {"init_keys": np.array(CHECK_KEYS), "init_sums": np.array([init_sums[k] for k in CHECK_KEYS]),
+           "init_total_abs": np.array(total_abs), "n_keys": np.array(len(sd0)),
+           "key_list_hash": np.array(hash_keys(sd0)), "H": np.array(H), "W": np.array(W), "B": np.array(B)}
+    if variant == "softmax":
+        heat, feat, temp = out
+        assert torch.allclose(o[0], heat, rtol=1e-4, atol=1e-9), (o[0] - heat).abs().max()
+        assert torch.allclose(o[1], feat, rtol=1e-4, atol=1e-5)
+        rec.update(heat=sub(heat), feat=sub(feat, 16, 4), logits=sub(o[3]), temp=np.array(float(temp)),
+                   heat_sum=np.array(float(heat.double().sum())), feat_abs=np.array(float(feat.double().abs().sum())))
+        # decode through the reference's own functions
+        _, _, hd, inf, _ = ref_shim.modules()
+        rec["soft_coords"] = hd.get_final_preds(heat, True).numpy()
+        rec["argmax_h"] = hd.get_final_preds(heat, False).numpy()
+        p, mv = inf.get_max_preds(heat.numpy())
+        rec["max_preds"], rec["maxvals"] = p, mv
+    else:
+        logits, feat = out
+        assert torch.allclose(o[0], logits, rtol=1e-4, atol=1e-6), (o[0] - logits).abs().max()
+        assert torch.allclose(o[1], feat, rtol=1e-4, atol=1e-5)
+        rec.update(logits=sub(logits), feat=sub(feat, 4, 4),
+                   logits_abs=np.array(float(logits.double().abs().sum())),
+                   feat_abs=np.array(float(feat.double().abs().sum())))
+        _, _, hd, inf, _ = ref_shim.modules()
+        p, mv = inf.get_max_preds(logits.numpy())
+        rec["max_preds"], rec["maxvals"] = p, mv
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print(name, "ok; oracle == reference; keys", len(sd0))
+
+
+def hash_keys(sd):
+    import hashlib
+    return hashlib.sha256("\n".join(sorted("%s %s %s" % (k, tuple(v.shape), v.dtype) for k, v in sd.items())).encode()).hexdigest()
+
+
+def decode_fixture():
+    _, _, hd, inf, _ = ref_shim.modules()
+    g = torch.Generator().manual_seed(7)
+    cases = {}
+    for tag, (B, J, h, w) in {"sq": (2, 21, 16, 16), "rect": (2, 21, 24, 16), "j20": (1, 20, 8, 12)}.items():
+        logits = torch.randn(B, J, h, w, generator=g) * 3
+        hm = torch.softmax(logits.reshape(B, J, -1), 2).reshape(B, J, h, w)
+        edge = logits.clone()
+        edge[0, 0] = 0.0                                  # all-zero map
+        edge[0, 1] = -edge[0, 1].abs() - 1.0              # all-negative map
+        edge[0, 2] = 0.0; edge[0, 2, 3, 5] = 2.0; edge[0, 2, 5, 1] = 2.0       # exact tie: first wins
+        for k, (py, px) in enumerate([(0, 0), (1, 1), (h - 2, w - 2), (h - 1, w - 1), (2, 2), (h - 3, w - 3), (2, w - 2)]):
+            edge[0, 3 + k] = torch.rand(h, w, generator=g) * 0.1
+            edge[0, 3 + k, py, px] = 5.0
+        edge[0, 10] = 0.0; edge[0, 10, 4, 4] = 1.0        # flat neighbourhood -> sign(0) = 0
+        center = (torch.rand(B, 2, generator=g) * 200 + 60).numpy().astype(np.float32)
+        scale = (torch.rand(B, 2, generator=g) + 0.5).numpy().astype(np.float32)
+        for nm, t in (("soft", hm), ("edge", edge)):
+            a = t.numpy()
+            cases["%s_%s_in" % (tag, nm)] = a
+            p, mv = inf.get_max_preds(a.copy())
+            cases["%s_%s_maxpreds" % (tag, nm)], cases["%s_%s_maxvals" % (tag, nm)] = p, mv
+            cases["%s_%s_hstride" % (tag, nm)] = hd.get_final_preds(t, False).numpy()
+            cases["%s_%s_expect" % (tag, nm)] = hd.get_final_preds(t, True).numpy()
+            for pp in (0, 1):
+                cfg = ref_shim.to_attr({"TEST": {"POST_PROCESS": bool(pp)}})
+                fp, fmv = inf.get_final_preds(cfg, a.copy(), center, scale)
+                cases["%s_%s_final%d" % (tag, nm, pp)] = fp
+            # oracle checks
+            op, omv = decode_oracle.get_max_preds(a.copy())
+            assert np.array_equal(op, p) and np.array_equal(omv, mv)
+            assert np.array_equal(decode_oracle.argmax_hstride(a), cases["%s_%s_hstride" % (tag, nm)])
+            assert np.allclose(decode_oracle.spatial_expectation2d(a), cases["%s_%s_expect" % (tag, nm)], rtol=1e-4, atol=1e-3), np.abs(decode_oracle.spatial_expectation2d(a) - cases["%s_%s_expect" % (tag, nm)]).max()
+            for pp in (0, 1):
+                ofp, _ = decode_oracle.final_preds(a.copy(), center, scale, bool(pp))
+                assert np.allclose(ofp, cases["%s_%s_final%d" % (tag, nm, pp)], rtol=1e-5, atol=1e-4), tag
+        cases[tag + "_center"], cases[tag + "_scale"] = center, scale
+        cases[tag + "_logits"] = logits.numpy()
+        sm_ref = torch.softmax(logits.reshape(B, J, -1) * 1.7, 2).reshape(B, J, h, w).numpy()
+        assert np.allclose(decode_oracle.spatial_softmax(logits.numpy(), 1.7), sm_ref, rtol=1e-5, atol=1e-8)
+        cases[tag + "_softmax17"] = sm_ref
+    np.savez_compressed(os.path.join(GOLD, "decode.npz"), **cases)
+    print("decode ok; oracle == reference")
+
+
+def loss_fixture():
+    *_, loss = ref_shim.modules()
+    g = torch.Generator().manual_seed(11)
+    rec = {}
+    for tag, (B, J, h, w) in {"a": (2, 21, 16, 16), "b": (3, 20, 8, 12)}.items():
+        pred = torch.rand(B, J, h, w, generator=g, requires_grad=True)
+        gt, xy, vis = fixtures.targets(B, J, h, w)
+        for mode in ("l2", "l1"):
+            l = loss.HeatmapLoss(mode)(pred, gt)
+            (gr,) = torch.autograd.grad(l, pred)
+            rec["%s_hm_%s" % (tag, mode)] = l.detach().numpy()
+            rec["%s_hm_%s_grad" % (tag, mode)] = gr.numpy()
+            assert np.allclose(loss_oracle.heatmap_loss(pred.detach().numpy(), gt.numpy(), mode), l.item(), rtol=1e-5)
+            assert np.allclose(loss_oracle.heatmap_loss_grad(pred.detach().numpy(), gt.numpy(), mode), gr.numpy(), rtol=1e-5, atol=1e-8)
+        pp = (xy + torch.randn(B, J, 2, generator=g) * 2).requires_grad_(True)
+        with torch.no_grad():
+            pp[0, 0] = xy[0, 0]                      # exactly-zero distance -> zero gradient
+        for vtag, v in (("vis", vis), ("novis", None), ("zerovis", torch.zeros_like(vis))):
+            l = loss.JointsMSELoss()(pp, xy, v)
+            (gr,) = torch.autograd.grad(l, pp)
+            rec["%s_p2d_%s" % (tag, vtag)] = l.detach().numpy()
+            rec["%s_p2d_%s_grad" % (tag, vtag)] = gr.numpy()
+            vn = v.numpy() if v is not None else None
+            assert np.allclose(loss_oracle.pose2d_loss(pp.detach().numpy(), xy.numpy(), vn), l.item(), rtol=1e-5)
+            assert np.allclose(loss_oracle.pose2d_loss_grad(pp.detach().numpy(), xy.numpy(), vn), gr.numpy(), rtol=1e-4, atol=1e-7)
+        rec.update({tag + "_pred": pred.detach().numpy(), tag + "_gt": gt.numpy(), tag + "_pp": pp.detach().numpy(),
+                    tag + "_xy": xy.numpy(), tag + "_vis": vis.numpy()})
+    np.savez_compressed(os.path.join(GOLD, "loss.npz"), **rec)
+    print("loss ok; oracle == reference")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    decode_fixture()
+    loss_fixture()
+    Y = "experiments/RHD/RHD_HRNet_w32_softmax_hm-pose2dloss_v1.yaml"
+    YR = "experiments/RHD/RHD_HRNet_w32_max_hmloss_v1.yaml"
+    net_fixture("hrnet_w32_softmax", Y, "softmax")
+    net_fixture("hrnet_w32_softmax_sharp", Y, "softmax", sharpen=True)
+    net_fixture("hrnet_w32_raw", YR, "raw")
+    net_fixture("hrnet_w48_softmax_rect", "experiments/RHD/RHD_HRNet_w48_trainable_softmax_hm-pose2dloss_v1.yaml",
+                "softmax", H=128, W=96, B=2)

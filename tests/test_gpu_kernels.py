@@ -1,0 +1,260 @@
+"""-m gpu: every CUDA kernel behind the C ABI against a PyTorch fp32 reference of the same op (convs,
+elementwise) or the numpy oracle + reference-generated golden vectors (decode, losses)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _conv_case(N, H, W, cin, cout, k, stride, relu, use_res, mb=None, nchw=False, force_gather=False, seed=0):
+    from hrnet_b200.ops import ConvLayer, PF8
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(N, cin, H, W, device="cuda", generator=g)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5
+    scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(cout, device="cuda", generator=g) * 0.1
+    Ho, Wo = H // stride, W // stride
+    res = torch.randn(N, cout, Ho, Wo, device="cuda", generator=g) if use_res else None
+    layer = ConvLayer(w, scale, shift, stride=stride, relu=relu, out_nchw=nchw)
+    layer.force_gather = force_gather
+    xp = PF8.from_nchw(x)
+    rp = PF8.from_nchw(res) if use_res else None
+    if nchw:
+        out = torch.full((N, cout, Ho, Wo), float("nan"), device="cuda")
+        layer(xp, out, rp, mb=mb)
+        got = out
+    else:
+        op = PF8(N, cout, Ho, Wo)
+        op.buf.fill_(7.0)     # poison: padding must be rewritten to zero by the kernel
+        op.buf[:, :op.lead] = 0
+        op.buf[:, op.lead + op.P:] = 0
+        layer(xp, op, rp, mb=mb)
+        got = op.to_nchw()
+        assert op.padding_is_zero(), "conv must keep PF8 padding/guards zero"
+    ref = F.conv2d(_bf16(x), _bf16(w * scale.view(-1, 1, 1, 1)), None, stride=stride, padding=k // 2)
+    ref = ref + shift.view(1, -1, 1, 1)
+    if use_res:
+        ref = ref + _bf16(res)
+    if relu:
+        ref = F.relu(ref)
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item()
+    tol = 2e-2 * max(1.0, ref.abs().max().item()) if not nchw else 2e-3 * max(1.0, ref.abs().max().item())
+    return err, tol
+
+
+CONV_CASES = [
+    # N, H, W, cin, cout, k, stride, relu, res, mb, nchw, force_gather
+    (2, 16, 16, 64, 64, 1, 1, False, False, 1, False, False),      # plain 1x1 GEMM
+    (2, 16, 16, 64, 64, 1, 1, True, True, 2, False, False),
+    (2, 64, 64, 32, 32, 3, 1, True, True, 1, False, False),        # dominant HRNet shape
+    (2, 64, 64, 32, 32, 3, 1, True, True, 2, False, False),
+    (1, 64, 64, 32, 32, 3, 1, True, False, 4, False, False),
+    (3, 32, 32, 64, 64, 3, 1, True, True, None, False, False),
+    (2, 16, 16, 128, 128, 3, 1, True, True, 2, False, False),      # 2 K chunks
+    (4, 8, 8, 256, 256, 3, 1, True, True, 1, False, False),        # 4 K chunks, ring wrap
+    (2, 64, 64, 256, 32, 3, 1, True, False, None, False, False),   # transition1.0
+    (2, 64, 64, 64, 256, 1, 1, True, True, None, False, False),    # bottleneck conv3
+    (2, 32, 32, 32, 64, 3, 2, False, False, 1, False, False),      # stride-2 fuse conv (gather)
+    (2, 64, 64, 64, 64, 3, 2, True, False, 2, False, False),       # stem conv2 (gather)
+    (2, 16, 16, 256, 64, 3, 2, True, False, None, False, False),
+    (2, 16, 16, 64, 64, 1, 1, False, False, 1, False, True),       # 1x1 through the gather producer
+    (2, 16, 16, 32, 32, 3, 1, True, True, 1, False, True),         # 3x3 s1 through the gather producer
+    (2, 32, 32, 480, 480, 1, 1, True, False, None, False, False),  # head conv, 2 N tiles of 240, KC=6
+    (2, 32, 32, 480, 21, 1, 1, False, False, None, True, False),   # final conv, fp32 NCHW output
+    (2, 16, 16, 96, 21, 3, 1, False, False, None, True, False),    # FINAL_CONV_KERNEL = 3
+    (2, 24, 16, 48, 48, 3, 1, True, True, None, False, False),     # W48 widths, non-square
+    (2, 12, 8, 96, 192, 3, 2, False, False, None, False, False),
+    (1, 24, 16, 720, 720, 1, 1, True, False, None, False, False),  # W48 head, 3 N tiles of 240
+    (2, 16, 16, 384, 384, 3, 1, True, True, None, False, False),   # BN=192 x 2
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "N%d_%dx%d_c%d-%d_k%d_s%d_r%d_res%d_mb%s_nchw%d_g%d" % c)
+def test_conv_matches_torch(case):
+    err, tol = _conv_case(*case)
+    assert err <= tol, (err, tol)
+
+
+def test_stem_conv1():
+    from hrnet_b200.ops import PF8, stem_conv1
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(2, 3, 64, 96, device="cuda", generator=g)
+    w = torch.randn(64, 3, 3, 3, device="cuda", generator=g) * 0.2
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    out = PF8(2, 64, 32, 48)
+    stem_conv1(x, w.reshape(64, 27).contiguous(), b, out)
+    ref = F.relu(F.conv2d(x, w, b, stride=2, padding=1))
+    assert (out.to_nchw() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert out.padding_is_zero()
+
+
+def test_layout_roundtrip():
+    from hrnet_b200.ops import PF8
+    x = torch.randn(3, 40, 12, 20, device="cuda")
+    t = PF8.from_nchw(x)
+    assert torch.equal(t.to_nchw(), _bf16(x))
+    assert torch.equal(t.torch_interior(), _bf16(x))
+    assert t.padding_is_zero()
+
+
+def test_fuse_sum_matches_torch():
+    from hrnet_b200.ops import PF8, fuse_sum
+    N, C, H, W = 2, 32, 32, 16
+    a = torch.randn(N, C, H, W, device="cuda")
+    b = torch.randn(N, C, H // 2, W // 2, device="cuda")
+    c = torch.randn(N, C, H // 4, W // 4, device="cuda")
+    d = torch.randn(N, C, H // 8, W // 8, device="cuda")
+    out = PF8(N, C, H, W)
+    fuse_sum([PF8.from_nchw(t) for t in (a, b, c, d)], [0, 1, 2, 3], out, relu=True)
+    ref = _bf16(a)
+    for t, s in ((b, 2), (c, 4), (d, 8)):
+        ref = ref + F.interpolate(_bf16(t), scale_factor=s, mode="nearest")
+    ref = F.relu(ref)
+    assert (out.to_nchw() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert out.padding_is_zero()
+
+
+@pytest.mark.parametrize("align", [True, False])
+def test_bilinear_matches_torch(align):
+    from hrnet_b200.ops import PF8, bilinear_up
+    N, C = 2, 64
+    src = torch.randn(N, C, 8, 6, device="cuda")
+    cat = PF8(N, 32 + C, 32, 24)
+    dst = cat.view_planes(4, C // 8)
+    bilinear_up(PF8.from_nchw(src), dst, align)
+    ref = F.interpolate(_bf16(src), size=(32, 24), mode="bilinear", align_corners=align)
+    got = dst.to_nchw()
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert (cat.view_planes(0, 4).to_nchw() == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# decode / loss: oracle + golden vectors
+# ---------------------------------------------------------------------------------------------------
+def _gold(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_decode_against_golden(golden_dir):
+    from hrnet_b200.core import inference
+    from hrnet_b200.utils import heatmap_decoding
+    from hrnet_b200.config import to_cfg
+    g = _gold(golden_dir, "decode.npz")
+    for tag in ("sq", "rect", "j20"):
+        for nm in ("soft", "edge"):
+            a = g["%s_%s_in" % (tag, nm)]
+            p, mv = inference.get_max_preds(a.copy())
+            assert np.array_equal(p, g["%s_%s_maxpreds" % (tag, nm)])          # bit-exact indices
+            assert np.array_equal(mv, g["%s_%s_maxvals" % (tag, nm)])
+            t = torch.from_numpy(a).cuda()
+            assert np.array_equal(heatmap_decoding.get_final_preds(t, False).cpu().numpy(), g["%s_%s_hstride" % (tag, nm)])
+            e = heatmap_decoding.get_final_preds(t, True).cpu().numpy()
+            assert np.allclose(e, g["%s_%s_expect" % (tag, nm)], rtol=1e-4, atol=1e-3)
+            for pp in (0, 1):
+                cfg = to_cfg({"TEST": {"POST_PROCESS": bool(pp)}})
+                fp, fmv = inference.get_final_preds(cfg, a.copy(), g[tag + "_center"], g[tag + "_scale"])
+                assert np.allclose(fp, g["%s_%s_final%d" % (tag, nm, pp)], rtol=1e-5, atol=1e-4)
+                assert np.array_equal(fmv, g["%s_%s_maxvals" % (tag, nm)])
+
+
+def test_softmax_softargmax_against_golden_and_oracle(golden_dir):
+    from hrnet_b200 import _lib
+    from oracle import decode_oracle
+    g = _gold(golden_dir, "decode.npz")
+    for tag in ("sq", "rect", "j20"):
+        logits = torch.from_numpy(g[tag + "_logits"]).cuda()
+        B, J, h, w = logits.shape
+        heat = torch.empty_like(logits)
+        coords = torch.empty(B, J, 2, device="cuda")
+        temp = torch.tensor([1.7], device="cuda")
+        _lib.check(_lib.lib().hrnb_softmax_softargmax(logits.data_ptr(), temp.data_ptr(), B * J, h, w, heat.data_ptr(),
+                                                      coords.data_ptr(), _lib.stream_ptr()))
+        assert np.allclose(heat.cpu().numpy(), g[tag + "_softmax17"], rtol=1e-4, atol=1e-9)
+        exp = decode_oracle.spatial_expectation2d(g[tag + "_softmax17"])
+        assert np.abs(coords.cpu().numpy() - exp).max() < 1e-3     # << the 0.05 px budget
+
+
+def test_softargmax_backward_matches_autograd():
+    from hrnet_b200.utils.heatmap_decoding import get_final_preds
+    hm = torch.rand(2, 21, 16, 12, device="cuda", requires_grad=True)
+    out = get_final_preds(hm, True)
+    wgt = torch.randn_like(out)
+    (out * wgt).sum().backward()
+    xs = torch.arange(12, device="cuda", dtype=torch.float32).view(1, 1, 1, 12)
+    ys = torch.arange(16, device="cuda", dtype=torch.float32).view(1, 1, 16, 1)
+    ref = wgt[..., 0, None, None] * xs + wgt[..., 1, None, None] * ys
+    assert torch.allclose(hm.grad, ref.expand_as(hm), atol=1e-5)
+
+
+def test_softmax_backward_matches_autograd():
+    from hrnet_b200 import _lib
+    B, J, h, w = 2, 5, 16, 12
+    logits = torch.randn(B, J, h, w, device="cuda", requires_grad=True)
+    temp = torch.tensor(1.3, device="cuda", requires_grad=True)
+    heat_ref = torch.softmax(logits.reshape(B, J, -1) * temp, 2).reshape(B, J, h, w)
+    xs = torch.arange(w, device="cuda", dtype=torch.float32).view(1, 1, 1, w)
+    ys = torch.arange(h, device="cuda", dtype=torch.float32).view(1, 1, h, 1)
+    coords_ref = torch.stack(((heat_ref * xs).sum((2, 3)), (heat_ref * ys).sum((2, 3))), -1)
+    dheat = torch.randn_like(heat_ref)
+    dcoords = torch.randn_like(coords_ref)
+    ((heat_ref * dheat).sum() + (coords_ref * dcoords).sum()).backward()
+    d_logits = torch.empty_like(logits)
+    d_temp = torch.zeros(1, device="cuda")
+    t1 = temp.detach().reshape(1).clone()
+    lg = logits.detach()
+    _lib.check(_lib.lib().hrnb_softmax_softargmax_bwd(lg.data_ptr(), t1.data_ptr(), heat_ref.detach().contiguous().data_ptr(),
+                                                      dheat.data_ptr(), dcoords.data_ptr(), B * J, h, w,
+                                                      d_logits.data_ptr(), d_temp.data_ptr(), _lib.stream_ptr()))
+    assert torch.allclose(d_logits, logits.grad, rtol=1e-3, atol=1e-6)
+    assert torch.allclose(d_temp[0], temp.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_losses_against_golden(golden_dir):
+    from hrnet_b200.core.loss import HeatmapLoss, JointsMSELoss
+    g = _gold(golden_dir, "loss.npz")
+    for tag in ("a", "b"):
+        gt = torch.from_numpy(g[tag + "_gt"]).cuda()
+        for mode in ("l2", "l1"):
+            pred = torch.from_numpy(g[tag + "_pred"]).cuda().requires_grad_(True)
+            l = HeatmapLoss(mode)(pred, gt)
+            l.backward()
+            assert np.allclose(l.item(), g["%s_hm_%s" % (tag, mode)], rtol=1e-5)
+            assert np.allclose(pred.grad.cpu().numpy(), g["%s_hm_%s_grad" % (tag, mode)], rtol=1e-5, atol=1e-8)
+        xy = torch.from_numpy(g[tag + "_xy"]).cuda()
+        vis = torch.from_numpy(g[tag + "_vis"]).cuda()
+        for vtag, v in (("vis", vis), ("novis", None), ("zerovis", torch.zeros_like(vis))):
+            pp = torch.from_numpy(g[tag + "_pp"]).cuda().requires_grad_(True)
+            l = JointsMSELoss()(pp, xy, v)
+            l.backward()
+            assert np.allclose(l.item(), g["%s_p2d_%s" % (tag, vtag)], rtol=1e-5)
+            assert np.allclose(pp.grad.cpu().numpy(), g["%s_p2d_%s_grad" % (tag, vtag)], rtol=1e-4, atol=1e-7)
+
+
+def test_decode_full_size_properties():
+    """BASELINE-size maps (B=64, 21 joints, 64x64): size-independent properties."""
+    from hrnet_b200.core.inference import get_max_preds_cuda
+    from hrnet_b200.utils.heatmap_decoding import get_final_preds
+    B, J, h, w = 64, 21, 64, 64
+    hm = torch.rand(B, J, h, w, device="cuda")
+    yy = torch.randint(0, h, (B, J), device="cuda")
+    xx = torch.randint(0, w, (B, J), device="cuda")
+    hm[torch.arange(B)[:, None], torch.arange(J)[None, :], yy, xx] = 2.0     # planted unique maxima
+    p, mv = get_max_preds_cuda(hm)
+    assert torch.equal(p[..., 0].long(), xx) and torch.equal(p[..., 1].long(), yy)
+    assert (mv == 2.0).all()
+    idx = hm.reshape(B, J, -1).argmax(2)
+    assert torch.equal(get_final_preds(hm, False), torch.stack((idx % h, idx // h), 2).float())
+    # expectation is linear: E[a*p + b*q] = a*E[p] + b*E[q]
+    q = torch.rand_like(hm)
+    lhs = get_final_preds(0.3 * hm + 0.7 * q, True)
+    rhs = 0.3 * get_final_preds(hm, True) + 0.7 * get_final_preds(q, True)
+    assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-1)
