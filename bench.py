@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py - HRNet hand-pose hot path throughput on B200 (contract: see DESIGN.md §6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--width 32|48] [--impl b200|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+
+A step = one pass of the hot path over one batch of synthetic images: pose_hrnet_softmax forward (stem ->
+stages -> head) + spatial softmax + integral soft-argmax decode, weights random-init (reference default init,
+seed 0), images ~ N(0,1).  `value` is images/s with the batch already resident in HBM; `e2e` is the same
+metric through the public nn.Module API with pinned-host input and the decoded joints read back every step.
+`--impl reference` times the CPU restatement of the reference (oracle/, torch-CPU fp32, all host threads) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_IMG = {(32, 256, 256): 22584492032, (48, 256, 256): 46731362304, (48, 384, 288): 78859173888}
+METRIC = "HRNet-W32 256x256 images/sec fwd (forward + softmax soft-argmax decode)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def conv_flops(arch_mod, cfg, H, W):
+    """Algorithmic FLOPs per image by the reference's convention (lib/utils/utils.py:154-159):
+    weight.numel() * H_out * W_out MACs per conv, FLOP = 2 MAC."""
+    a = arch_mod.arch_from_cfg(cfg)
+    res = {}
+    total = 0
+    for sp in arch_mod.layer_specs(a):
+        if not isinstance(sp, arch_mod.Conv):
+            continue
+        res[sp.key] = sp
+    return a, res
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(width, H, W, device):
+    import torch
+    from hrnet_b200.config import make_cfg
+    from hrnet_b200.models import pose_hrnet_softmax
+    cfg = make_cfg(width, image_size=(H, W))
+    torch.manual_seed(0)
+    model = pose_hrnet_softmax.get_pose_net(cfg, is_train=False).eval().to(device)
+    return model, cfg
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_port_throughput(width, H, W, batch, steps, warmup):
+    import numpy as np
+    import torch
+    from oracle import decode_oracle, fixtures, hrnet_oracle
+    from hrnet_b200.config import make_cfg
+    from hrnet_b200.models import pose_hrnet_softmax
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = make_cfg(width, image_size=(H, W))
+    torch.manual_seed(0)
+    sd = pose_hrnet_softmax.get_pose_net(cfg, is_train=False).state_dict()
+    arch = hrnet_oracle.Arch.from_cfg(cfg)
+    x = fixtures.images(batch, H, W)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        heat = hrnet_oracle.forward(sd, x, arch, "softmax")[0]
+        decode_oracle.spatial_expectation2d(heat.numpy())
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return batch * len(times) / total, total / len(times) * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bs = min(args.batch, 8)
+    ips, ms, cores = cpu_port_throughput(args.width, args.height, args.img_width, bs, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, bs, note="CPU restatement of the reference (oracle port, torch-CPU fp32), "
+                                  "bounded sample: batch %d per step" % bs),
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x batch %d of the same workload" % (args.steps, bs)},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, batch, note=None):
+    c = {"workload": "pose_hrnet_softmax HRNet-W%d %dx%d inference forward + spatial softmax + soft-argmax decode, "
+                     "21 joints, batch %d/GPU (BASELINE configs[1] geometry; training backward not built yet)"
+                     % (args.width, args.height, args.img_width, batch),
+         "batch_per_gpu": batch, "global_batch": batch * args.gpus, "parallelism": "dp%d (batch sharded, no collective)" % args.gpus,
+         "l2": "each step streams ~%.1f GB of activations (>> 126 MB L2) and reads a fresh input batch from a pool of 4 "
+               "(4 x %.0f MB > L2); no explicit flush" % (0.061 * batch * (args.height * args.img_width) / 65536.0,
+                                                         batch * 3 * args.height * args.img_width * 4 / 1e6)}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def per_kernel_conv_timing(plan, torch, reps=3):
+    """Eager, single-stream pass with a CUDA-event pair around every launch -> per-launch durations of the
+    dominant kernel (conv_tc_kernel).  Returns (sum_ms_conv, sum_ms_all, n_conv)."""
+    steps = [s for s in plan.steps if s.kind == "op"]
+    best = None
+    for _ in range(reps):
+        evs = []
+        for s in steps:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); s.fn(); b.record()
+            evs.append((s.name, a, b))
+        torch.cuda.synchronize()
+        d = [(n, a.elapsed_time(b)) for n, a, b in evs]
+        tot = sum(t for _, t in d)
+        if best is None or tot < best[0]:
+            best = (tot, d)
+    d = best[1]
+    is_conv = lambda n: n not in ("conv1", "softmax_softargmax", "decode_argmax") and ".fuse." not in n and "bilinear" not in n
+    conv_ms = sum(t for n, t in d if is_conv(n))
+    return conv_ms, best[0], sum(1 for n, _ in d if is_conv(n)), d
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from hrnet_b200 import _lib
+    from oracle import fixtures
+    H, W, B = args.height, args.img_width, args.batch
+    model, cfg = build_model(args.width, H, W, dev)
+    model.return_features = False      # the decode path does not consume the 480-channel feature tensor
+    model.static_outputs = True
+    eng = model.engine()
+    plan = eng.plan(B, H, W)
+    pool = [fixtures.images(B, H, W, seed=1 + rank * 16 + i).to(dev) for i in range(4)]
+    hbm, tf_burst, tf_sust, peak_kind = peaks()
+    flop_img = FLOP_PER_IMG.get((args.width, H, W))
+
+    def step(i):
+        plan.x.copy_(pool[i % 4], non_blocking=True)
+        plan.run(want_features=False, use_graph=True)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- e2e: public nn.Module API, pinned host input, decoded joints read back each step ------------
+    from hrnet_b200.utils.heatmap_decoding import get_final_preds
+    host = [fixtures.images(B, H, W, seed=100 + rank * 16 + i).pin_memory() for i in range(2)]
+    out_host = torch.empty((B, 21, 2), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        xd = host[i % 2].to(dev, non_blocking=True)
+        heat, _, _ = model(xd)
+        coords = get_final_preds(heat, True)
+        out_host.copy_(coords, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the user reads the joints every step
+
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    g1.record()
+    torch.cuda.synchronize()
+    e2e_ms = g0.elapsed_time(g1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0) ------------------------------------------------------
+    conv_ms, all_ms, n_conv, detail = per_kernel_conv_timing(plan, torch)
+    roof = None
+    if flop_img:
+        stem_flops = 2 * 64 * 27 * (H // 2) * (W // 2)       # conv1 runs on CUDA cores, not in conv_tc_kernel
+        conv_flop_step = (flop_img - stem_flops) * B
+        achieved = conv_flop_step / (conv_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (all %d launches of one step)" % n_conv,
+                "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
+                "traffic": None, "peak_source": "%s bf16_tflops (burst; kernels timed one by one with CUDA events, "
+                "eager single-stream pass)" % peak_kind,
+                "avg_launch_us": conv_ms / n_conv * 1e3,
+                "conv_share_of_serial_step": conv_ms / all_ms,
+                "step_frac_of_sustained_peak": (value / world) * flop_img / 1e12 / tf_sust}
+    # ---- CPU baseline (bounded sample) ---------------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, cms, cores = cpu_port_throughput(args.width, H, W, 8, 3, 1)
+        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "oracle port (torch-CPU fp32 + numpy decode), 3 steps x batch 8 after 1 warm-up, %.0f ms/step" % cms}
+    line = {
+        "metric": METRIC if args.width == 32 else METRIC.replace("W32 256x256", "W%d %dx%d" % (args.width, H, W)),
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, B),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
+                "d2h_bytes_per_step": B * 21 * 2 * 4, "ms_per_step": e2e_ms / args.steps,
+                "api": "model(x.cuda()) -> get_final_preds(heat, True) -> .cpu()"},
+        "gpu_launches": args.steps * plan.launches(False),
+        "roofline": roof, "cpu_baseline": cpu,
+        "tensor_frac_of_burst_peak": (value / world) * flop_img / 1e12 / tf_burst if flop_img else None,
+    }
+    print(json.dumps(line))
+    if args.detail:
+        with open(args.detail, "w") as f:
+            json.dump({"per_launch_ms": detail, "conv_ms": conv_ms, "all_ms": all_ms}, f, indent=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--width", type=int, default=32)
+    ap.add_argument("--height", type=int, default=256)
+    ap.add_argument("--img-width", type=int, default=256)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", default=None, help="write per-launch timings (json) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -373,6 +373,9 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
       kSmemHeader + (long long)k->SA * k->a_stage_bytes + (long long)SB * k->b_stage_bytes > limit) {
     k->SA = 1;
   }
+  if (gather && kSmemHeader + (long long)k->SA * k->a_stage_bytes + (long long)SB * k->b_stage_bytes > limit) {
+    k->SA = 3;  // the gather producer runs LAG = 2 stages ahead: 3 is the minimum ring depth
+  }
   const long long smem = kSmemHeader + (long long)k->SA * k->a_stage_bytes + (long long)SB * k->b_stage_bytes;
   if (smem > 227 * 1024) return fail(HRNB_EINVAL, "conv: tile does not fit in shared memory");
   k->SB = SB;

@@ -71,6 +71,7 @@ class PoseHighResolutionNet(nn.Module):
         self._engine = None
         self._engine_key = None
         self.return_features = True   # set False to skip materialising the NCHW fp32 feature output
+        self.static_outputs = False   # True: return the engine's static buffers (overwritten by the next call)
 
     # ---- reference API -----------------------------------------------------------------------------
     def init_weights(self, pretrained=""):
@@ -132,9 +133,12 @@ class PoseHighResolutionNet(nn.Module):
             raise RuntimeError("input must be a CUDA tensor (no CPU fallback)")
         eng = self.engine()
         out = eng.forward(x, want_features=self.return_features)
+        # the engine's outputs are static CUDA-graph buffers; hand out copies unless told otherwise
+        get = (lambda k: out[k]) if self.static_outputs else (lambda k: out[k].clone())
+        feat = get("features") if self.return_features else None
         if self.variant == "softmax":
-            return out["heatmap"], out["features"], self.trainable_temp
-        return out["logits"], out["features"]
+            return get("heatmap"), feat, self.trainable_temp
+        return get("logits"), feat
 
 
 def build(cfg, is_train, variant, **kwargs):

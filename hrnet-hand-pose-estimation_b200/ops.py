@@ -93,6 +93,9 @@ class ConvLayer:
         P = x.N * (H + 1) * (W + 1)
         p.MB = mb or pick_mb(P, self.BN, self.taps, self.n_tiles)
         p.flags = self.flags | (HRNB_CONV_GATHER if self.force_gather else 0)
+        lib = _lib.lib()
+        while p.MB > 1 and lib.hrnb_conv_smem_bytes(C.byref(p)) < 0:
+            p.MB //= 2          # tile does not fit in shared memory at this MB
         return p
 
     def __call__(self, x, out, res=None, mb=None):

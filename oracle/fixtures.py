@@ -11,7 +11,7 @@ def perturb_state_dict(sd, seed=123):
     """Make BN statistics / affine parameters non-trivial (default init is mean 0, var 1, gamma 1, beta 0,
     which would leave BN folding untested).  Operates in place, in key order, with its own generator."""
     g = torch.Generator().manual_seed(seed)
-    for k in sd:
+    for k in sorted(sd):            # sorted: independent of module registration order
         v = sd[k]
         if k.endswith("running_mean"):
             v.copy_(torch.randn(v.shape, generator=g) * 0.1)

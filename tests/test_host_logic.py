@@ -1,0 +1,84 @@
+"""CPU: host-side logic - cfg handling, module tree, error behaviour, state_dict interchange with the reference."""
+import pytest
+import torch
+
+from hrnet_b200 import arch as A
+from hrnet_b200.config import make_cfg, to_cfg
+from hrnet_b200.models import pose_hrnet, pose_hrnet_softmax
+
+
+def test_cfg_dual_access_and_arch():
+    cfg = make_cfg(48)
+    assert cfg.MODEL.EXTRA.STAGE4.NUM_CHANNELS == cfg["MODEL"]["EXTRA"]["STAGE4"]["NUM_CHANNELS"] == [48, 96, 192, 384]
+    a = A.arch_from_cfg(cfg)
+    assert a.head_channels == 720 and a.modules == (1, 4, 3)
+    convs = [s for s in A.layer_specs(a) if isinstance(s, A.Conv)]
+    bns = [s for s in A.layer_specs(a) if isinstance(s, A.BN)]
+    assert (len(convs), len(bns)) == (307, 306)           # SURVEY §6 census
+
+
+def test_branch_mismatch_raises_value_error_like_reference():
+    cfg = make_cfg(32)
+    cfg.MODEL.EXTRA.STAGE3.NUM_BLOCKS = [4, 4]
+    with pytest.raises(ValueError, match="NUM_BRANCHES"):
+        pose_hrnet.get_pose_net(cfg, is_train=False)
+    cfg = make_cfg(32)
+    cfg.MODEL.EXTRA.STAGE2.NUM_CHANNELS = [32]
+    with pytest.raises(ValueError, match="NUM_CHANNELS"):
+        pose_hrnet.get_pose_net(cfg, is_train=False)
+
+
+def test_missing_pretrained_file_raises_value_error():
+    cfg = make_cfg(32, init_weights=True)
+    cfg.MODEL.PRETRAINED = "/nonexistent/model.pth"
+    with pytest.raises(ValueError, match="does not exist"):
+        pose_hrnet.get_pose_net(cfg, is_train=True)
+
+
+def test_module_tree_surface():
+    m = pose_hrnet_softmax.get_pose_net(make_cfg(32, trainable_softmax=True), is_train=False)
+    assert m.trainable_temp.requires_grad and float(m.trainable_temp) == 1.0
+    assert m.transition2[0] is None and m.transition2[2] is not None and len(m.transition3) == 4
+    assert len(m.stage4) == 3 and len(m.stage4[0].branches) == 4 and len(m.layer1) == 4
+    assert m.last_layer[0].bias is not None and m.last_layer[3].out_channels == 21
+    assert sum(p.numel() for p in m.stage4.parameters()) > 0        # wrappers freeze/unfreeze by sub-tree
+    m2 = pose_hrnet.get_pose_net(make_cfg(32, softmax=False), is_train=False)
+    assert "trainable_temp" not in m2.state_dict() and len(m2.state_dict()) == 1839
+
+
+def test_init_weights_statistics():
+    m = pose_hrnet.get_pose_net(make_cfg(32, softmax=False, init_weights=True), is_train=True)
+    w = m.stage3[1].branches[2][0].conv1.weight
+    assert abs(float(w.std()) - 0.001) < 2e-4 and float(m.last_layer[3].bias.abs().sum()) == 0.0
+
+
+def test_no_cpu_fallback():
+    m = pose_hrnet_softmax.get_pose_net(make_cfg(32), is_train=False).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 256, 256))
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 256, 256))
+    from hrnet_b200.core.loss import HeatmapLoss
+    from hrnet_b200.utils.heatmap_decoding import get_final_preds
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        HeatmapLoss()(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        get_final_preds(torch.zeros(1, 2, 4, 4))
+    with pytest.raises(AssertionError):
+        get_final_preds(torch.zeros(2, 4, 4).numpy())
+
+
+def test_state_dict_interchange_with_reference():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref_hrnet, ref_softmax, *_ = ref_shim.modules()
+    cfg = ref_shim.load_cfg()
+    ref = ref_softmax.get_pose_net(cfg, is_train=False)
+    ours = pose_hrnet_softmax.get_pose_net(cfg, is_train=False)          # the reference's own cfg object
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ours.load_state_dict({"module." + k: v for k, v in ref.state_dict().items()}, strict=False)  # DP prefix: no match, no crash
+    for k, v in ref.state_dict().items():
+        assert ours.state_dict()[k].shape == v.shape and ours.state_dict()[k].dtype == v.dtype

@@ -1,0 +1,115 @@
+"""CPU: the oracle restatements against the golden vectors generated from the unmodified reference
+(oracle/make_golden.py), and the product's seeded initialisation / key layout against the same."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_oracle, fixtures, hrnet_oracle, loss_oracle
+from hrnet_b200.config import make_cfg
+from hrnet_b200.models import pose_hrnet, pose_hrnet_softmax
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _key_hash(sd):
+    return hashlib.sha256("\n".join(sorted("%s %s %s" % (k, tuple(v.shape), v.dtype) for k, v in sd.items())).encode()).hexdigest()
+
+
+def _product_model(width, variant, trainable=False):
+    cfg = make_cfg(width, softmax=(variant == "softmax"), trainable_softmax=trainable)
+    mod = pose_hrnet_softmax if variant == "softmax" else pose_hrnet
+    torch.manual_seed(0)
+    return mod.get_pose_net(cfg, is_train=False), cfg
+
+
+NETS = [("hrnet_w32_softmax", 32, "softmax", False), ("hrnet_w32_softmax_sharp", 32, "softmax", True),
+        ("hrnet_w32_raw", 32, "raw", False), ("hrnet_w48_softmax_rect", 48, "softmax", False)]
+
+
+@pytest.mark.parametrize("name,width,variant,sharp", NETS)
+def test_network_oracle_and_seeded_init_match_reference(golden_dir, name, width, variant, sharp):
+    g = _load(golden_dir, name + ".npz")
+    model, cfg = _product_model(width, variant)
+    sd = model.state_dict()
+    # same keys / shapes / dtypes as the reference module tree
+    assert len(sd) == int(g["n_keys"])
+    assert _key_hash(sd) == str(g["key_list_hash"])
+    # same seeded default initialisation (parameter creation order consumes the RNG identically)
+    for k, s in zip(g["init_keys"], g["init_sums"]):
+        assert np.isclose(float(sd[str(k)].double().abs().sum()), float(s), rtol=1e-9), k
+    total = float(sum(v.double().abs().sum() for v in sd.values() if v.dtype.is_floating_point))
+    assert np.isclose(total, float(g["init_total_abs"]), rtol=1e-9)
+    # oracle forward on the perturbed weights == reference forward
+    fixtures.perturb_state_dict(sd)
+    if sharp:
+        fixtures.sharpen_head(sd)
+    if variant == "softmax":
+        sd["trainable_temp"].fill_(1.7)
+    x = fixtures.images(int(g["B"]), int(g["H"]), int(g["W"]))
+    arch = hrnet_oracle.Arch.from_cfg(cfg)
+    out = hrnet_oracle.forward(sd, x, arch, variant)
+    if variant == "softmax":
+        heat, feat, temp, logits = out
+        assert np.allclose(heat[:, :, ::2, ::2].numpy(), g["heat"], rtol=2e-4, atol=1e-9)
+        assert np.allclose(logits[:, :, ::2, ::2].numpy(), g["logits"], rtol=1e-3, atol=1e-5)
+        assert np.allclose(feat[:, ::16, ::4, ::4].numpy(), g["feat"], rtol=1e-3, atol=1e-5)
+        assert np.isclose(float(heat.double().sum()), float(g["heat_sum"]), rtol=1e-6)
+        assert np.allclose(decode_oracle.spatial_expectation2d(heat.numpy()), g["soft_coords"], atol=2e-3)
+        p, mv = decode_oracle.get_max_preds(heat.numpy())
+        # argmax of nearly flat default-init maps may flip under thread-count dependent summation order;
+        # the sharpened set must agree exactly
+        if sharp:
+            assert np.array_equal(p, g["max_preds"])
+        assert np.allclose(mv, g["maxvals"], rtol=1e-3)
+    else:
+        logits, feat = out
+        assert np.allclose(logits[:, :, ::2, ::2].numpy(), g["logits"], rtol=1e-3, atol=1e-5)
+        assert np.allclose(feat[:, ::4, ::4, ::4].numpy(), g["feat"], rtol=1e-3, atol=1e-5)
+
+
+def test_decode_oracle_matches_reference_golden(golden_dir):
+    g = _load(golden_dir, "decode.npz")
+    for tag in ("sq", "rect", "j20"):
+        for nm in ("soft", "edge"):
+            a = g["%s_%s_in" % (tag, nm)]
+            p, mv = decode_oracle.get_max_preds(a.copy())
+            assert np.array_equal(p, g["%s_%s_maxpreds" % (tag, nm)])
+            assert np.array_equal(mv, g["%s_%s_maxvals" % (tag, nm)])
+            assert np.array_equal(decode_oracle.argmax_hstride(a), g["%s_%s_hstride" % (tag, nm)])
+            assert np.allclose(decode_oracle.spatial_expectation2d(a), g["%s_%s_expect" % (tag, nm)], rtol=1e-4, atol=1e-3)
+            for pp in (0, 1):
+                fp, _ = decode_oracle.final_preds(a.copy(), g[tag + "_center"], g[tag + "_scale"], bool(pp))
+                assert np.allclose(fp, g["%s_%s_final%d" % (tag, nm, pp)], rtol=1e-5, atol=1e-4)
+        assert np.allclose(decode_oracle.spatial_softmax(g[tag + "_logits"], 1.7), g[tag + "_softmax17"], rtol=1e-5, atol=1e-8)
+
+
+def test_decode_edge_semantics(golden_dir):
+    """The reference's documented corner cases: all-zero, all-negative, ties, H-stride bug."""
+    g = _load(golden_dir, "decode.npz")
+    a = g["rect_edge_in"]                                  # 24 x 16 maps
+    p, mv = decode_oracle.get_max_preds(a.copy())
+    assert (p[0, 0] == 0).all() and mv[0, 0, 0] == 0       # all-zero: masked to (0, 0)
+    assert (p[0, 1] == 0).all() and mv[0, 1, 0] < 0        # all-negative: coords zeroed, maxval kept
+    assert tuple(p[0, 2]) == (5.0, 3.0)                    # tie: first index in row-major order
+    hs = decode_oracle.argmax_hstride(a)
+    idx = a.reshape(a.shape[0], a.shape[1], -1).argmax(2)
+    assert np.array_equal(hs[..., 0], idx % 24) and np.array_equal(hs[..., 1], idx // 24)   # H used as stride
+
+
+def test_loss_oracle_matches_reference_golden(golden_dir):
+    g = _load(golden_dir, "loss.npz")
+    for tag in ("a", "b"):
+        for mode in ("l2", "l1"):
+            assert np.isclose(loss_oracle.heatmap_loss(g[tag + "_pred"], g[tag + "_gt"], mode), g["%s_hm_%s" % (tag, mode)], rtol=1e-5)
+            assert np.allclose(loss_oracle.heatmap_loss_grad(g[tag + "_pred"], g[tag + "_gt"], mode),
+                               g["%s_hm_%s_grad" % (tag, mode)], rtol=1e-5, atol=1e-8)
+        vis = g[tag + "_vis"]
+        for vtag, v in (("vis", vis), ("novis", None), ("zerovis", np.zeros_like(vis))):
+            assert np.isclose(loss_oracle.pose2d_loss(g[tag + "_pp"], g[tag + "_xy"], v), g["%s_p2d_%s" % (tag, vtag)], rtol=1e-5)
+            assert np.allclose(loss_oracle.pose2d_loss_grad(g[tag + "_pp"], g[tag + "_xy"], v),
+                               g["%s_p2d_%s_grad" % (tag, vtag)], rtol=1e-4, atol=1e-7)
