@@ -28,7 +28,7 @@ def sub(t, cs=1, ss=2):
     return t[:, ::cs, ::ss, ::ss].contiguous().numpy()
 
 
-def net_fixture(name, yaml_rel, variant, width_override=None, H=256, W=256, B=1, sharpen=False):
+def net_fixture(name, yaml_rel, variant, width_override=None, H=256, W=256, B=1, sharpen=False, perturb=True):
     pose_hrnet, pose_hrnet_softmax, *_ = ref_shim.modules()
     cfg = ref_shim.load_cfg(yaml_rel)
     if width_override:
@@ -40,10 +40,11 @@ def net_fixture(name, yaml_rel, variant, width_override=None, H=256, W=256, B=1,
     sd0 = ref.state_dict()
     init_sums = fixtures.tensor_checksums(sd0, CHECK_KEYS)
     total_abs = float(sum(v.double().abs().sum() for k, v in sd0.items() if v.dtype.is_floating_point))
-    fixtures.perturb_state_dict(sd0)
+    if perturb:
+        fixtures.perturb_state_dict(sd0)
     if sharpen:
         fixtures.sharpen_head(sd0)
-    if variant == "softmax":
+    if variant == "softmax" and perturb:
         sd0["trainable_temp"].fill_(1.7)
     ref.load_state_dict(sd0)
     x = fixtures.images(B, H, W)
@@ -168,6 +169,7 @@ if __name__ == "__main__":
     loss_fixture()
     Y = "experiments/RHD/RHD_HRNet_w32_softmax_hm-pose2dloss_v1.yaml"
     YR = "experiments/RHD/RHD_HRNet_w32_max_hmloss_v1.yaml"
+    net_fixture("hrnet_w32_softmax_default", Y, "softmax", perturb=False)   # the spec's "shared random-init weights"
     net_fixture("hrnet_w32_softmax", Y, "softmax")
     net_fixture("hrnet_w32_softmax_sharp", Y, "softmax", sharpen=True)
     net_fixture("hrnet_w32_raw", YR, "raw")

@@ -27,7 +27,8 @@ def _product_model(width, variant, trainable=False):
     return mod.get_pose_net(cfg, is_train=False), cfg
 
 
-NETS = [("hrnet_w32_softmax", 32, "softmax", False), ("hrnet_w32_softmax_sharp", 32, "softmax", True),
+NETS = [("hrnet_w32_softmax_default", 32, "softmax", False), ("hrnet_w32_softmax", 32, "softmax", False),
+        ("hrnet_w32_softmax_sharp", 32, "softmax", True),
         ("hrnet_w32_raw", 32, "raw", False), ("hrnet_w48_softmax_rect", 48, "softmax", False)]
 
 
@@ -45,10 +46,12 @@ def test_network_oracle_and_seeded_init_match_reference(golden_dir, name, width,
     total = float(sum(v.double().abs().sum() for v in sd.values() if v.dtype.is_floating_point))
     assert np.isclose(total, float(g["init_total_abs"]), rtol=1e-9)
     # oracle forward on the perturbed weights == reference forward
-    fixtures.perturb_state_dict(sd)
+    perturb = not name.endswith("_default")
+    if perturb:
+        fixtures.perturb_state_dict(sd)
     if sharp:
         fixtures.sharpen_head(sd)
-    if variant == "softmax":
+    if variant == "softmax" and perturb:
         sd["trainable_temp"].fill_(1.7)
     x = fixtures.images(int(g["B"]), int(g["H"]), int(g["W"]))
     arch = hrnet_oracle.Arch.from_cfg(cfg)
