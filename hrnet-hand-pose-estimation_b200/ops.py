@@ -19,39 +19,62 @@ def pick_kc(cin):
     raise ValueError("cin must be a multiple of 16, got %d" % cin)
 
 
-def pick_bn(cout):
+def bn_candidates(cout):
+    """legal N tiles: multiples of 16 that divide cout (<= 256); a single padded tile when cout % 16 != 0"""
     if cout % 16:
-        return (cout + 15) // 16 * 16 if cout < 256 else None
-    if cout <= 256:
-        return cout
-    for bn in (256, 240, 224, 208, 192, 176, 160, 144, 128):
-        if cout % bn == 0:
-            return bn
-    raise ValueError("no N tile for cout=%d" % cout)
+        if cout > 256:
+            raise ValueError("cout=%d is neither a multiple of 16 nor <= 256" % cout)
+        return [(cout + 15) // 16 * 16]
+    return [bn for bn in range(min(cout, 256), 15, -16) if cout % bn == 0]
 
 
-def pick_mb(P, BN, taps, n_tiles):
-    """M blocks per CTA: amortise the 3x3 halo / weight tiles while keeping >= ~2 waves of CTAs."""
-    env = os.environ.get("HRNB_MB")
-    if env:
-        mb = int(env)
-        while mb * BN > 512:
-            mb //= 2
-        return max(mb, 1)
+def pick_bn(cout):
+    return bn_candidates(cout)[0]
+
+
+def _tile_model(P, W, cin, cout, taps, stride, has_res, bn, mb, kc):
+    """Rough cycle model of one conv launch for tile shape (bn, mb): per-tile cost = max(tensor pipe incl. the
+    shared-memory operand fetch, L2/HBM bytes), times the number of tile rounds on 148 SMs."""
     mblocks = (P + 127) // 128
-    best = 1
-    for mb in (2, 4):
-        if mb * BN > 512:
-            break
-        if (mblocks + mb - 1) // mb * n_tiles >= 2 * NUM_SMS:
-            best = mb
-    return best
+    tiles = (mblocks + mb - 1) // mb * (cout // bn if cout % 16 == 0 else 1)
+    ksteps = taps * cin // 16
+    mma = ksteps * mb * max(bn / 2.0, (4096 + bn * 32) / 128.0)
+    gather = stride == 2
+    halo = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0)
+    a_bytes = (128 * mb * taps if gather else halo) * cin * 2
+    io = a_bytes + bn * taps * cin * 2 + mb * 128 * bn * 2 * (2 if has_res else 1)
+    a_stage = kc * (128 * mb if gather else halo) * 16
+    smem = 3328 + (4 if gather else 2) * a_stage + 4 * kc * bn * 16
+    if smem > 200 * 1024:
+        return None
+    per_sm = 2 if (smem <= 110 * 1024 and mb * bn <= 128) else 1
+    cost = max(mma, io / 40.0)
+    rounds = -(-tiles // (NUM_SMS * per_sm))
+    return rounds * per_sm * cost + 3000.0 / per_sm + 1500.0
+
+
+def pick_tile(P, W, cin, cout, taps, stride, has_res, kc):
+    env_mb, env_bn = os.environ.get("HRNB_MB"), os.environ.get("HRNB_BN")
+    best = None
+    for bn in bn_candidates(cout):
+        if env_bn and bn != int(env_bn) and int(env_bn) in bn_candidates(cout):
+            continue
+        for mb in (4, 2, 1):
+            if mb * bn > 256 or (env_mb and mb != int(env_mb) and int(env_mb) * bn <= 256):
+                continue
+            t = _tile_model(P, W, cin, cout, taps, stride, has_res, bn, mb, kc)
+            if t is not None and (best is None or t < best[0]):
+                best = (t, bn, mb)
+    if best is None:
+        raise ValueError("no tile shape fits shared memory for cin=%d cout=%d" % (cin, cout))
+    return best[1], best[2]
 
 
 class ConvLayer:
     """conv (1x1 / 3x3 pad 1, stride 1 or 2) + folded BN (+ residual) (+ ReLU) on PF8 tensors.
 
     weight: OIHW fp32 (device); scale/shift: per-output-channel fp32 folded BN (None = 1 / 0).
+    Weights are packed lazily per N-tile width (the tile shape depends on the batch/resolution it runs at).
     """
 
     def __init__(self, weight, scale=None, shift=None, stride=1, relu=False, out_nchw=False, kc=None, bn=None):
@@ -61,26 +84,42 @@ class ConvLayer:
         self.cout, self.cin, self.taps, self.stride = cout, cin, kh * kw, stride
         self.relu, self.out_nchw = relu, out_nchw
         self.KC = kc or pick_kc(cin)
-        self.BN = bn or pick_bn(cout)
-        self.n_tiles = (cout + self.BN - 1) // self.BN
-        dev = weight.device
-        self.wpk = torch.empty(self.n_tiles * self.BN * self.taps * cin, dtype=torch.bfloat16, device=dev)
-        self.bias = torch.empty(self.n_tiles * self.BN, dtype=torch.float32, device=dev)
-        w = weight.contiguous()
-        sc = scale.contiguous().float() if scale is not None else None
-        sh = shift.contiguous().float() if shift is not None else None
-        _lib.check(_lib.lib().hrnb_pack_conv_weights(
-            w.data_ptr(), sc.data_ptr() if sc is not None else None, sh.data_ptr() if sh is not None else None,
-            cout, cin, self.taps, self.KC, self.BN, self.wpk.data_ptr(), self.bias.data_ptr(), _lib.stream_ptr()))
+        self.fixed_bn = bn
+        self.w = weight.contiguous()
+        self.sc = scale.contiguous().float() if scale is not None else None
+        self.sh = shift.contiguous().float() if shift is not None else None
+        self.packs = {}
         self.flags = (HRNB_CONV_RELU if relu else 0) | (HRNB_CONV_OUT_NCHW if out_nchw else 0) | \
                      (HRNB_CONV_GATHER if stride == 2 else 0)
         self.force_gather = False
 
-    def params(self, x, out, res=None, mb=None):
+    def pack(self, bn):
+        if bn not in self.packs:
+            n_tiles = (self.cout + bn - 1) // bn
+            dev = self.w.device
+            wpk = torch.empty(n_tiles * bn * self.taps * self.cin, dtype=torch.bfloat16, device=dev)
+            bias = torch.empty(n_tiles * bn, dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().hrnb_pack_conv_weights(
+                self.w.data_ptr(), self.sc.data_ptr() if self.sc is not None else None,
+                self.sh.data_ptr() if self.sh is not None else None, self.cout, self.cin, self.taps, self.KC, bn,
+                wpk.data_ptr(), bias.data_ptr(), _lib.stream_ptr()))
+            self.packs[bn] = (wpk, bias)
+        return self.packs[bn]
+
+    def params(self, x, out, res=None, mb=None, bn=None):
         H, W = x.H // self.stride, x.W // self.stride
+        P = x.N * (H + 1) * (W + 1)
+        stride_eff = 2 if (self.stride == 2 or self.force_gather) else 1
+        tbn, tmb = pick_tile(P, W, self.cin, self.cout, self.taps, stride_eff, res is not None, self.KC)
+        bn = bn or self.fixed_bn or tbn
+        if mb is None:
+            mb = tmb if bn == tbn else 1
+        while mb * bn > 256:
+            mb //= 2
+        wpk, bias = self.pack(bn)
         p = ConvParams()
         p.inp, p.in_ps = x.ptr, x.ps
-        p.wpk, p.bias = self.wpk.data_ptr(), self.bias.data_ptr()
+        p.wpk, p.bias = wpk.data_ptr(), bias.data_ptr()
         p.res, p.res_ps = (res.ptr, res.ps) if res is not None else (None, 0)
         if self.out_nchw:
             p.out, p.out_ps = out.data_ptr(), 0
@@ -89,18 +128,16 @@ class ConvLayer:
             p.out, p.out_ps = out.ptr, out.ps
         p.N, p.H, p.W, p.in_H, p.in_W = x.N, H, W, x.H, x.W
         p.cin, p.cout, p.taps, p.stride = self.cin, self.cout, self.taps, self.stride
-        p.KC, p.BN = self.KC, self.BN
-        P = x.N * (H + 1) * (W + 1)
-        p.MB = mb or pick_mb(P, self.BN, self.taps, self.n_tiles)
+        p.KC, p.BN, p.MB = self.KC, bn, mb
         p.flags = self.flags | (HRNB_CONV_GATHER if self.force_gather else 0)
         lib = _lib.lib()
         while p.MB > 1 and lib.hrnb_conv_smem_bytes(C.byref(p)) < 0:
             p.MB //= 2          # tile does not fit in shared memory at this MB
         return p
 
-    def __call__(self, x, out, res=None, mb=None):
+    def __call__(self, x, out, res=None, mb=None, bn=None):
         assert x.C == self.cin, (x.C, self.cin)
-        p = self.params(x, out, res, mb)
+        p = self.params(x, out, res, mb, bn)
         _lib.check(_lib.lib().hrnb_conv(C.byref(p), _lib.stream_ptr()))
         return out
 

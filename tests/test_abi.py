@@ -42,28 +42,28 @@ def test_conv_geometry_validation_and_smem_budget():
     ok = lib.hrnb_conv_smem_bytes(C.byref(_params()))
     assert 0 < ok <= 227 * 1024
     for bad in (dict(taps=4), dict(stride=2), dict(cin=24), dict(KC=3), dict(BN=24), dict(MB=3),
-                dict(MB=4, BN=256), dict(in_H=32), dict(cout=48)):
+                dict(MB=4, BN=128), dict(in_H=32), dict(cout=48)):
         assert lib.hrnb_conv_smem_bytes(C.byref(_params(**bad))) < 0, bad
         assert lib.hrnb_last_error()
     # every conv shape of HRNet-W32/W48 at batch 64 must fit the shared-memory budget
     from hrnet_b200 import arch as A
     from hrnet_b200.config import make_cfg
-    from hrnet_b200.ops import pick_bn, pick_kc, pick_mb
+    from hrnet_b200.ops import pick_kc, pick_tile
     for width in (32, 48):
         a = A.arch_from_cfg(make_cfg(width))
         for sp in A.layer_specs(a):
             if not isinstance(sp, A.Conv) or sp.key == "conv1":
                 continue
-            for hw in (64, 32, 16, 8):
-                bn = pick_bn(sp.cout)
-                nt = (sp.cout + bn - 1) // bn
-                P = 64 * (hw + 1) * (hw + 1)
-                p = _params(cin=sp.cin, cout=sp.cout, taps=sp.k * sp.k, stride=sp.stride, KC=pick_kc(sp.cin), BN=bn,
-                            MB=pick_mb(P, bn, sp.k * sp.k, nt), H=hw, W=hw, in_H=hw * sp.stride, in_W=hw * sp.stride,
-                            N=64, flags=(4 if sp.stride == 2 else 0) | (2 if sp.cout % 16 else 0))
-                while p.MB > 1 and lib.hrnb_conv_smem_bytes(C.byref(p)) < 0:
-                    p.MB //= 2                      # same back-off as ConvLayer.params
-                assert lib.hrnb_conv_smem_bytes(C.byref(p)) > 0, (sp, hw, lib.hrnb_last_error())
+            for batch in (1, 64):
+                for hw in (64, 32, 16, 8):
+                    P = batch * (hw + 1) * (hw + 1)
+                    kc = pick_kc(sp.cin)
+                    bn, mb = pick_tile(P, hw, sp.cin, sp.cout, sp.k * sp.k, sp.stride, True, kc)
+                    assert mb * bn <= 256
+                    p = _params(cin=sp.cin, cout=sp.cout, taps=sp.k * sp.k, stride=sp.stride, KC=kc, BN=bn, MB=mb,
+                                H=hw, W=hw, in_H=hw * sp.stride, in_W=hw * sp.stride, N=batch,
+                                flags=(4 if sp.stride == 2 else 0) | (2 if sp.cout % 16 else 0))
+                    assert lib.hrnb_conv_smem_bytes(C.byref(p)) > 0, (sp, hw, bn, mb, lib.hrnb_last_error())
 
 
 def test_null_pointers_are_rejected_without_touching_the_gpu():
