@@ -74,8 +74,11 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
   uint8_t* a_ring = smem + kSmemHeader;
   uint8_t* b_ring = a_ring + (size_t)k.SA * k.a_stage_bytes;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue now; this kernel's own
+  // prologue (barrier init, TMEM allocation, bias staging - weights only) overlaps the predecessor's tail.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < k.SA; ++i) {
@@ -103,13 +106,16 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything below reads activations written by earlier kernels of the stream
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int rowsA = GATHER ? 128 * k.MB : k.halo;  // rows per plane in an A stage
   const int acc_cols = k.MB * k.BN;                // fp32 columns of one accumulator stage
 
   if (warp == 0) {
     // =============================== bulk-copy producer ===============================
-    if (lane == 0) {
+    // executed by the whole warp (uniform operands); one elected lane issues the copies
+    {
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       const size_t b_elems = k.b_stage_bytes / 2;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x) {
@@ -120,19 +126,25 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
         for (int c = 0; c < k.nchunks; ++c) {
           if (!GATHER) {
             mbar_wait(&empty_a[a_stage], a_phase ^ 1);
-            mbar_arrive_expect_tx(&full_a[a_stage], k.a_stage_bytes);
-            uint8_t* dst = a_ring + (size_t)a_stage * k.a_stage_bytes;
-            const uint32_t plane_bytes = (uint32_t)k.halo * 16u;
-            for (int j = 0; j < k.KC; ++j) {
-              const __nv_bfloat16* src = k.in + ((long long)(c * k.KC + j) * k.in_ps + pstart) * 8;
-              bulk_g2s(dst + (size_t)j * plane_bytes, src, plane_bytes, &full_a[a_stage]);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full_a[a_stage], k.a_stage_bytes);
+              uint8_t* dst = a_ring + (size_t)a_stage * k.a_stage_bytes;
+              const uint32_t plane_bytes = (uint32_t)k.halo * 16u;
+              for (int j = 0; j < k.KC; ++j) {
+                const __nv_bfloat16* src = k.in + ((long long)(c * k.KC + j) * k.in_ps + pstart) * 8;
+                bulk_g2s(dst + (size_t)j * plane_bytes, src, plane_bytes, &full_a[a_stage]);
+              }
             }
+            __syncwarp();
             if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
           }
           for (int t = 0; t < k.taps; ++t) {
             mbar_wait(&empty_b[b_stage], b_phase ^ 1);
-            mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
-            bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, k.b_stage_bytes, &full_b[b_stage]);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
+              bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, k.b_stage_bytes, &full_b[b_stage]);
+            }
+            __syncwarp();
             wsrc += b_elems;
             if (++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
           }
@@ -141,12 +153,20 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // Executed by the whole warp so that descriptors stay in uniform registers; one elected lane issues.
+    // Per-MMA scalar work is two 32-bit adds: the 64-bit descriptors are (constant hi word, running lo word)
+    // [measured: with descriptors rebuilt from scratch per MMA the issue loop, not the tensor pipe, set the pace].
+    {
       const uint32_t idesc = make_idesc_bf16_m128((uint32_t)k.BN);
-      const uint32_t a_lbo = (uint32_t)rowsA * 16u;
-      const uint32_t b_lbo = (uint32_t)k.BN * 16u;
-      const uint32_t a_ring_addr = smem_u32(a_ring);
-      const uint32_t b_ring_addr = smem_u32(b_ring);
+      const uint32_t a_lbo16 = (uint32_t)rowsA;            // LBO in 16-byte units (rows * 16 B)
+      const uint32_t b_lbo16 = (uint32_t)k.BN;
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
+      const uint32_t a_lo_ring = (smem_u32(a_ring) >> 4) | (a_lbo16 << 16);
+      const uint32_t b_lo_ring = (smem_u32(b_ring) >> 4) | (b_lbo16 << 16);
+      const uint32_t a_stage16 = k.a_stage_bytes >> 4, b_stage16 = k.b_stage_bytes >> 4;
+      const uint32_t a_jstep = 2u * a_lbo16, b_jstep = 2u * b_lbo16;   // K advance of 16 elements = two planes
+      const int ksteps = k.KC / 2;
+      const bool shifted = !GATHER && k.taps == 9;
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
@@ -160,142 +180,160 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
             mbar_wait(&full_a[a_stage], a_phase);
             tc_fence_after_sync();
           }
+          uint32_t shift = 0;   // row shift of the current tap: r * Wp + s
+          int scol = 0;
           for (int t = 0; t < k.taps; ++t) {
             if (GATHER) mbar_wait(&full_a[a_stage], a_phase);
             mbar_wait(&full_b[b_stage], b_phase);
             tc_fence_after_sync();
-            const uint32_t shift = (!GATHER && k.taps == 9) ? (uint32_t)((t / 3) * k.Wp + (t % 3)) : 0u;
-            const uint32_t a_base = a_ring_addr + (uint32_t)a_stage * k.a_stage_bytes + shift * 16u;
-            const uint32_t b_base = b_ring_addr + (uint32_t)b_stage * k.b_stage_bytes;
+            const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + shift;
+            const uint32_t b_lo_tap = b_lo_ring + (uint32_t)b_stage * b_stage16;
+            uint32_t d = d_base;
+            uint32_t a_lo_mb = a_lo_tap;
             for (int mb = 0; mb < k.MB; ++mb) {
+              uint32_t a_lo = a_lo_mb, b_lo = b_lo_tap;
               uint32_t acc = accumulate;
-              for (int j = 0; j < k.KC / 2; ++j) {
-                const uint64_t adesc =
-                    make_kmajor_desc(a_base + (uint32_t)mb * 2048u + (uint32_t)j * 2u * a_lbo, a_lbo, 128u);
-                const uint64_t bdesc = make_kmajor_desc(b_base + (uint32_t)j * 2u * b_lbo, b_lbo, 128u);
-                umma_bf16_ss(d_base + (uint32_t)(mb * k.BN), adesc, bdesc, idesc, acc);
+#pragma unroll 4
+              for (int j = 0; j < ksteps; ++j) {
+                const uint64_t adesc = ((uint64_t)desc_hi << 32) | a_lo;
+                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
+                if (elect_one_sync()) umma_bf16_ss(d, adesc, bdesc, idesc, acc);
                 acc = 1u;
+                a_lo += a_jstep;
+                b_lo += b_jstep;
               }
+              d += (uint32_t)k.BN;
+              a_lo_mb += 128u;   // next 128-row block: 128 rows * 16 B
             }
             accumulate = 1u;
-            umma_commit(&empty_b[b_stage]);
+            __syncwarp();
+            if (elect_one_sync()) {
+              umma_commit(&empty_b[b_stage]);
+              if (GATHER) umma_commit(&empty_a[a_stage]);
+            }
             if (++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
             if (GATHER) {
-              umma_commit(&empty_a[a_stage]);
               if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
+            }
+            if (shifted) {   // next tap: (r, s+1) or (r+1, 0)
+              if (++scol == 3) { scol = 0; shift += (uint32_t)k.Wp - 2u; } else { shift += 1u; }
             }
           }
           if (!GATHER) {
-            umma_commit(&empty_a[a_stage]);
+            if (elect_one_sync()) umma_commit(&empty_a[a_stage]);
             if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
           }
         }
-        umma_commit(&tmem_full[as]);
+        if (elect_one_sync()) umma_commit(&tmem_full[as]);
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
     // =============================== epilogue ===============================
+    // The epilogue is HBM-latency bound (residual reads), so residuals are prefetched PD 16-channel groups ahead
+    // into a register ring; the first PD groups of a tile are requested BEFORE waiting for its accumulator.
+    constexpr int PD = 4;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const bool relu = (k.flags & HRNB_CONV_RELU) != 0;
     const bool nchw = (k.flags & HRNB_CONV_OUT_NCHW) != 0;
     const bool has_res = k.res != nullptr;
     const int groups = k.BN / 16;  // 16-column groups per M block
+    const int E = k.MB * groups;   // groups per tile
     int it = 0;
     for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1, aph = (it >> 1) & 1;
       const int mg = tile / k.n_tiles, ntile = tile - mg * k.n_tiles;
-      // per-M-block row bookkeeping (independent of the accumulator: done before the wait)
-      long long pos[4];
-      int pxs[4], pys[4], ns[4];
+      const long long p0 = (long long)mg * k.MB * 128 + q * 32 + lane;  // row of M block 0
       unsigned validm = 0, realm = 0;
       for (int mb = 0; mb < k.MB; ++mb) {
-        const long long p = ((long long)mg * k.MB + mb) * 128 + q * 32 + lane;
-        pos[mb] = p;
+        const long long p = p0 + mb * 128;
         const int px = (int)(p % k.Wp);
-        const int rowi = (int)(p / k.Wp);
-        pxs[mb] = px;
-        pys[mb] = rowi % k.Hp;
-        ns[mb] = rowi / k.Hp;
+        const int py = (int)((p / k.Wp) % k.Hp);
         if (p < k.P) {
           validm |= 1u << mb;
-          if (px > 0 && pys[mb] > 0) realm |= 1u << mb;
+          if (px > 0 && py > 0) realm |= 1u << mb;
         }
       }
       const int plane0 = ntile * (k.BN / 8);
-      uint4 rcur[2], rnext[2];
-      rcur[0] = rcur[1] = rnext[0] = rnext[1] = make_uint4(0u, 0u, 0u, 0u);
-      if (has_res && (realm & 1u)) {  // residual of (mb 0, group 0): prefetched before the accumulator is ready
-        rcur[0] = ldg_nc_v4(k.res + ((long long)plane0 * k.res_ps + pos[0]) * 8);
-        rcur[1] = ldg_nc_v4(k.res + ((long long)(plane0 + 1) * k.res_ps + pos[0]) * 8);
-      }
+      const __nv_bfloat16* res_base = has_res ? k.res + ((long long)plane0 * k.res_ps + p0) * 8 : nullptr;
+      const long long res_gstep = 2 * k.res_ps * 8;  // two planes per 16-channel group
+      uint4 rb[PD][2];
+      int pmb = 0, pg = 0;  // prefetch cursor
+      auto prefetch = [&](uint4(&dst)[2]) {
+        if (has_res && pmb < k.MB && ((realm >> pmb) & 1u)) {
+          const __nv_bfloat16* src = res_base + (long long)pg * res_gstep + (long long)pmb * 1024;
+          dst[0] = ldg_nc_v4(src);
+          dst[1] = ldg_nc_v4(src + k.res_ps * 8);
+        } else {
+          dst[0] = dst[1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (++pg == groups) { pg = 0; ++pmb; }
+      };
+#pragma unroll
+      for (int u = 0; u < PD; ++u) prefetch(rb[u]);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after_sync();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
-      for (int mb = 0; mb < k.MB; ++mb) {
-        const bool valid = (validm >> mb) & 1u, real = (realm >> mb) & 1u;
-        const long long p = pos[mb];
-        for (int g = 0; g < groups; ++g) {
-          uint32_t v[16];
-          tmem_ld16(t_base + (uint32_t)(mb * k.BN + g * 16), v);
-          // prefetch the next group's residual while the TMEM load is in flight
-          if (has_res) {
-            int nmb = mb, ng = g + 1;
-            if (ng == groups) { ng = 0; ++nmb; }
-            if (nmb < k.MB && ((realm >> nmb) & 1u)) {
-              const long long pl = plane0 + ng * 2;
-              rnext[0] = ldg_nc_v4(k.res + (pl * k.res_ps + pos[nmb]) * 8);
-              rnext[1] = ldg_nc_v4(k.res + ((pl + 1) * k.res_ps + pos[nmb]) * 8);
-            } else {
-              rnext[0] = rnext[1] = make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
-          tmem_ld_wait();
-          const int cb = ntile * k.BN + g * 16;
-          if (nchw) {
-            if (real) {
-              float* o = reinterpret_cast<float*>(k.out);
+      int cmb = 0, cg = 0;  // consume cursor
+      for (int e0 = 0; e0 < E; e0 += PD) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int c = cb + i;
-                if (c < k.cout) {
-                  float x = __uint_as_float(v[i]) + bias_s[cb + i];
-                  if (relu) x = fmaxf(x, 0.f);
-                  o[(((long long)ns[mb] * k.cout + c) * k.H + (pys[mb] - 1)) * k.W + (pxs[mb] - 1)] = x;
+        for (int u = 0; u < PD; ++u) {
+          if (e0 + u < E) {
+            const bool valid = (validm >> cmb) & 1u, real = (realm >> cmb) & 1u;
+            const long long p = p0 + cmb * 128;
+            uint32_t v[16];
+            tmem_ld16(t_base + (uint32_t)(cmb * k.BN + cg * 16), v);
+            tmem_ld_wait();
+            const int cb = ntile * k.BN + cg * 16;
+            if (nchw) {
+              if (real) {
+                float* o = reinterpret_cast<float*>(k.out);
+                const int px = (int)(p % k.Wp);
+                const int rowi = (int)(p / k.Wp);
+                const int py = rowi % k.Hp, n = rowi / k.Hp;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int c = cb + i;
+                  if (c < k.cout) {
+                    float x = __uint_as_float(v[i]) + bias_s[cb + i];
+                    if (relu) x = fmaxf(x, 0.f);
+                    o[(((long long)n * k.cout + c) * k.H + (py - 1)) * k.W + (px - 1)] = x;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[h * 8 + i]) + bias_s[cb + h * 8 + i];
+                const uint4 r = rb[u][h];  // zeros when there is no residual / padding row
+                x[0] += bf16_lo(r.x); x[1] += bf16_hi(r.x);
+                x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
+                x[4] += bf16_lo(r.z); x[5] += bf16_hi(r.z);
+                x[6] += bf16_lo(r.w); x[7] += bf16_hi(r.w);
+                if (relu) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+                }
+                uint4 o;
+                if (real) {
+                  o.x = pack_bf16x2(x[0], x[1]);
+                  o.y = pack_bf16x2(x[2], x[3]);
+                  o.z = pack_bf16x2(x[4], x[5]);
+                  o.w = pack_bf16x2(x[6], x[7]);
+                } else {
+                  o = make_uint4(0u, 0u, 0u, 0u);  // keep the shared zero padding intact
+                }
+                if (valid) {
+                  const long long plane = (long long)(cb / 8 + h);
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(k.out) + (plane * k.out_ps + p) * 8) = o;
                 }
               }
             }
-          } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float x[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[h * 8 + i]) + bias_s[cb + h * 8 + i];
-              const uint4 r = rcur[h];  // zeros when there is no residual / padding row
-              x[0] += bf16_lo(r.x); x[1] += bf16_hi(r.x);
-              x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
-              x[4] += bf16_lo(r.z); x[5] += bf16_hi(r.z);
-              x[6] += bf16_lo(r.w); x[7] += bf16_hi(r.w);
-              if (relu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
-              }
-              uint4 o;
-              if (real) {
-                o.x = pack_bf16x2(x[0], x[1]);
-                o.y = pack_bf16x2(x[2], x[3]);
-                o.z = pack_bf16x2(x[4], x[5]);
-                o.w = pack_bf16x2(x[6], x[7]);
-              } else {
-                o = make_uint4(0u, 0u, 0u, 0u);  // keep the shared zero padding intact
-              }
-              if (valid) {
-                const long long plane = (long long)(cb / 8 + h);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(k.out) + (plane * k.out_ps + p) * 8) = o;
-              }
-            }
+            prefetch(rb[u]);  // refill this ring slot with the group PD ahead
+            if (++cg == groups) { cg = 0; ++cmb; }
           }
-          rcur[0] = rnext[0];
-          rcur[1] = rnext[1];
         }
       }
       // hand the accumulator stage back to the MMA warp
@@ -488,10 +526,18 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (g_debug[1] > 0) per_sm = g_debug[1] == 1 ? 1 : per_sm;   // debug: force one CTA per SM
   int grid = sm_count[dev] * per_sm;
   if (grid > k.num_tiles) grid = k.num_tiles;
-  if (gather)
-    conv_tc_kernel<true><<<grid, 320, (size_t)smem, st>>>(k);
-  else
-    conv_tc_kernel<false><<<grid, 192, (size_t)smem, st>>>(k);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(gather ? 320u : 192u);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_debug[2] ? 0 : 1;   // debug knob 2: disable programmatic dependent launch
+  cudaError_t le = gather ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, k) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, k);
   count_launch();
+  if (le != cudaSuccess) return fail_cuda(le, "conv_tc_kernel launch");
   return check_launch("conv_tc_kernel");
 }

@@ -18,6 +18,20 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// One lane of the (converged) warp returns true.  The MMA / TMA issue loops are executed by the WHOLE warp with
+// warp-uniform operands and only the async instruction itself is predicated on this: that keeps descriptors in
+// uniform registers (UTCHMMA / UBLKCP take UR operands; a loop run by a single lane pays ~5 R2UR per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %1;\n\t"
+      "@%%px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
