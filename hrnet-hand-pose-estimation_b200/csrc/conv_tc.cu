@@ -52,6 +52,7 @@ struct ConvK {
   int tmem_cols;
   int n_tiles, num_tiles; // N tiles, total tiles (m groups x N tiles)
   int nbias;              // n_tiles * BN
+  int dbg;                // debug bitmask (hrnb_debug_set(3, m)): 1 no residual loads, 2 no stores, 4 no TMEM loads
   unsigned a_stage_bytes, b_stage_bytes;
 };
 
@@ -60,8 +61,12 @@ constexpr int kBiasBytes = 3072;  // up to 768 fp32 (whole padded bias vector)
 constexpr int kSmemHeader = kBarBytes + kBiasBytes;
 constexpr int kMaxSA = 4, kMaxSB = 8;
 
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, splitting the column groups
+constexpr int kThreadsFS = 64 + 32 * kEpiWarps;    // producer + MMA + epilogue
+constexpr int kThreadsGather = kThreadsFS + 128;   // + gather producers
+
 template <bool GATHER>
-__global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const ConvK k) {
+__global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ? 1 : 2) conv_tc_kernel(const ConvK k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_a = full_a + kMaxSA;
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1u);
-      mbar_init(&tmem_empty[i], 4u);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], (uint32_t)kEpiWarps);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -99,8 +104,8 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
     tmem_alloc(tmem_ptr_smem, (uint32_t)k.tmem_cols);
     tmem_relinquish();
   }
-  if (warp >= 2 && warp < 6) {
-    for (int i = threadIdx.x - 64; i < k.nbias; i += 128) bias_s[i] = k.bias[i];
+  if (warp >= 2 && warp < 2 + kEpiWarps) {
+    for (int i = threadIdx.x - 64; i < k.nbias; i += 32 * kEpiWarps) bias_s[i] = k.bias[i];
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -126,7 +131,9 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
         for (int c = 0; c < k.nchunks; ++c) {
           if (!GATHER) {
             mbar_wait(&empty_a[a_stage], a_phase ^ 1);
-            if (elect_one_sync()) {
+            if (k.dbg & 8) {
+              if (elect_one_sync()) mbar_arrive(&full_a[a_stage]);
+            } else if (elect_one_sync()) {
               mbar_arrive_expect_tx(&full_a[a_stage], k.a_stage_bytes);
               uint8_t* dst = a_ring + (size_t)a_stage * k.a_stage_bytes;
               const uint32_t plane_bytes = (uint32_t)k.halo * 16u;
@@ -140,7 +147,9 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
           }
           for (int t = 0; t < k.taps; ++t) {
             mbar_wait(&empty_b[b_stage], b_phase ^ 1);
-            if (elect_one_sync()) {
+            if (k.dbg & 16) {
+              if (elect_one_sync()) mbar_arrive(&full_b[b_stage]);
+            } else if (elect_one_sync()) {
               mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
               bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, k.b_stage_bytes, &full_b[b_stage]);
             }
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
               for (int j = 0; j < ksteps; ++j) {
                 const uint64_t adesc = ((uint64_t)desc_hi << 32) | a_lo;
                 const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
-                if (elect_one_sync()) umma_bf16_ss(d, adesc, bdesc, idesc, acc);
+                if (!(k.dbg & 32) && elect_one_sync()) umma_bf16_ss(d, adesc, bdesc, idesc, acc);
                 acc = 1u;
                 a_lo += a_jstep;
                 b_lo += b_jstep;
@@ -228,27 +237,30 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + kEpiWarps) {
     // =============================== epilogue ===============================
     // The epilogue is HBM-latency bound (residual reads), so residuals are prefetched PD 16-channel groups ahead
     // into a register ring; the first PD groups of a tile are requested BEFORE waiting for its accumulator.
     constexpr int PD = 4;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int cs = (warp - 2) >> 2;     // which share of the column groups this warp takes
+    constexpr int CS = kEpiWarps / 4;   // warps per quarter
     const bool relu = (k.flags & HRNB_CONV_RELU) != 0;
     const bool nchw = (k.flags & HRNB_CONV_OUT_NCHW) != 0;
-    const bool has_res = k.res != nullptr;
+    const bool has_res = k.res != nullptr && !(k.dbg & 1);
     const int groups = k.BN / 16;  // 16-column groups per M block
-    const int E = k.MB * groups;   // groups per tile
+    const int E = k.MB * groups;   // groups per tile; this warp takes e = cs, cs + CS, ...
     int it = 0;
     for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1, aph = (it >> 1) & 1;
       const int mg = tile / k.n_tiles, ntile = tile - mg * k.n_tiles;
-      const long long p0 = (long long)mg * k.MB * 128 + q * 32 + lane;  // row of M block 0
+      const int p0 = mg * k.MB * 128 + q * 32 + lane;  // row of M block 0 (P < 2^31)
       unsigned validm = 0, realm = 0;
       for (int mb = 0; mb < k.MB; ++mb) {
-        const long long p = p0 + mb * 128;
-        const int px = (int)(p % k.Wp);
-        const int py = (int)((p / k.Wp) % k.Hp);
+        const int p = p0 + mb * 128;
+        const int rowi = p / k.Wp;
+        const int px = p - rowi * k.Wp;
+        const int py = rowi % k.Hp;
         if (p < k.P) {
           validm |= 1u << mb;
           if (px > 0 && py > 0) realm |= 1u << mb;
@@ -258,7 +270,8 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
       const __nv_bfloat16* res_base = has_res ? k.res + ((long long)plane0 * k.res_ps + p0) * 8 : nullptr;
       const long long res_gstep = 2 * k.res_ps * 8;  // two planes per 16-channel group
       uint4 rb[PD][2];
-      int pmb = 0, pg = 0;  // prefetch cursor
+      int pmb = 0, pg = cs;  // prefetch cursor (mb, group)
+      while (pg >= groups) { pg -= groups; ++pmb; }
       auto prefetch = [&](uint4(&dst)[2]) {
         if (has_res && pmb < k.MB && ((realm >> pmb) & 1u)) {
           const __nv_bfloat16* src = res_base + (long long)pg * res_gstep + (long long)pmb * 1024;
@@ -267,35 +280,49 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
         } else {
           dst[0] = dst[1] = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (++pg == groups) { pg = 0; ++pmb; }
+        pg += CS;
+        while (pg >= groups) { pg -= groups; ++pmb; }
       };
 #pragma unroll
       for (int u = 0; u < PD; ++u) prefetch(rb[u]);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after_sync();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
-      int cmb = 0, cg = 0;  // consume cursor
-      for (int e0 = 0; e0 < E; e0 += PD) {
+      int cmb = 0, cg = cs;  // consume cursor
+      while (cg >= groups) { cg -= groups; ++cmb; }
+      for (int e0 = cs; e0 < ((k.dbg & 64) ? 0 : E); e0 += PD * CS) {
 #pragma unroll
         for (int u = 0; u < PD; ++u) {
-          if (e0 + u < E) {
+          if (e0 + u * CS < E) {
             const bool valid = (validm >> cmb) & 1u, real = (realm >> cmb) & 1u;
-            const long long p = p0 + cmb * 128;
+            const int p = p0 + cmb * 128;
             uint32_t v[16];
-            tmem_ld16(t_base + (uint32_t)(cmb * k.BN + cg * 16), v);
-            tmem_ld_wait();
+            if (!(k.dbg & 4)) {
+              tmem_ld16(t_base + (uint32_t)(cmb * k.BN + cg * 16), v);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0u;
+            }
             const int cb = ntile * k.BN + cg * 16;
+            float bsv[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[cb + 4 * i]);
+              bsv[4 * i] = b4.x; bsv[4 * i + 1] = b4.y; bsv[4 * i + 2] = b4.z; bsv[4 * i + 3] = b4.w;
+            }
             if (nchw) {
               if (real) {
                 float* o = reinterpret_cast<float*>(k.out);
-                const int px = (int)(p % k.Wp);
-                const int rowi = (int)(p / k.Wp);
-                const int py = rowi % k.Hp, n = rowi / k.Hp;
+                const int rowi = p / k.Wp;
+                const int px = p - rowi * k.Wp;
+                const int n = rowi / k.Hp;
+                const int py = rowi - n * k.Hp;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const int c = cb + i;
                   if (c < k.cout) {
-                    float x = __uint_as_float(v[i]) + bias_s[cb + i];
+                    float x = __uint_as_float(v[i]) + bsv[i];
                     if (relu) x = fmaxf(x, 0.f);
                     o[(((long long)n * k.cout + c) * k.H + (py - 1)) * k.W + (px - 1)] = x;
                   }
@@ -306,7 +333,7 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
               for (int h = 0; h < 2; ++h) {
                 float x[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[h * 8 + i]) + bias_s[cb + h * 8 + i];
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[h * 8 + i]) + bsv[h * 8 + i];
                 const uint4 r = rb[u][h];  // zeros when there is no residual / padding row
                 x[0] += bf16_lo(r.x); x[1] += bf16_hi(r.x);
                 x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
@@ -325,14 +352,15 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
                 } else {
                   o = make_uint4(0u, 0u, 0u, 0u);  // keep the shared zero padding intact
                 }
-                if (valid) {
+                if (valid && !(k.dbg & 2)) {
                   const long long plane = (long long)(cb / 8 + h);
                   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(k.out) + (plane * k.out_ps + p) * 8) = o;
                 }
               }
             }
             prefetch(rb[u]);  // refill this ring slot with the group PD ahead
-            if (++cg == groups) { cg = 0; ++cmb; }
+            cg += CS;
+            while (cg >= groups) { cg -= groups; ++cmb; }
           }
         }
       }
@@ -344,7 +372,7 @@ __global__ void __launch_bounds__(GATHER ? 320 : 192, 1) conv_tc_kernel(const Co
   } else {
     // =============================== gather producers (GATHER only) ===============================
     if (GATHER) {
-      const int g = threadIdx.x - 192;  // A row handled by this thread (per M block)
+      const int g = threadIdx.x - kThreadsFS;  // A row handled by this thread (per M block)
       constexpr int LAG = 2;
       int it = 0;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x) {
@@ -459,6 +487,7 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   k->flags = p->flags;
   k->n_tiles = (p->cout + p->BN - 1) / p->BN;
   k->nbias = k->n_tiles * p->BN;
+  k->dbg = g_debug[3];
   if (k->nbias * 4 > kBiasBytes) return fail(HRNB_EINVAL, "conv: more than 768 (padded) output channels");
   const int mblocks = (k->P + 127) / 128;
   k->num_tiles = ((mblocks + p->MB - 1) / p->MB) * k->n_tiles;
@@ -528,7 +557,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (grid > k.num_tiles) grid = k.num_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(gather ? 320u : 192u);
+  cfg.blockDim = dim3(gather ? (unsigned)kThreadsGather : (unsigned)kThreadsFS);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -35,11 +35,16 @@ def main():
     ap.add_argument("--bn", type=int, default=0)
     ap.add_argument("--mb", type=int, default=0)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--dbg", type=int, default=0)
+    ap.add_argument("--pdl-off", action="store_true")
     ap.add_argument("--once", action="store_true", help="one launch per shape (for ncu)")
     args = ap.parse_args()
     import torch
     from hrnet_b200.ops import ConvLayer, PF8
     dev = torch.device("cuda")
+    from hrnet_b200 import _lib as _l
+    _l.lib().hrnb_debug_set(3, args.dbg)
+    _l.lib().hrnb_debug_set(2, 1 if args.pdl_off else 0)
     results = []
     for name in args.shapes.split(","):
         hw, cin, cout, k, stride, relu, use_res = SHAPES[name]
@@ -82,7 +87,7 @@ def main():
         flops = 2.0 * N * hw * hw * cout * cin * k * k
         byts = 2.0 * N * (cin * (hw * stride) ** 2 + cout * hw * hw * (2 if use_res else 1)) if not nchw else \
             N * (2.0 * cin * hw * hw + 4.0 * cout * hw * hw)
-        r = {"shape": name, "bn": prm[0].BN, "mb": prm[0].MB, "us": med * 1e3, "min_us": ts[0] * 1e3,
+        r = {"dbg": args.dbg, "shape": name, "bn": prm[0].BN, "mb": prm[0].MB, "us": med * 1e3, "min_us": ts[0] * 1e3,
              "tflops": flops / med / 1e9, "gbs": byts / med / 1e6}
         results.append(r)
         print(json.dumps(r), flush=True)
