@@ -68,6 +68,7 @@ _SIGS = {
     "hrnb_abi_version": (C.c_int, []),
     "hrnb_launch_count": (_i64, []),
     "hrnb_debug_set": (C.c_int, [C.c_int, C.c_int]),
+    "hrnb_debug_trace": (C.c_int, [_vp]),
 }
 EXPORTS = tuple(_SIGS)
 

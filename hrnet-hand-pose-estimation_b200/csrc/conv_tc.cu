@@ -52,9 +52,17 @@ struct ConvK {
   int tmem_cols;
   int n_tiles, num_tiles; // N tiles, total tiles (m groups x N tiles)
   int nbias;              // n_tiles * BN
+  long long* trace;       // debug: per-role timeline of CTA 0 (hrnb_debug_trace)
   int dbg;                // debug bitmask (hrnb_debug_set(3, m)): 1 no residual loads, 2 no stores, 4 no TMEM loads
   unsigned a_stage_bytes, b_stage_bytes;
 };
+
+// debug timeline: slot = role*64 + 2*tile_iter + {0,1}; written by one lane of CTA 0 only when tracing is on
+#define HRNB_TRACE(role, iter, ev)                                                                   \
+  do {                                                                                                \
+    if (k.trace != nullptr && blockIdx.x == 0 && lane == 0 && (iter) < 16)                            \
+      k.trace[(role) * 64 + 2 * (iter) + (ev)] = clock64();                                           \
+  } while (0)
 
 constexpr int kBarBytes = 256;    // mbarriers + tmem ptr
 constexpr int kBiasBytes = 3072;  // up to 768 fp32 (whole padded bias vector)
@@ -65,7 +73,10 @@ constexpr int kEpiWarps = 8;                       // two warps per TMEM lane qu
 constexpr int kThreadsFS = 64 + 32 * kEpiWarps;    // producer + MMA + epilogue
 constexpr int kThreadsGather = kThreadsFS + 128;   // + gather producers
 
-template <bool GATHER>
+// KSTEPS = KC/2 (K=16 MMA steps per tap and chunk) is a template parameter so that the MMA issue loop is straight-line code:
+// the issuing thread can only run about one MMA ahead of the tensor pipe, so every scalar instruction and branch between two
+// tcgen05.mma is tensor-pipe idle time for the thin (N = 32 / 64) layers [measured: 106 cycles/MMA with a runtime loop].
+template <bool GATHER, bool NCHW, int KSTEPS>
 __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ? 1 : 2) conv_tc_kernel(const ConvK k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
@@ -127,7 +138,9 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
         const int mg = tile / k.n_tiles, ntile = tile - mg * k.n_tiles;
         const long long pstart =
             (long long)mg * k.MB * 128 - (k.taps == 9 ? (k.Wp + 1) : 0);  // first halo position (may be < 0: guard)
-        const __nv_bfloat16* wsrc = k.wpk + (size_t)ntile * k.nchunks * k.taps * b_elems;
+        const __nv_bfloat16* wsrc = k.wpk + (size_t)ntile * k.nchunks * b_elems;
+        const int pit = (tile - (int)blockIdx.x) / (int)gridDim.x;
+        HRNB_TRACE(0, pit, 0);
         for (int c = 0; c < k.nchunks; ++c) {
           if (!GATHER) {
             mbar_wait(&empty_a[a_stage], a_phase ^ 1);
@@ -145,18 +158,18 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
             __syncwarp();
             if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
           }
-          for (int t = 0; t < k.taps; ++t) {
-            mbar_wait(&empty_b[b_stage], b_phase ^ 1);
-            if (k.dbg & 16) {
-              if (elect_one_sync()) mbar_arrive(&full_b[b_stage]);
-            } else if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
-              bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, k.b_stage_bytes, &full_b[b_stage]);
-            }
-            __syncwarp();
-            wsrc += b_elems;
-            if (++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
+          // one weight stage per K chunk: all taps of the chunk in a single bulk copy (one hand-off per chunk)
+          mbar_wait(&empty_b[b_stage], b_phase ^ 1);
+          if (k.dbg & 16) {
+            if (elect_one_sync()) mbar_arrive(&full_b[b_stage]);
+          } else if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
+            bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, k.b_stage_bytes, &full_b[b_stage]);
           }
+          __syncwarp();
+          wsrc += b_elems;
+          if (++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
+          if (c == k.nchunks - 1) HRNB_TRACE(0, pit, 1);
         }
       }
     }
@@ -174,65 +187,73 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       const uint32_t b_lo_ring = (smem_u32(b_ring) >> 4) | (b_lbo16 << 16);
       const uint32_t a_stage16 = k.a_stage_bytes >> 4, b_stage16 = k.b_stage_bytes >> 4;
       const uint32_t a_jstep = 2u * a_lbo16, b_jstep = 2u * b_lbo16;   // K advance of 16 elements = two planes
-      const int ksteps = k.KC / 2;
+      const uint32_t b_tap16 = (uint32_t)(k.KC * k.BN);                 // one tap's weight tile in 16-byte units
       const bool shifted = !GATHER && k.taps == 9;
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1, aph = (it >> 1) & 1;
+        HRNB_TRACE(1, it, 0);
         mbar_wait(&tmem_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after_sync();
+        HRNB_TRACE(2, it, 0);
         const uint32_t d_base = tmem_base + (uint32_t)(as * acc_cols);
         uint32_t accumulate = 0;
         for (int c = 0; c < k.nchunks; ++c) {
-          if (!GATHER) {
-            mbar_wait(&full_a[a_stage], a_phase);
-            tc_fence_after_sync();
-          }
+          // one wait per chunk for the A halo (flat-shift) and for the weights of all taps: every wait / commit
+          // stalls the tensor pipe (~100-140 cycles each, measured), so hand-offs are per chunk, not per tap
+          if (!GATHER) mbar_wait(&full_a[a_stage], a_phase);
+          mbar_wait(&full_b[b_stage], b_phase);
+          tc_fence_after_sync();
+          if (c == 0) HRNB_TRACE(2, it, 1);
           uint32_t shift = 0;   // row shift of the current tap: r * Wp + s
           int scol = 0;
+          uint32_t b_lo_tap = b_lo_ring + (uint32_t)b_stage * b_stage16;
           for (int t = 0; t < k.taps; ++t) {
-            if (GATHER) mbar_wait(&full_a[a_stage], a_phase);
-            mbar_wait(&full_b[b_stage], b_phase);
-            tc_fence_after_sync();
+            if (GATHER) {
+              mbar_wait(&full_a[a_stage], a_phase);
+              tc_fence_after_sync();
+            }
             const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + shift;
-            const uint32_t b_lo_tap = b_lo_ring + (uint32_t)b_stage * b_stage16;
             uint32_t d = d_base;
             uint32_t a_lo_mb = a_lo_tap;
             for (int mb = 0; mb < k.MB; ++mb) {
-              uint32_t a_lo = a_lo_mb, b_lo = b_lo_tap;
-              uint32_t acc = accumulate;
-#pragma unroll 4
-              for (int j = 0; j < ksteps; ++j) {
-                const uint64_t adesc = ((uint64_t)desc_hi << 32) | a_lo;
-                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
-                if (!(k.dbg & 32) && elect_one_sync()) umma_bf16_ss(d, adesc, bdesc, idesc, acc);
-                acc = 1u;
-                a_lo += a_jstep;
-                b_lo += b_jstep;
+              uint64_t adesc = ((uint64_t)desc_hi << 32) | a_lo_mb;
+              uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo_tap;
+              if (elect_one_sync()) {
+                umma_bf16_ss(d, adesc, bdesc, idesc, accumulate);
+#pragma unroll
+                for (int j = 1; j < KSTEPS; ++j) {
+                  adesc += a_jstep;
+                  bdesc += b_jstep;
+                  umma_bf16_ss(d, adesc, bdesc, idesc, 1u);
+                }
               }
               d += (uint32_t)k.BN;
               a_lo_mb += 128u;   // next 128-row block: 128 rows * 16 B
             }
             accumulate = 1u;
-            __syncwarp();
-            if (elect_one_sync()) {
-              umma_commit(&empty_b[b_stage]);
-              if (GATHER) umma_commit(&empty_a[a_stage]);
-            }
-            if (++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
+            b_lo_tap += b_tap16;
             if (GATHER) {
+              __syncwarp();
+              if (elect_one_sync()) umma_commit(&empty_a[a_stage]);
               if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
             }
             if (shifted) {   // next tap: (r, s+1) or (r+1, 0)
               if (++scol == 3) { scol = 0; shift += (uint32_t)k.Wp - 2u; } else { shift += 1u; }
             }
           }
+          __syncwarp();
+          if (elect_one_sync()) {
+            umma_commit(&empty_b[b_stage]);
+            if (!GATHER) umma_commit(&empty_a[a_stage]);
+          }
+          if (++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
           if (!GATHER) {
-            if (elect_one_sync()) umma_commit(&empty_a[a_stage]);
             if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
           }
         }
+        HRNB_TRACE(1, it, 1);
         if (elect_one_sync()) umma_commit(&tmem_full[as]);
         __syncwarp();
       }
@@ -246,7 +267,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     const int cs = (warp - 2) >> 2;     // which share of the column groups this warp takes
     constexpr int CS = kEpiWarps / 4;   // warps per quarter
     const bool relu = (k.flags & HRNB_CONV_RELU) != 0;
-    const bool nchw = (k.flags & HRNB_CONV_OUT_NCHW) != 0;
+    constexpr bool nchw = NCHW;
     const bool has_res = k.res != nullptr && !(k.dbg & 1);
     const int groups = k.BN / 16;  // 16-column groups per M block
     const int E = k.MB * groups;   // groups per tile; this warp takes e = cs, cs + CS, ...
@@ -285,8 +306,10 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       };
 #pragma unroll
       for (int u = 0; u < PD; ++u) prefetch(rb[u]);
+      if (warp == 2) HRNB_TRACE(3, it, 0);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after_sync();
+      if (warp == 2) HRNB_TRACE(3, it, 1);
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
       int cmb = 0, cg = cs;  // consume cursor
       while (cg >= groups) { cg -= groups; ++cmb; }
@@ -311,7 +334,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
               const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[cb + 4 * i]);
               bsv[4 * i] = b4.x; bsv[4 * i + 1] = b4.y; bsv[4 * i + 2] = b4.z; bsv[4 * i + 3] = b4.w;
             }
-            if (nchw) {
+            if constexpr (nchw) {
               if (real) {
                 float* o = reinterpret_cast<float*>(k.out);
                 const int rowi = p / k.Wp;
@@ -339,19 +362,19 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
                 x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
                 x[4] += bf16_lo(r.z); x[5] += bf16_hi(r.z);
                 x[6] += bf16_lo(r.w); x[7] += bf16_hi(r.w);
-                if (relu) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
-                }
                 uint4 o;
-                if (real) {
+                if (relu) {   // ReLU is folded into the bf16x2 conversion
+                  o.x = pack_bf16x2_relu(x[0], x[1]);
+                  o.y = pack_bf16x2_relu(x[2], x[3]);
+                  o.z = pack_bf16x2_relu(x[4], x[5]);
+                  o.w = pack_bf16x2_relu(x[6], x[7]);
+                } else {
                   o.x = pack_bf16x2(x[0], x[1]);
                   o.y = pack_bf16x2(x[2], x[3]);
                   o.z = pack_bf16x2(x[4], x[5]);
                   o.w = pack_bf16x2(x[6], x[7]);
-                } else {
-                  o = make_uint4(0u, 0u, 0u, 0u);  // keep the shared zero padding intact
                 }
+                if (!real) o = make_uint4(0u, 0u, 0u, 0u);  // keep the shared zero padding intact
                 if (valid && !(k.dbg & 2)) {
                   const long long plane = (long long)(cb / 8 + h);
                   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(k.out) + (plane * k.out_ps + p) * 8) = o;
@@ -364,6 +387,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           }
         }
       }
+      if (warp == 2) HRNB_TRACE(4, it, 0);
       // hand the accumulator stage back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
@@ -432,6 +456,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
 }
 
 int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+long long* g_trace = nullptr;
 
 static int next_pow2_cols(int c) {
   int r = 32;
@@ -488,11 +513,12 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   k->n_tiles = (p->cout + p->BN - 1) / p->BN;
   k->nbias = k->n_tiles * p->BN;
   k->dbg = g_debug[3];
+  k->trace = g_trace;
   if (k->nbias * 4 > kBiasBytes) return fail(HRNB_EINVAL, "conv: more than 768 (padded) output channels");
   const int mblocks = (k->P + 127) / 128;
   k->num_tiles = ((mblocks + p->MB - 1) / p->MB) * k->n_tiles;
   k->tmem_cols = next_pow2_cols(2 * p->MB * p->BN);
-  k->b_stage_bytes = (unsigned)(p->KC * p->BN * 16);
+  k->b_stage_bytes = (unsigned)(p->taps * p->KC * p->BN * 16);   // all taps of one K chunk
   if (gather) {
     k->halo = 128 * p->MB;
     k->a_stage_bytes = (unsigned)(p->KC * 128 * p->MB * 16);
@@ -503,12 +529,12 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }
   const long long limit = 200 * 1024;
-  int SB = 6;
+  int SB = 3;
   auto total = [&](int sa, int sb) { return kSmemHeader + (long long)sa * k->a_stage_bytes + (long long)sb * k->b_stage_bytes; };
   while (SB > 2 && total(k->SA, SB) > limit) --SB;
   if (gather && total(k->SA, SB) > limit) k->SA = 3;  // the gather producer runs LAG = 2 stages ahead: minimum ring depth 3
   const long long smem = total(k->SA, SB);
-  if (smem > 227 * 1024) return fail(HRNB_EINVAL, "conv: tile does not fit in shared memory");
+  if (smem > 227 * 1024) return fail(HRNB_EINVAL, "conv: tile does not fit in shared memory (reduce KC, BN or MB)");
   k->SB = SB;
   return smem;
 }
@@ -523,6 +549,11 @@ extern "C" int hrnb_debug_set(int key, int value) {
   return HRNB_OK;
 }
 
+extern "C" int hrnb_debug_trace(void* dev_buf_5x64_i64) {
+  g_trace = (long long*)dev_buf_5x64_i64;
+  return HRNB_OK;
+}
+
 extern "C" int64_t hrnb_conv_smem_bytes(const hrnb_conv_params* p) {
   ConvK k;
   return derive(p, &k);
@@ -534,16 +565,30 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (smem < 0) return (int)smem;
   const bool gather = (p->flags & HRNB_CONV_GATHER) != 0;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[64][2] = {};
+  static bool attr_set[64][21] = {};
   static int sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
-  if (!attr_set[dev][gather ? 1 : 0]) {
-    cudaError_t e = gather ? cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                           : cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const bool nchw_out = (p->flags & HRNB_CONV_OUT_NCHW) != 0;
+  if (gather && nchw_out) return fail(HRNB_EINVAL, "conv: NCHW output is not available for the gather variant");
+  const int ks = p->KC / 2;
+  int ksi = -1;
+  const void* fn = nullptr;
+#define HRNB_PICK(KS, IDX)                                                                                   \
+  if (ks == KS) {                                                                                            \
+    ksi = IDX;                                                                                               \
+    fn = gather ? (const void*)conv_tc_kernel<true, false, KS>                                               \
+                : (nchw_out ? (const void*)conv_tc_kernel<false, true, KS> : (const void*)conv_tc_kernel<false, false, KS>); \
+  }
+  HRNB_PICK(1, 0) HRNB_PICK(2, 1) HRNB_PICK(3, 2) HRNB_PICK(4, 3) HRNB_PICK(6, 4) HRNB_PICK(8, 5) HRNB_PICK(16, 6)
+#undef HRNB_PICK
+  if (!fn) return fail(HRNB_EINVAL, "conv: KC must be one of 2, 4, 6, 8, 12, 16, 32");
+  const int variant = ksi * 3 + (gather ? 2 : (nchw_out ? 1 : 0));
+  if (!attr_set[dev][variant]) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "conv: cudaFuncSetAttribute");
-    attr_set[dev][gather ? 1 : 0] = true;
+    attr_set[dev][variant] = true;
   }
   if (sm_count[dev] == 0) {
     int n = 0;
@@ -565,7 +610,8 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_debug[2] ? 0 : 1;   // debug knob 2: disable programmatic dependent launch
-  cudaError_t le = gather ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, k) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, k);
+  void* kargs[1] = {(void*)&k};
+  cudaError_t le = cudaLaunchKernelExC(&cfg, fn, kargs);
   count_launch();
   if (le != cudaSuccess) return fail_cuda(le, "conv_tc_kernel launch");
   return check_launch("conv_tc_kernel");

@@ -11,12 +11,16 @@ from .pf8 import PF8
 NUM_SMS = 148
 
 
-def pick_kc(cin):
+def kc_candidates(cin):
+    """even numbers of 8-channel planes per K chunk that divide cin/8, largest first"""
     planes = cin // 8
-    for kc in (8, 6, 4, 2):
-        if planes % kc == 0:
-            return kc
-    raise ValueError("cin must be a multiple of 16, got %d" % cin)
+    if cin % 16:
+        raise ValueError("cin must be a multiple of 16, got %d" % cin)
+    return [kc for kc in (32, 16, 12, 8, 6, 4, 2) if kc <= planes and planes % kc == 0]
+
+
+def pick_kc(cin):
+    return kc_candidates(cin)[0]
 
 
 def bn_candidates(cout):
@@ -32,42 +36,55 @@ def pick_bn(cout):
     return bn_candidates(cout)[0]
 
 
+def _smem_bytes(W, taps, gather, bn, mb, kc):
+    halo = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0)
+    a_stage = kc * (128 * mb if gather else halo) * 16
+    b_stage = taps * kc * bn * 16
+    return 3328 + (3 if gather else 2) * a_stage + 2 * b_stage
+
+
 def _tile_model(P, W, cin, cout, taps, stride, has_res, bn, mb, kc):
-    """Rough cycle model of one conv launch for tile shape (bn, mb): per-tile cost = max(tensor pipe incl. the
-    shared-memory operand fetch, L2/HBM bytes), times the number of tile rounds on 148 SMs."""
+    """Rough cycle model of one conv launch for tile shape (bn, mb, kc): per-tile cost = max(tensor pipe incl. the
+    shared-memory operand fetch and the per-chunk hand-off stalls, HBM/L2 bytes), times the tile rounds on 148 SMs."""
     mblocks = (P + 127) // 128
     tiles = (mblocks + mb - 1) // mb * (cout // bn if cout % 16 == 0 else 1)
-    ksteps = taps * cin // 16
-    mma = ksteps * mb * max(bn / 2.0, (4096 + bn * 32) / 128.0)
     gather = stride == 2
-    halo = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0)
-    a_bytes = (128 * mb * taps if gather else halo) * cin * 2
-    io = a_bytes + bn * taps * cin * 2 + mb * 128 * bn * 2 * (2 if has_res else 1)
-    a_stage = kc * (128 * mb if gather else halo) * 16
-    smem = 3328 + (4 if gather else 2) * a_stage + 4 * kc * bn * 16
+    smem = _smem_bytes(W, taps, gather, bn, mb, kc)
     if smem > 200 * 1024:
         return None
+    ksteps = taps * cin // 16
+    nchunks = (cin // 8) // kc
+    handoffs = nchunks * (taps if gather else 1)
+    mma = ksteps * mb * max(bn / 2.0, (4096 + bn * 32) / 128.0) + 300.0 * handoffs + 400.0
+    halo = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0)
+    a_bytes = (128 * mb * taps if gather else halo) * cin * 2
+    io = a_bytes + bn * taps * cin * 2 * 0.5 + mb * 128 * bn * 2 * (2 if has_res else 1)
     per_sm = 2 if (smem <= 110 * 1024 and mb * bn <= 128) else 1
-    cost = max(mma, io / 40.0)
+    cost = max(mma, io / 23.0)
     rounds = -(-tiles // (NUM_SMS * per_sm))
     return rounds * per_sm * cost + 3000.0 / per_sm + 1500.0
 
 
-def pick_tile(P, W, cin, cout, taps, stride, has_res, kc):
-    env_mb, env_bn = os.environ.get("HRNB_MB"), os.environ.get("HRNB_BN")
+def pick_tile(P, W, cin, cout, taps, stride, has_res, kc=None):
+    """-> (BN, MB, KC) minimising the launch-time model"""
+    env_mb, env_bn, env_kc = os.environ.get("HRNB_MB"), os.environ.get("HRNB_BN"), os.environ.get("HRNB_KC")
     best = None
+    kcs = [kc] if kc else kc_candidates(cin)
+    if env_kc and int(env_kc) in kcs:
+        kcs = [int(env_kc)]
     for bn in bn_candidates(cout):
         if env_bn and bn != int(env_bn) and int(env_bn) in bn_candidates(cout):
             continue
         for mb in (4, 2, 1):
             if mb * bn > 256 or (env_mb and mb != int(env_mb) and int(env_mb) * bn <= 256):
                 continue
-            t = _tile_model(P, W, cin, cout, taps, stride, has_res, bn, mb, kc)
-            if t is not None and (best is None or t < best[0]):
-                best = (t, bn, mb)
+            for kcc in kcs:
+                t = _tile_model(P, W, cin, cout, taps, stride, has_res, bn, mb, kcc)
+                if t is not None and (best is None or t < best[0]):
+                    best = (t, bn, mb, kcc)
     if best is None:
         raise ValueError("no tile shape fits shared memory for cin=%d cout=%d" % (cin, cout))
-    return best[1], best[2]
+    return best[1], best[2], best[3]
 
 
 class ConvLayer:
@@ -83,7 +100,7 @@ class ConvLayer:
         assert kh == kw and kh in (1, 3)
         self.cout, self.cin, self.taps, self.stride = cout, cin, kh * kw, stride
         self.relu, self.out_nchw = relu, out_nchw
-        self.KC = kc or pick_kc(cin)
+        self.fixed_kc = kc
         self.fixed_bn = bn
         self.w = weight.contiguous()
         self.sc = scale.contiguous().float() if scale is not None else None
@@ -93,30 +110,37 @@ class ConvLayer:
                      (HRNB_CONV_GATHER if stride == 2 else 0)
         self.force_gather = False
 
-    def pack(self, bn):
-        if bn not in self.packs:
+    def pack(self, bn, kc):
+        if (bn, kc) not in self.packs:
             n_tiles = (self.cout + bn - 1) // bn
             dev = self.w.device
             wpk = torch.empty(n_tiles * bn * self.taps * self.cin, dtype=torch.bfloat16, device=dev)
             bias = torch.empty(n_tiles * bn, dtype=torch.float32, device=dev)
             _lib.check(_lib.lib().hrnb_pack_conv_weights(
                 self.w.data_ptr(), self.sc.data_ptr() if self.sc is not None else None,
-                self.sh.data_ptr() if self.sh is not None else None, self.cout, self.cin, self.taps, self.KC, bn,
+                self.sh.data_ptr() if self.sh is not None else None, self.cout, self.cin, self.taps, kc, bn,
                 wpk.data_ptr(), bias.data_ptr(), _lib.stream_ptr()))
-            self.packs[bn] = (wpk, bias)
-        return self.packs[bn]
+            self.packs[(bn, kc)] = (wpk, bias)
+        return self.packs[(bn, kc)]
 
-    def params(self, x, out, res=None, mb=None, bn=None):
+    def params(self, x, out, res=None, mb=None, bn=None, kc=None):
         H, W = x.H // self.stride, x.W // self.stride
         P = x.N * (H + 1) * (W + 1)
         stride_eff = 2 if (self.stride == 2 or self.force_gather) else 1
-        tbn, tmb = pick_tile(P, W, self.cin, self.cout, self.taps, stride_eff, res is not None, self.KC)
+        tbn, tmb, tkc = pick_tile(P, W, self.cin, self.cout, self.taps, stride_eff, res is not None, kc or self.fixed_kc)
         bn = bn or self.fixed_bn or tbn
         if mb is None:
             mb = tmb if bn == tbn else 1
         while mb * bn > 256:
             mb //= 2
-        wpk, bias = self.pack(bn)
+        kc = tkc
+        lib = _lib.lib()
+        if bn != tbn or mb != tmb:      # forced shape: take the largest K chunk that fits
+            for cand in ([kc] if (kc and self.fixed_kc) else kc_candidates(self.cin)):
+                if _smem_bytes(W, self.taps, stride_eff == 2, bn, mb, cand) <= 200 * 1024:
+                    kc = cand
+                    break
+        wpk, bias = self.pack(bn, kc)
         p = ConvParams()
         p.inp, p.in_ps = x.ptr, x.ps
         p.wpk, p.bias = wpk.data_ptr(), bias.data_ptr()
@@ -128,9 +152,8 @@ class ConvLayer:
             p.out, p.out_ps = out.ptr, out.ps
         p.N, p.H, p.W, p.in_H, p.in_W = x.N, H, W, x.H, x.W
         p.cin, p.cout, p.taps, p.stride = self.cin, self.cout, self.taps, self.stride
-        p.KC, p.BN, p.MB = self.KC, bn, mb
+        p.KC, p.BN, p.MB = kc, bn, mb
         p.flags = self.flags | (HRNB_CONV_GATHER if self.force_gather else 0)
-        lib = _lib.lib()
         while p.MB > 1 and lib.hrnb_conv_smem_bytes(C.byref(p)) < 0:
             p.MB //= 2          # tile does not fit in shared memory at this MB
         return p

@@ -163,6 +163,8 @@ int hrnb_abi_version(void);
 int64_t hrnb_launch_count(void);
 /* debug knobs (key 0: exchange the LBO/SBO roles of the UMMA descriptors); not part of the product API */
 int hrnb_debug_set(int key, int value);
+/* debug: device buffer of 5*64 int64 receiving clock64 timestamps of CTA 0's roles (NULL = off) */
+int hrnb_debug_trace(void* dev_buf_5x64_i64);
 
 #ifdef __cplusplus
 }

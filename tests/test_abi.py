@@ -48,7 +48,7 @@ def test_conv_geometry_validation_and_smem_budget():
     # every conv shape of HRNet-W32/W48 at batch 64 must fit the shared-memory budget
     from hrnet_b200 import arch as A
     from hrnet_b200.config import make_cfg
-    from hrnet_b200.ops import pick_kc, pick_tile
+    from hrnet_b200.ops import pick_tile
     for width in (32, 48):
         a = A.arch_from_cfg(make_cfg(width))
         for sp in A.layer_specs(a):
@@ -57,8 +57,7 @@ def test_conv_geometry_validation_and_smem_budget():
             for batch in (1, 64):
                 for hw in (64, 32, 16, 8):
                     P = batch * (hw + 1) * (hw + 1)
-                    kc = pick_kc(sp.cin)
-                    bn, mb = pick_tile(P, hw, sp.cin, sp.cout, sp.k * sp.k, sp.stride, True, kc)
+                    bn, mb, kc = pick_tile(P, hw, sp.cin, sp.cout, sp.k * sp.k, sp.stride, True)
                     assert mb * bn <= 256
                     p = _params(cin=sp.cin, cout=sp.cout, taps=sp.k * sp.k, stride=sp.stride, KC=kc, BN=bn, MB=mb,
                                 H=hw, W=hw, in_H=hw * sp.stride, in_W=hw * sp.stride, N=batch,

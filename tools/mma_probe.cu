@@ -9,7 +9,7 @@ using namespace hrnb;
 
 // MODE 0: no swizzle, plane layout (LBO = 4096, SBO = 128); MODE 1: SW128 (SBO = 1024); MODE 2: no swizzle, start + 16 B
 template <int MODE, int NACC>
-__global__ void __launch_bounds__(128, 1) probe(int N, int reps, long long* out) {
+__global__ void __launch_bounds__(128, 1) probe(int N, int reps, long long* out, unsigned a_lbo_bytes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_ptr;
@@ -27,9 +27,9 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int reps, long long* out)
     const uint32_t layout_hi = (MODE == 1 ? (2u << 29) : 0u) | (1u << 14);
     const uint32_t a_hi = layout_hi | ((MODE == 1 ? 1024u : 128u) >> 4);
     const uint32_t b_hi = a_hi;
-    const uint32_t a_lo = (a0 >> 4) | ((MODE == 1 ? 1u : (4096u >> 4)) << 16);
+    const uint32_t a_lo = (a0 >> 4) | ((MODE == 1 ? 1u : (a_lbo_bytes >> 4)) << 16);
     const uint32_t b_lo = (b0 >> 4) | ((MODE == 1 ? 1u : (((uint32_t)N * 16u) >> 4)) << 16);
-    const uint32_t a_step = MODE == 1 ? 2u : (2u * 4096u >> 4), b_step = MODE == 1 ? 2u : ((2u * (uint32_t)N * 16u) >> 4);
+    const uint32_t a_step = MODE == 1 ? 2u : (2u * a_lbo_bytes >> 4), b_step = MODE == 1 ? 2u : ((2u * (uint32_t)N * 16u) >> 4);
     uint32_t phase = 0;
     for (int rep = 0; rep < 3; ++rep) {
       long long t0 = clock64();
@@ -55,16 +55,16 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int reps, long long* out)
 }
 
 template <int MODE, int NACC>
-void run(const char* name, long long* d) {
+void run(const char* name, long long* d, unsigned lbo = 4096) {
   cudaFuncSetAttribute(probe<MODE, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int reps = 4000;
   for (int N : {32, 64, 128, 256}) {
     if (NACC * N > 512) continue;
-    probe<MODE, NACC><<<148, 128, 160 * 1024>>>(N, reps, d);
+    probe<MODE, NACC><<<148, 128, 160 * 1024>>>(N, reps, d, lbo);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[3] = {0, 0, 0};
     cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
-    printf("%-28s nacc=%d N=%3d  cycles/MMA %.1f  ideal %.0f  %s\n", name, NACC, N, (double)h[2] / reps, N / 2.0,
+    printf("%-28s lbo=%5u nacc=%d N=%3d  cycles/MMA %.1f  ideal %.0f  %s\n", name, lbo, NACC, N, (double)h[2] / reps, N / 2.0,
            e == cudaSuccess ? "" : cudaGetErrorString(e));
   }
 }
@@ -72,8 +72,6 @@ void run(const char* name, long long* d) {
 int main() {
   long long* d;
   cudaMalloc(&d, 64);
-  run<0, 1>("noswz plane", d); run<0, 2>("noswz plane", d); run<0, 4>("noswz plane", d); run<0, 8>("noswz plane", d);
-  run<1, 1>("SW128", d); run<1, 2>("SW128", d); run<1, 4>("SW128", d); run<1, 8>("SW128", d);
-  run<2, 1>("noswz plane +16B", d); run<2, 4>("noswz plane +16B", d);
+  for (unsigned lbo : {4096u, 9280u, 9344u, 10304u, 2048u, 4160u, 2368u}) { run<0, 4>("noswz plane", d, lbo); run<2, 4>("noswz plane +16B", d, lbo); }
   return 0;
 }

@@ -1,0 +1,22 @@
+"""Run the whole plan eagerly (no CUDA graph, single pass after a warm-up) - the command profiled by ncu."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["HRNB_NO_GRAPH"] = "1"
+import torch  # noqa: E402
+from bench import build_model  # noqa: E402
+from oracle import fixtures  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+passes = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+dev = torch.device("cuda", 0)
+model, cfg = build_model(32, 256, 256, dev)
+model.return_features = False
+model.static_outputs = True
+x = fixtures.images(B, 256, 256).to(dev)
+for _ in range(passes):
+    model(x)
+torch.cuda.synchronize()
+print("launches per pass", model.engine().plan(B, 256, 256).launches(False))
