@@ -35,19 +35,6 @@ def peaks():
         return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def conv_flops(arch_mod, cfg, H, W):
-    """Algorithmic FLOPs per image by the reference's convention (lib/utils/utils.py:154-159):
-    weight.numel() * H_out * W_out MACs per conv, FLOP = 2 MAC."""
-    a = arch_mod.arch_from_cfg(cfg)
-    res = {}
-    total = 0
-    for sp in arch_mod.layer_specs(a):
-        if not isinstance(sp, arch_mod.Conv):
-            continue
-        res[sp.key] = sp
-    return a, res
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -241,43 +228,36 @@ def run_b200(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    from hrnet_b200.parallel import max_over_ranks
+    ms = max_over_ranks(ms, device=dev)
     if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- e2e: public nn.Module API, pinned host input, decoded joints read back each step ------------
-    from hrnet_b200.utils.heatmap_decoding import get_final_preds
-    host = [fixtures.images(B, H, W, seed=100 + rank * 16 + i).pin_memory() for i in range(2)]
-    out_host = torch.empty((B, 21, 2), dtype=torch.float32).pin_memory()
+    # ---- e2e: public API (pipeline.StreamingPredictor), pinned host input, decoded joints read back each step ----
+    from hrnet_b200.pipeline import StreamingPredictor
+    host = [fixtures.images(B, H, W, seed=100 + rank * 16 + i).pin_memory() for i in range(3)]
+    pred = StreamingPredictor(model)
 
-    def e2e_step(i):
-        xd = host[i % 2].to(dev, non_blocking=True)
-        heat, _, _ = model(xd)
-        coords = get_final_preds(heat, True)
-        out_host.copy_(coords, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the user reads the joints every step
+    def host_batches(n):
+        for i in range(n):
+            yield host[i % 3]
 
-    for i in range(3):
-        e2e_step(i)
+    for _ in pred.run(host_batches(3)):
+        pass
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    n_out = 0
+    for joints in pred.run(host_batches(args.steps)):
+        n_out += joints.shape[0]          # the user consumes the joints of every step on the host
     g1.record()
     torch.cuda.synchronize()
-    e2e_ms = g0.elapsed_time(g1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    assert n_out == B * args.steps
+    e2e_ms = max_over_ranks(g0.elapsed_time(g1), device=dev)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
     if rank != 0:
@@ -315,7 +295,7 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
                 "d2h_bytes_per_step": B * 21 * 2 * 4, "ms_per_step": e2e_ms / args.steps,
-                "api": "model(x.cuda()) -> get_final_preds(heat, True) -> .cpu()"},
+                "api": "pipeline.StreamingPredictor(model).run(pinned host batches): H2D copy + model() + get_final_preds + D2H of every batch, copies overlapped with the previous/next batch"},
         "gpu_launches": args.steps * plan.launches(False),
         "roofline": roof, "cpu_baseline": cpu,
         "tensor_frac_of_burst_peak": (value / world) * flop_img / 1e12 / tf_burst if flop_img else None,

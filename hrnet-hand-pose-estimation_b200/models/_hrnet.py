@@ -70,6 +70,7 @@ class PoseHighResolutionNet(nn.Module):
             self.trainable_temp = nn.Parameter(torch.tensor(1.0), requires_grad=trainable)
         self._engine = None
         self._engine_key = None
+        self._tensors = None
         self.return_features = True   # set False to skip materialising the NCHW fp32 feature output
         self.static_outputs = False   # True: return the engine's static buffers (overwritten by the next call)
 
@@ -100,6 +101,7 @@ class PoseHighResolutionNet(nn.Module):
         """Drop the packed weights (call after mutating parameters in place)."""
         self._engine = None
         self._engine_key = None
+        self._tensors = None
 
     def _apply(self, fn, *a, **k):
         self.invalidate()
@@ -110,7 +112,9 @@ class PoseHighResolutionNet(nn.Module):
         return super().load_state_dict(*a, **k)
 
     def _param_versions(self):
-        return tuple(t._version for t in list(self.parameters()) + list(self.buffers()))
+        if self._tensors is None:
+            self._tensors = list(self.parameters()) + list(self.buffers())
+        return sum(t._version for t in self._tensors), len(self._tensors)
 
     def engine(self):
         from ..engine import HRNetEngine

@@ -59,10 +59,9 @@ def _tile_model(P, W, cin, cout, taps, stride, has_res, bn, mb, kc):
     halo = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0)
     a_bytes = (128 * mb * taps if gather else halo) * cin * 2
     io = a_bytes + bn * taps * cin * 2 * 0.5 + mb * 128 * bn * 2 * (2 if has_res else 1)
-    per_sm = 2 if (smem <= 110 * 1024 and mb * bn <= 128) else 1
     cost = max(mma, io / 23.0)
-    rounds = -(-tiles // (NUM_SMS * per_sm))
-    return rounds * per_sm * cost + 3000.0 / per_sm + 1500.0
+    rounds = -(-tiles // NUM_SMS)        # one persistent CTA per SM
+    return rounds * cost + 4500.0
 
 
 def pick_tile(P, W, cin, cout, taps, stride, has_res, kc=None):

@@ -1,0 +1,57 @@
+"""Streaming inference over host batches: the public end-to-end entry point.
+
+`StreamingPredictor(model).run(batches)` takes an iterable of pinned host tensors [B,3,H,W] float32 and yields the
+decoded joints [B,J,2] (host tensors), overlapping the host->device copy of batch i+1 and the device->host read of
+batch i-1 with the network of batch i (two device input slots, one copy stream).  Every batch still pays its own
+H2D copy, forward, decode and D2H read; they are just not serialised.
+The per-batch work is what tools/evaluate_2D.py:223-238 of the reference does (model -> get_final_preds -> .cpu()).
+"""
+import torch
+
+from .utils.heatmap_decoding import get_final_preds
+
+
+class StreamingPredictor:
+    def __init__(self, model, use_softmax=None, depth=2):
+        self.model = model
+        self.use_softmax = (model.variant == "softmax") if use_softmax is None else use_softmax
+        self.depth = depth
+        self.device = next(model.parameters()).device
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._slots = None
+
+    def _ensure(self, shape):
+        if self._slots is None or self._slots[0]["x"].shape != shape:
+            J = self.model.arch.num_joints
+            self._slots = [dict(x=torch.empty(shape, dtype=torch.float32, device=self.device),
+                                out=torch.empty((shape[0], J, 2), dtype=torch.float32).pin_memory(),
+                                copied=torch.cuda.Event(), done=torch.cuda.Event(), used=False)
+                           for _ in range(self.depth)]
+
+    def run(self, batches):
+        main = torch.cuda.current_stream(self.device)
+        pending = []                      # slots whose results have not been handed out yet (FIFO)
+        i = 0
+        for host in batches:
+            self._ensure(tuple(host.shape))
+            s = self._slots[i % self.depth]
+            if s["used"]:
+                if pending and pending[0] is s:      # hand out the oldest result before its slot is reused
+                    pending.pop(0)
+                    s["done"].synchronize()
+                    yield s["out"]
+                self.copy_stream.wait_event(s["done"])
+            with torch.cuda.stream(self.copy_stream):
+                s["x"].copy_(host, non_blocking=True)
+                s["copied"].record(self.copy_stream)
+            main.wait_event(s["copied"])
+            out = self.model(s["x"])
+            coords = get_final_preds(out[0], self.use_softmax)
+            s["out"].copy_(coords, non_blocking=True)
+            s["done"].record(main)
+            s["used"] = True
+            pending.append(s)
+            i += 1
+        for s in pending:
+            s["done"].synchronize()
+            yield s["out"]
