@@ -15,6 +15,8 @@ _lock = threading.Lock()
 HRNB_CONV_RELU = 1
 HRNB_CONV_OUT_NCHW = 2
 HRNB_CONV_GATHER = 4
+HRNB_CONV_IN_PHASES = 8
+HRNB_CONV_OUT_PHASES = 16
 
 
 def guard_lead(Wp):
@@ -35,6 +37,7 @@ class ConvParams(C.Structure):
         ("in_H", C.c_int32), ("in_W", C.c_int32),
         ("cin", C.c_int32), ("cout", C.c_int32), ("taps", C.c_int32), ("stride", C.c_int32),
         ("KC", C.c_int32), ("BN", C.c_int32), ("MB", C.c_int32), ("flags", C.c_int32),
+        ("in_phase_stride", C.c_int64), ("out_phase_stride", C.c_int64),
     ]
 
 
@@ -53,6 +56,8 @@ _SIGS = {
     "hrnb_conv_smem_bytes": (_i64, [C.POINTER(ConvParams)]),
     "hrnb_pack_conv_weights": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hrnb_stem_conv1": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "hrnb_stem_im2col": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "hrnb_phase_split": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp]),
     "hrnb_fuse_sum": (C.c_int, [C.POINTER(FuseParams), _vp]),
     "hrnb_bilinear_up": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
     "hrnb_pf8_to_nchw_f32": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -47,6 +47,12 @@ struct ConvK {
   int H, W;               // output real dims
   int nchunks, KC, taps, stride;
   int BN, MB, SA, SB;
+  int nsrc;               // 1, or 4 = stride-2 conv over a phase-split input (4 half-resolution PF8 tensors)
+  long long src_stride;   // elements between consecutive phase tensors of the input
+  long long out_phase_stride;  // elements between phase tensors of the output (HRNB_CONV_OUT_PHASES), else 0
+  int oHp2, oWp2;         // padded dims of the output phase grid
+  int lead;               // halo rows in front of the tile's first position
+  int lag;                // gather producer: stages issued ahead of the one being published (SA - 2)
   int halo;               // A rows per plane per stage
   int cout, flags;
   int tmem_cols;
@@ -67,7 +73,7 @@ struct ConvK {
 constexpr int kBarBytes = 256;    // mbarriers + tmem ptr
 constexpr int kBiasBytes = 3072;  // up to 768 fp32 (whole padded bias vector)
 constexpr int kSmemHeader = kBarBytes + kBiasBytes;
-constexpr int kMaxSA = 4, kMaxSB = 8;
+constexpr int kMaxSA = 8, kMaxSB = 4;
 
 constexpr int kEpiWarps = 16;                      // four warps per TMEM lane quarter, splitting the column groups
 constexpr int kThreadsFS = 64 + 32 * kEpiWarps;    // producer + MMA + epilogue
@@ -136,8 +142,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
       const size_t b_elems = k.b_stage_bytes / 2;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x) {
         const int mg = tile / k.n_tiles, ntile = tile - mg * k.n_tiles;
-        const long long pstart =
-            (long long)mg * k.MB * 128 - (k.taps == 9 ? (k.Wp + 1) : 0);  // first halo position (may be < 0: guard)
+        const long long pstart = (long long)mg * k.MB * 128 - k.lead;  // first halo position (may be < 0: guard band)
         const __nv_bfloat16* wsrc = k.wpk + (size_t)ntile * k.nchunks * b_elems;
         const int pit = (tile - (int)blockIdx.x) / (int)gridDim.x;
         HRNB_TRACE(0, pit, 0);
@@ -150,9 +155,12 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
               mbar_arrive_expect_tx(&full_a[a_stage], k.a_stage_bytes);
               uint8_t* dst = a_ring + (size_t)a_stage * k.a_stage_bytes;
               const uint32_t plane_bytes = (uint32_t)k.halo * 16u;
-              for (int j = 0; j < k.KC; ++j) {
-                const __nv_bfloat16* src = k.in + ((long long)(c * k.KC + j) * k.in_ps + pstart) * 8;
-                bulk_g2s(dst + (size_t)j * plane_bytes, src, plane_bytes, &full_a[a_stage]);
+              for (int sidx = 0; sidx < k.nsrc; ++sidx) {       // stage layout [source][plane][row]
+                for (int j = 0; j < k.KC; ++j) {
+                  const __nv_bfloat16* src =
+                      k.in + sidx * k.src_stride + ((long long)(c * k.KC + j) * k.in_ps + pstart) * 8;
+                  bulk_g2s(dst + (size_t)(sidx * k.KC + j) * plane_bytes, src, plane_bytes, &full_a[a_stage]);
+                }
               }
             }
             __syncwarp();
@@ -188,7 +196,8 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
       const uint32_t a_stage16 = k.a_stage_bytes >> 4, b_stage16 = k.b_stage_bytes >> 4;
       const uint32_t a_jstep = 2u * a_lbo16, b_jstep = 2u * b_lbo16;   // K advance of 16 elements = two planes
       const uint32_t b_tap16 = (uint32_t)(k.KC * k.BN);                 // one tap's weight tile in 16-byte units
-      const bool shifted = !GATHER && k.taps == 9;
+      const bool phased = !GATHER && k.nsrc == 4;
+      const bool shifted = !GATHER && k.taps == 9 && !phased;
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
@@ -206,15 +215,18 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
           mbar_wait(&full_b[b_stage], b_phase);
           tc_fence_after_sync();
           if (c == 0) HRNB_TRACE(2, it, 1);
-          uint32_t shift = 0;   // row shift of the current tap: r * Wp + s
-          int scol = 0;
+          uint32_t shift = 0;   // row shift of the current tap inside the halo stage (16-byte rows)
+          int scol = 0, srow = 0;
+          const uint32_t src16 = (uint32_t)(k.KC * k.halo);   // one source's planes, in rows
+          if (phased) shift = 0;   // tap (0,0): phase (1,1) at (dy,dx) = (-1,-1) -> row 0 of source 3
+          uint32_t tap_src = phased ? 3u : 0u;
           uint32_t b_lo_tap = b_lo_ring + (uint32_t)b_stage * b_stage16;
           for (int t = 0; t < k.taps; ++t) {
             if (GATHER) {
               mbar_wait(&full_a[a_stage], a_phase);
               tc_fence_after_sync();
             }
-            const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + shift;
+            const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + tap_src * src16 + shift;
             uint32_t d = d_base;
             uint32_t a_lo_mb = a_lo_tap;
             for (int mb = 0; mb < k.MB; ++mb) {
@@ -241,6 +253,12 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
             }
             if (shifted) {   // next tap: (r, s+1) or (r+1, 0)
               if (++scol == 3) { scol = 0; shift += (uint32_t)k.Wp - 2u; } else { shift += 1u; }
+            } else if (phased) {
+              // stride 2 over phases: tap (r,s) reads phase (r != 1, s != 1) at (dy,dx) = (-(r == 0), -(s == 0))
+              if (++scol == 3) { scol = 0; ++srow; }
+              const uint32_t pr = srow != 1, pc = scol != 1;
+              tap_src = pr * 2u + pc;
+              shift = (srow == 0 ? 0u : (uint32_t)k.Wp) + (scol == 0 ? 0u : 1u);
             }
           }
           __syncwarp();
@@ -319,6 +337,15 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
           if (e0 + u * CS < E) {
             const bool valid = (validm >> cmb) & 1u, real = (realm >> cmb) & 1u;
             const int p = p0 + cmb * 128;
+            long long ph_off = 0;
+            if (k.out_phase_stride != 0 && real) {
+              const int rowi = p / k.Wp;
+              const int x = p - rowi * k.Wp - 1;
+              const int n = rowi / k.Hp;
+              const int y = rowi - n * k.Hp - 1;
+              ph_off = (long long)((y & 1) * 2 + (x & 1)) * k.out_phase_stride +
+                       ((long long)(n * k.oHp2 + (y >> 1) + 1) * k.oWp2 + (x >> 1) + 1) * 8;
+            }
             uint32_t v[16];
             if (!(k.dbg & 4)) {
               tmem_ld16(t_base + (uint32_t)(cmb * k.BN + cg * 16), v);
@@ -377,7 +404,13 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
                 if (!real) o = make_uint4(0u, 0u, 0u, 0u);  // keep the shared zero padding intact
                 if (valid && !(k.dbg & 2)) {
                   const long long plane = (long long)(cb / 8 + h);
-                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(k.out) + (plane * k.out_ps + p) * 8) = o;
+                  if (k.out_phase_stride == 0) {
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(k.out) + (plane * k.out_ps + p) * 8) = o;
+                  } else if (real) {
+                    // write the output as 4 half-resolution phase tensors (input of a following stride-2 conv);
+                    // their padding is never written and stays zero
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(k.out) + ph_off + plane * k.out_ps * 8) = o;
+                  }
                 }
               }
             }
@@ -397,7 +430,17 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
     // =============================== gather producers (GATHER only) ===============================
     if (GATHER) {
       const int g = threadIdx.x - kThreadsFS;  // A row handled by this thread (per M block)
-      constexpr int LAG = 2;
+      const int LAG = k.lag;
+      auto wait_lag = [&]() {   // cp.async.wait_group needs an immediate
+        switch (LAG) {
+          case 1: cp_async_wait<1>(); break;
+          case 2: cp_async_wait<2>(); break;
+          case 3: cp_async_wait<3>(); break;
+          case 4: cp_async_wait<4>(); break;
+          case 5: cp_async_wait<5>(); break;
+          default: cp_async_wait<6>(); break;
+        }
+      };
       int it = 0;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x) {
         const int mg = tile / k.n_tiles;
@@ -432,7 +475,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
             }
             cp_async_commit();
             if (it >= LAG) {
-              cp_async_wait<LAG>();
+              wait_lag();
               fence_proxy_async_smem();
               mbar_arrive(&full_a[(it - LAG) % k.SA]);
             }
@@ -475,7 +518,11 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   const bool gather = (p->flags & HRNB_CONV_GATHER) != 0;
   if (p->taps != 1 && p->taps != 9) return fail(HRNB_EINVAL, "conv: taps must be 1 or 9");
   if (p->stride != 1 && p->stride != 2) return fail(HRNB_EINVAL, "conv: stride must be 1 or 2");
-  if (p->stride == 2 && !gather) return fail(HRNB_EINVAL, "conv: stride 2 needs HRNB_CONV_GATHER");
+  const bool phases_in = (p->flags & HRNB_CONV_IN_PHASES) != 0;
+  if (p->stride == 2 && !gather && !phases_in) return fail(HRNB_EINVAL, "conv: stride 2 needs HRNB_CONV_GATHER or HRNB_CONV_IN_PHASES");
+  if (phases_in && (gather || p->stride != 2 || p->taps != 9)) return fail(HRNB_EINVAL, "conv: HRNB_CONV_IN_PHASES is for 3x3 stride-2 flat-shift convs");
+  if ((p->flags & HRNB_CONV_OUT_PHASES) && ((p->flags & HRNB_CONV_OUT_NCHW) || (p->H & 1) || (p->W & 1)))
+    return fail(HRNB_EINVAL, "conv: HRNB_CONV_OUT_PHASES needs PF8 output with even H and W");
   if (p->cin % 16 || p->cin <= 0) return fail(HRNB_EINVAL, "conv: cin must be a positive multiple of 16");
   if (p->KC <= 0 || (p->KC & 1) || (p->cin / 8) % p->KC) return fail(HRNB_EINVAL, "conv: KC must be even and divide cin/8");
   if (p->BN < 16 || p->BN > 256 || p->BN % 16) return fail(HRNB_EINVAL, "conv: BN must be a multiple of 16 in [16,256]");
@@ -518,21 +565,36 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   const int mblocks = (k->P + 127) / 128;
   k->num_tiles = ((mblocks + p->MB - 1) / p->MB) * k->n_tiles;
   k->tmem_cols = next_pow2_cols(2 * p->MB * p->BN);
+  k->nsrc = phases_in ? 4 : 1;
+  k->src_stride = p->in_phase_stride;
+  k->out_phase_stride = (p->flags & HRNB_CONV_OUT_PHASES) ? p->out_phase_stride : 0;
+  k->oHp2 = p->H / 2 + 1;
+  k->oWp2 = p->W / 2 + 1;
+  k->lead = 0;
+  if (phases_in && p->in_phase_stride <= 0) return fail(HRNB_EINVAL, "conv: in_phase_stride missing");
+  if ((p->flags & HRNB_CONV_OUT_PHASES) && p->out_phase_stride <= 0) return fail(HRNB_EINVAL, "conv: out_phase_stride missing");
   k->b_stage_bytes = (unsigned)(p->taps * p->KC * p->BN * 16);   // all taps of one K chunk
   if (gather) {
     k->halo = 128 * p->MB;
     k->a_stage_bytes = (unsigned)(p->KC * 128 * p->MB * 16);
-    k->SA = 4;
+    k->SA = 8;   // deep ring: the gather is latency bound, the producer runs SA - 2 taps ahead
   } else {
-    k->halo = 128 * p->MB + (p->taps == 9 ? 2 * (k->Wp + 1) : 0);
-    k->a_stage_bytes = (unsigned)(p->KC * k->halo * 16);
+    if (phases_in) {          // taps reach (dy,dx) in {-1,0}^2 on the half-resolution phase grid
+      k->lead = k->Wp + 1;
+      k->halo = 128 * p->MB + k->Wp + 1;
+    } else {
+      k->lead = p->taps == 9 ? k->Wp + 1 : 0;
+      k->halo = 128 * p->MB + (p->taps == 9 ? 2 * (k->Wp + 1) : 0);
+    }
+    k->a_stage_bytes = (unsigned)(k->nsrc * p->KC * k->halo * 16);
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }
   const long long limit = 200 * 1024;
   int SB = 3;
   auto total = [&](int sa, int sb) { return kSmemHeader + (long long)sa * k->a_stage_bytes + (long long)sb * k->b_stage_bytes; };
   while (SB > 2 && total(k->SA, SB) > limit) --SB;
-  if (gather && total(k->SA, SB) > limit) k->SA = 3;  // the gather producer runs LAG = 2 stages ahead: minimum ring depth 3
+  while (gather && k->SA > 3 && total(k->SA, SB) > limit) --k->SA;
+  k->lag = gather ? k->SA - 2 : 0;
   const long long smem = total(k->SA, SB);
   if (smem > 227 * 1024) return fail(HRNB_EINVAL, "conv: tile does not fit in shared memory (reduce KC, BN or MB)");
   k->SB = SB;

@@ -106,6 +106,67 @@ __global__ void __launch_bounds__(256) stem_conv1_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// stem im2col: [N,3,inH,inW] fp32 NCHW -> PF8 bf16, 32 channels (27 taps + 5 zeros) at (inH/2, inW/2)
+// thread = output position; 27 scalar loads (L1 resident), four 16-byte stores
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                         long long out_ps, Geo g, int inH, int inW) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.P) return;
+  const int px = (int)(p % g.Wp);
+  const long long rowi = p / g.Wp;
+  const int py = (int)(rowi % g.Hp);
+  const int n = (int)(rowi / g.Hp);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  if (px > 0 && py > 0) {
+    const int iy0 = (py - 1) * 2 - 1, ix0 = (px - 1) * 2 - 1;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      const float* xc = x + ((long long)n * 3 + ci) * inH * inW;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int iy = iy0 + r;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ix = ix0 + s;
+          if (iy >= 0 && iy < inH && ix >= 0 && ix < inW) v[ci * 9 + r * 3 + s] = __ldg(xc + (long long)iy * inW + ix);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int pl = 0; pl < 4; ++pl) {
+    uint4 o;
+    o.x = pack_bf16x2(v[pl * 8 + 0], v[pl * 8 + 1]); o.y = pack_bf16x2(v[pl * 8 + 2], v[pl * 8 + 3]);
+    o.z = pack_bf16x2(v[pl * 8 + 4], v[pl * 8 + 5]); o.w = pack_bf16x2(v[pl * 8 + 6], v[pl * 8 + 7]);
+    *reinterpret_cast<uint4*>(out + ((long long)pl * out_ps + p) * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase split: PF8 [N,C,H,W] -> 4 x PF8 [N,C,H/2,W/2]; thread = (plane, source position)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) phase_split_kernel(const __nv_bfloat16* __restrict__ src, long long src_ps, Geo g,
+                                                         __nv_bfloat16* __restrict__ dst, long long dst_ps,
+                                                         long long phase_stride) {
+  const int plane = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.P) return;
+  const int px = (int)(p % g.Wp);
+  const long long rowi = p / g.Wp;
+  const int py = (int)(rowi % g.Hp);
+  const int n = (int)(rowi / g.Hp);
+  if (px == 0 || py == 0) return;
+  const int y = py - 1, x = px - 1;
+  const uint4 v = *reinterpret_cast<const uint4*>(src + ((long long)plane * src_ps + p) * 8);
+  const int Hp2 = g.H / 2 + 1, Wp2 = g.W / 2 + 1;
+  const long long q = ((long long)n * Hp2 + (y >> 1) + 1) * Wp2 + (x >> 1) + 1;
+  *reinterpret_cast<uint4*>(dst + (long long)((y & 1) * 2 + (x & 1)) * phase_stride + ((long long)plane * dst_ps + q) * 8) = v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fuse sum
 // ------------------------------------------------------------------------------------------------
 struct FuseK {
@@ -281,6 +342,28 @@ extern "C" int hrnb_stem_conv1(const float* x, const float* w, const float* bias
   stem_conv1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, (__nv_bfloat16*)out, out_ps, g, in_H, in_W);
   count_launch();
   return check_launch("stem_conv1_kernel");
+}
+
+extern "C" int hrnb_stem_im2col(const float* x, void* out, int64_t out_ps, int32_t N, int32_t in_H, int32_t in_W,
+                                void* stream) {
+  if (!x || !out) return fail(HRNB_EINVAL, "stem_im2col: null pointer");
+  if (N <= 0 || in_H <= 0 || in_W <= 0 || (in_H & 1) || (in_W & 1)) return fail(HRNB_EINVAL, "stem_im2col: H, W must be even");
+  const Geo g = make_geo(N, in_H / 2, in_W / 2);
+  stem_im2col_kernel<<<(unsigned)((g.P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, out_ps, g,
+                                                                                      in_H, in_W);
+  count_launch();
+  return check_launch("stem_im2col_kernel");
+}
+
+extern "C" int hrnb_phase_split(const void* src, int64_t src_ps, int32_t N, int32_t C, int32_t H, int32_t W, void* dst,
+                                int64_t dst_ps, int64_t phase_stride, void* stream) {
+  if (!src || !dst || C % 8 || (H & 1) || (W & 1) || phase_stride <= 0) return fail(HRNB_EINVAL, "phase_split: bad params");
+  const Geo g = make_geo(N, H, W);
+  dim3 grid((unsigned)((g.P + 255) / 256), C / 8);
+  phase_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ps, g, (__nv_bfloat16*)dst,
+                                                              dst_ps, phase_stride);
+  count_launch();
+  return check_launch("phase_split_kernel");
 }
 
 extern "C" int hrnb_fuse_sum(const hrnb_fuse_params* p, void* stream) {

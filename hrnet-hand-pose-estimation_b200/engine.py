@@ -19,7 +19,7 @@ import os
 import torch
 
 from . import _lib, arch as A
-from .ops import ConvLayer, PF8
+from .ops import ConvLayer, PF8, PhasePF8
 from ._lib import FuseParams
 
 EPS = 1e-5
@@ -70,6 +70,22 @@ class Plan:
         self.keep.append(t)
         return t
 
+    def _phases(self, C_, H, W):
+        t = PhasePF8(self.B, C_, H, W, device=self.engine.device)
+        self.keep.append(t)
+        return t
+
+    def _split(self, sid, src, name=""):
+        """PF8 -> PhasePF8 copy feeding the 3x3 stride-2 convs that read `src` (one split serves all of them)."""
+        dst = self._phases(src.C, src.H, src.W)
+        lib = _lib.lib()
+
+        def fn(lib=lib, s=src, d=dst):
+            _lib.check(lib.hrnb_phase_split(s.ptr, s.ps, s.N, s.C, s.H, s.W, d.ptr, d.ps, d.phase_stride,
+                                            _lib.stream_ptr()))
+        self._op(sid, fn, name)
+        return dst
+
     def _conv(self, sid, layer, x, out, res=None, name=""):
         p = layer.params(x, out, res)
         self.keep.append(p)
@@ -106,14 +122,15 @@ class Plan:
         if self.H % 32 or self.W % 32:
             raise ValueError("input H and W must be multiples of 32 (four resolutions, each halving)")
 
-        # stem
-        t1 = self._buf(64, H2, W2)
-        x, w27, b1 = self.x, e.stem_w, e.stem_b
+        # stem: conv1 as im2col (27 -> 32 channel slab) + 1x1 conv on the tensor pipe, written directly as the 4
+        # phases conv2 (3x3 stride 2) reads; conv2 then runs on the flat-shift path
+        cols = self._buf(32, H2, W2)
+        x = self.x
 
-        def stem(lib=lib, x=x, w27=w27, b1=b1, t1=t1, B=B, H=self.H, W=self.W):
-            _lib.check(lib.hrnb_stem_conv1(x.data_ptr(), w27.data_ptr(), b1.data_ptr(), t1.ptr, t1.ps, B, H, W,
-                                           _lib.stream_ptr()))
-        self._op(0, stem, "conv1")
+        def stem(lib=lib, x=x, cols=cols, B=B, H=self.H, W=self.W):
+            _lib.check(lib.hrnb_stem_im2col(x.data_ptr(), cols.ptr, cols.ps, B, H, W, _lib.stream_ptr()))
+        self._op(0, stem, "conv1.im2col")
+        t1 = self._conv(0, L["conv1"], cols, self._phases(64, H2, W2), name="conv1")
         cur = self._conv(0, L["conv2"], t1, self._buf(64, H4, W4), name="conv2")
 
         # layer1: 4 bottlenecks
@@ -129,17 +146,19 @@ class Plan:
         # transition1
         res_hw = [(H4 >> i, W4 >> i) for i in range(4)]
         xs = [self._conv(0, L["transition1.0.0"], cur, self._buf(ch[0], *res_hw[0]), name="transition1.0")]
+        cur_ph = self._split(0, cur, "transition1.1.split")
         self._wait(1, 0)
-        xs.append(self._conv(1, L["transition1.1.0.0"], cur, self._buf(ch[1], *res_hw[1]), name="transition1.1"))
+        xs.append(self._conv(1, L["transition1.1.0.0"], cur_ph, self._buf(ch[1], *res_hw[1]), name="transition1.1"))
 
         cat = None
         stage3_b0 = None
         for s, nmod in zip((2, 3, 4), arch.modules):
             nb = s
             if s > 2:
-                self._wait(nb - 1, nb - 2)
                 key = "transition%d.%d.0.0" % (s - 1, nb - 1)
-                xs.append(self._conv(nb - 1, L[key], xs[-1], self._buf(ch[nb - 1], *res_hw[nb - 1]), name=key))
+                tph = self._split(nb - 2, xs[-1], key + ".split")
+                self._wait(nb - 1, nb - 2)
+                xs.append(self._conv(nb - 1, L[key], tph, self._buf(ch[nb - 1], *res_hw[nb - 1]), name=key))
             for m in range(nmod):
                 pre = "stage%d.%d" % (s, m)
                 last_module = (s == 4 and m == nmod - 1)
@@ -150,6 +169,8 @@ class Plan:
                         y = self._conv(i, L[bp + ".conv1"], xs[i], self._buf(ch[i], *res_hw[i]), name=bp + ".conv1")
                         xs[i] = self._conv(i, L[bp + ".conv2"], y, self._buf(ch[i], *res_hw[i]), res=xs[i],
                                            name=bp + ".conv2")
+                # branch outputs that feed stride-2 chains are phase-split once, on their own stream
+                split = {j: self._split(j, xs[j], "%s.split.%d" % (pre, j)) for j in range(nb - 1)}
                 # every fuse output needs every branch
                 for i in range(nb):
                     for j in range(nb):
@@ -165,11 +186,14 @@ class Plan:
                             z = self._conv(i, L[fp], xs[j], self._buf(ch[i], *res_hw[j]), name=fp)
                             srcs.append(z); shifts.append(j - i)
                         else:
-                            t = xs[j]
+                            t = split[j]
                             for k in range(i - j):
                                 fp = "%s.fuse_layers.%d.%d.%d.0" % (pre, i, j, k)
-                                co = ch[i] if k == i - j - 1 else ch[j]
-                                t = self._conv(i, L[fp], t, self._buf(co, *res_hw[j + k + 1]), name=fp)
+                                last = k == i - j - 1
+                                co = ch[i] if last else ch[j]
+                                # intermediate chain outputs are written as phases by the conv epilogue itself
+                                dst = self._buf(co, *res_hw[j + k + 1]) if last else self._phases(co, *res_hw[j + k + 1])
+                                t = self._conv(i, L[fp], t, dst, name=fp)
                             srcs.append(t); shifts.append(0)
                     if last_module and i == 0:
                         cat = self._buf(arch.head_channels, *res_hw[0])
@@ -315,9 +339,10 @@ class HRNetEngine:
                 scale, shift = _fold(sd, bn_after[k], cb)
             else:
                 scale, shift = None, (cb.float() if cb is not None else None)
-            if k == "conv1":
-                self.stem_w = (w.reshape(64, 27) * scale[:, None]).contiguous()
-                self.stem_b = shift.contiguous()
+            if k == "conv1":          # 3x3x3 stem conv == 1x1 conv over the 27(+5 zero)-channel im2col slab
+                w32 = torch.zeros((64, 32, 1, 1), dtype=torch.float32, device=w.device)
+                w32[:, :27, 0, 0] = w.reshape(64, 27)
+                self.layers[k] = ConvLayer(w32, scale, shift, stride=1, relu=True)
                 continue
             leaf = k.rsplit(".", 1)[-1]
             # residual convs (block conv2 / bottleneck conv3) apply ReLU after the add -> flag set

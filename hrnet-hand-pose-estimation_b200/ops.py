@@ -5,8 +5,9 @@ import os
 import torch
 
 from . import _lib
-from ._lib import ConvParams, FuseParams, HRNB_CONV_GATHER, HRNB_CONV_OUT_NCHW, HRNB_CONV_RELU
-from .pf8 import PF8
+from ._lib import (ConvParams, FuseParams, HRNB_CONV_GATHER, HRNB_CONV_IN_PHASES, HRNB_CONV_OUT_NCHW,
+                   HRNB_CONV_OUT_PHASES, HRNB_CONV_RELU)
+from .pf8 import PF8, PhasePF8
 
 NUM_SMS = 148
 
@@ -36,35 +37,44 @@ def pick_bn(cout):
     return bn_candidates(cout)[0]
 
 
-def _smem_bytes(W, taps, gather, bn, mb, kc):
-    halo = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0)
-    a_stage = kc * (128 * mb if gather else halo) * 16
+def _smem_bytes(W, taps, mode, bn, mb, kc):
+    """mode: 1 flat-shift, 2 gather (stride 2 or forced), 4 flat-shift over 4 input phases (stride 2)"""
+    gather = mode == 2
+    if mode == 4:
+        halo, nsrc = 128 * mb + W + 2, 4
+    else:
+        halo, nsrc = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0), 1
+    a_stage = nsrc * kc * (128 * mb if gather else halo) * 16
     b_stage = taps * kc * bn * 16
-    return 3328 + (3 if gather else 2) * a_stage + 2 * b_stage
+    return 3328 + (5 if gather else 2) * a_stage + 2 * b_stage
 
 
-def _tile_model(P, W, cin, cout, taps, stride, has_res, bn, mb, kc):
+def _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kc):
     """Rough cycle model of one conv launch for tile shape (bn, mb, kc): per-tile cost = max(tensor pipe incl. the
     shared-memory operand fetch and the per-chunk hand-off stalls, HBM/L2 bytes), times the tile rounds on 148 SMs."""
     mblocks = (P + 127) // 128
     tiles = (mblocks + mb - 1) // mb * (cout // bn if cout % 16 == 0 else 1)
-    gather = stride == 2
-    smem = _smem_bytes(W, taps, gather, bn, mb, kc)
+    gather = mode == 2
+    smem = _smem_bytes(W, taps, mode, bn, mb, kc)
     if smem > 200 * 1024:
         return None
     ksteps = taps * cin // 16
     nchunks = (cin // 8) // kc
     handoffs = nchunks * (taps if gather else 1)
-    mma = ksteps * mb * max(bn / 2.0, (4096 + bn * 32) / 128.0) + 300.0 * handoffs + 400.0
-    halo = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0)
-    a_bytes = (128 * mb * taps if gather else halo) * cin * 2
+    mma = ksteps * mb * max(bn / 2.0, (4096 + bn * 32) / 128.0) * 1.3 + 300.0 * handoffs + 400.0
+    if mode == 4:
+        a_bytes = 4 * (128 * mb + W + 2) * cin * 2
+    elif gather:
+        a_bytes = 128 * mb * taps * cin * 2 * 2        # 9 taps, half-used 32-byte sectors
+    else:
+        a_bytes = (128 * mb + (2 * (W + 2) if taps == 9 else 0)) * cin * 2
     io = a_bytes + bn * taps * cin * 2 * 0.5 + mb * 128 * bn * 2 * (2 if has_res else 1)
     cost = max(mma, io / 23.0)
     rounds = -(-tiles // NUM_SMS)        # one persistent CTA per SM
     return rounds * cost + 4500.0
 
 
-def pick_tile(P, W, cin, cout, taps, stride, has_res, kc=None):
+def pick_tile(P, W, cin, cout, taps, mode, has_res, kc=None):
     """-> (BN, MB, KC) minimising the launch-time model"""
     env_mb, env_bn, env_kc = os.environ.get("HRNB_MB"), os.environ.get("HRNB_BN"), os.environ.get("HRNB_KC")
     best = None
@@ -78,7 +88,7 @@ def pick_tile(P, W, cin, cout, taps, stride, has_res, kc=None):
             if mb * bn > 256 or (env_mb and mb != int(env_mb) and int(env_mb) * bn <= 256):
                 continue
             for kcc in kcs:
-                t = _tile_model(P, W, cin, cout, taps, stride, has_res, bn, mb, kcc)
+                t = _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kcc)
                 if t is not None and (best is None or t < best[0]):
                     best = (t, bn, mb, kcc)
     if best is None:
@@ -123,10 +133,15 @@ class ConvLayer:
         return self.packs[(bn, kc)]
 
     def params(self, x, out, res=None, mb=None, bn=None, kc=None):
+        in_ph, out_ph = isinstance(x, PhasePF8), isinstance(out, PhasePF8)
         H, W = x.H // self.stride, x.W // self.stride
         P = x.N * (H + 1) * (W + 1)
-        stride_eff = 2 if (self.stride == 2 or self.force_gather) else 1
-        tbn, tmb, tkc = pick_tile(P, W, self.cin, self.cout, self.taps, stride_eff, res is not None, kc or self.fixed_kc)
+        if in_ph:
+            assert self.stride == 2 and self.taps == 9 and not self.force_gather
+            mode = 4
+        else:
+            mode = 2 if (self.stride == 2 or self.force_gather) else 1
+        tbn, tmb, tkc = pick_tile(P, W, self.cin, self.cout, self.taps, mode, res is not None, kc or self.fixed_kc)
         bn = bn or self.fixed_bn or tbn
         if mb is None:
             mb = tmb if bn == tbn else 1
@@ -136,12 +151,13 @@ class ConvLayer:
         lib = _lib.lib()
         if bn != tbn or mb != tmb:      # forced shape: take the largest K chunk that fits
             for cand in ([kc] if (kc and self.fixed_kc) else kc_candidates(self.cin)):
-                if _smem_bytes(W, self.taps, stride_eff == 2, bn, mb, cand) <= 200 * 1024:
+                if _smem_bytes(W, self.taps, mode, bn, mb, cand) <= 200 * 1024:
                     kc = cand
                     break
         wpk, bias = self.pack(bn, kc)
         p = ConvParams()
         p.inp, p.in_ps = x.ptr, x.ps
+        p.in_phase_stride = x.phase_stride if in_ph else 0
         p.wpk, p.bias = wpk.data_ptr(), bias.data_ptr()
         p.res, p.res_ps = (res.ptr, res.ps) if res is not None else (None, 0)
         if self.out_nchw:
@@ -149,10 +165,16 @@ class ConvLayer:
         else:
             assert out.H == H and out.W == W and out.C == self.cout and out.N == x.N
             p.out, p.out_ps = out.ptr, out.ps
+        p.out_phase_stride = out.phase_stride if out_ph else 0
         p.N, p.H, p.W, p.in_H, p.in_W = x.N, H, W, x.H, x.W
         p.cin, p.cout, p.taps, p.stride = self.cin, self.cout, self.taps, self.stride
         p.KC, p.BN, p.MB = kc, bn, mb
-        p.flags = self.flags | (HRNB_CONV_GATHER if self.force_gather else 0)
+        flags = self.flags | (HRNB_CONV_GATHER if self.force_gather else 0)
+        if in_ph:
+            flags = (flags & ~HRNB_CONV_GATHER) | HRNB_CONV_IN_PHASES
+        if out_ph:
+            flags |= HRNB_CONV_OUT_PHASES
+        p.flags = flags
         while p.MB > 1 and lib.hrnb_conv_smem_bytes(C.byref(p)) < 0:
             p.MB //= 2          # tile does not fit in shared memory at this MB
         return p
@@ -189,4 +211,20 @@ def stem_conv1(x, w27, bias, out):
     assert c == 3 and out.C == 64 and out.H == H // 2 and out.W == W // 2
     _lib.check(_lib.lib().hrnb_stem_conv1(x.data_ptr(), w27.data_ptr(), bias.data_ptr(), out.ptr, out.ps,
                                           N, H, W, _lib.stream_ptr()))
+    return out
+
+
+def phase_split(src, dst):
+    """PF8 [N,C,H,W] -> PhasePF8 (4 half-resolution tensors) for a following 3x3 stride-2 conv."""
+    assert isinstance(dst, PhasePF8) and (src.N, src.C, src.H, src.W) == (dst.N, dst.C, dst.H, dst.W)
+    _lib.check(_lib.lib().hrnb_phase_split(src.ptr, src.ps, src.N, src.C, src.H, src.W, dst.ptr, dst.ps,
+                                           dst.phase_stride, _lib.stream_ptr()))
+    return dst
+
+
+def stem_im2col(x, out):
+    """x: [N,3,H,W] fp32 NCHW -> PF8 32 channels (27 taps + 5 zeros) at H/2 x W/2."""
+    N, c, H, W = x.shape
+    assert c == 3 and out.C == 32 and out.H == H // 2 and out.W == W // 2
+    _lib.check(_lib.lib().hrnb_stem_im2col(x.data_ptr(), out.ptr, out.ps, N, H, W, _lib.stream_ptr()))
     return out

@@ -75,3 +75,45 @@ class PF8:
         ok = bool((body[:, :, 0, :, :] == 0).all()) and bool((body[:, :, :, 0, :] == 0).all())
         ok = ok and bool((pl[:, :self.lead] == 0).all()) and bool((pl[:, self.lead + self.P:] == 0).all())
         return ok
+
+
+class PhasePF8:
+    """A [N, C, H, W] activation stored as 4 half-resolution PF8 tensors (phase (a,b) = X[2y+a, 2x+b], index 2a+b):
+    the input format of the 3x3 stride-2 convs on the flat-shift path (include/hrnb.h, HRNB_CONV_IN_PHASES)."""
+    __slots__ = ("buf", "N", "C", "H", "W", "half", "phase_stride", "_ptr")
+
+    def __init__(self, N, C_, H, W, device="cuda"):
+        assert C_ % 8 == 0 and H % 2 == 0 and W % 2 == 0
+        self.N, self.C, self.H, self.W = N, C_, H, W
+        g = PF8.__new__(PF8)               # geometry helper of one phase (no storage of its own)
+        g.N, g.C, g.H, g.W = N, C_, H // 2, W // 2
+        g.Hp, g.Wp = g.H + 1, g.W + 1
+        g.P = N * g.Hp * g.Wp
+        g.planes = C_ // 8
+        g.lead = _lib.guard_lead(g.Wp)
+        g.ps = g.lead + (g.P + 7) // 8 * 8 + _lib.guard_tail(g.Wp)
+        self.half = g
+        self.buf = torch.zeros((4, g.planes, g.ps, 8), dtype=torch.bfloat16, device=device)
+        self.phase_stride = g.planes * g.ps * 8
+        self._ptr = self.buf.data_ptr() + g.lead * 16
+
+    @property
+    def ptr(self):
+        return self._ptr
+
+    @property
+    def ps(self):
+        return self.half.ps
+
+    def to_nchw(self):
+        """[N, C, H, W] float32 reassembled with torch indexing (test helper)."""
+        g = self.half
+        body = self.buf[:, :, g.lead:g.lead + g.P, :].reshape(4, g.planes, self.N, g.Hp, g.Wp, 8)[:, :, :, 1:, 1:, :]
+        t = body.permute(2, 1, 5, 3, 4, 0).reshape(self.N, self.C, g.H, g.W, 2, 2)      # n c y x a b
+        return t.permute(0, 1, 2, 4, 3, 5).reshape(self.N, self.C, self.H, self.W).float()
+
+    def padding_is_zero(self):
+        g = self.half
+        body = self.buf[:, :, g.lead:g.lead + g.P, :].reshape(4, g.planes, self.N, g.Hp, g.Wp, 8)
+        ok = bool((body[:, :, :, 0] == 0).all()) and bool((body[:, :, :, :, 0] == 0).all())
+        return ok and bool((self.buf[:, :, :g.lead] == 0).all()) and bool((self.buf[:, :, g.lead + g.P:] == 0).all())

@@ -40,7 +40,9 @@ extern "C" {
 enum {
   HRNB_CONV_RELU = 1,       /* ReLU after bias (+ residual)                                   */
   HRNB_CONV_OUT_NCHW = 2,   /* write fp32 NCHW [N, cout_real, H, W] instead of PF8 bf16       */
-  HRNB_CONV_GATHER = 4      /* per-tap gathered A operand (stride-2 3x3); otherwise flat-shift */
+  HRNB_CONV_GATHER = 4,     /* per-tap gathered A operand (any stride); otherwise flat-shift      */
+  HRNB_CONV_IN_PHASES = 8,  /* 3x3 stride-2 conv whose input is given as 4 phase tensors (see below) */
+  HRNB_CONV_OUT_PHASES = 16 /* write the PF8 output as 4 phase tensors for a following stride-2 conv */
 };
 
 /* One conv + folded-BN bias (+ residual) (+ ReLU) launch.
@@ -67,6 +69,12 @@ typedef struct hrnb_conv_params {
   int32_t BN;            /* N tile: multiple of 16, <= 256                                      */
   int32_t MB;            /* 128-row M blocks per CTA (1, 2 or 4); MB*BN <= 512                  */
   int32_t flags;
+  /* Phase-split tensors: a [N,C,H,W] tensor stored as 4 PF8 tensors of [N,C,H/2,W/2], phase (a,b) holding
+   * X[2y+a, 2x+b], tensor index 2a+b, consecutive tensors `*_phase_stride` ELEMENTS apart, same plane stride.
+   * A 3x3 stride-2 pad-1 conv then is a flat-shift conv over the 4 phases (tap (r,s) reads phase (r!=1, s!=1)
+   * at offset (-(r==0), -(s==0))), so it runs on the bulk-copy path with ~1.3x instead of 18x input reads. */
+  int64_t in_phase_stride;   /* HRNB_CONV_IN_PHASES: `in` is phase (0,0); in_ps is the phases' plane stride */
+  int64_t out_phase_stride;  /* HRNB_CONV_OUT_PHASES: `out` is phase (0,0); out_ps the phases' plane stride  */
 } hrnb_conv_params;
 
 int hrnb_conv(const hrnb_conv_params* p, void* stream);
@@ -88,6 +96,17 @@ int hrnb_pack_conv_weights(const float* w_oihw, const float* scale, const float*
  * bias[64]. */
 int hrnb_stem_conv1(const float* x_nchw, const float* w, const float* bias, void* out, int64_t out_ps,
                     int32_t N, int32_t in_H, int32_t in_W, void* stream);
+
+/* NCHW fp32 [N,3,H,W] -> PF8 bf16 with 32 channels at (H/2, W/2): channel k = ci*9 + r*3 + s holds the input value
+ * tap (r,s) of the 3x3 stride-2 pad-1 stem conv would read (27..31 = 0), so that conv1 (lib/models/pose_hrnet.py:283)
+ * becomes a 1x1 conv on the tensor pipe. */
+int hrnb_stem_im2col(const float* x_nchw, void* out, int64_t out_ps, int32_t N, int32_t in_H, int32_t in_W,
+                     void* stream);
+
+/* PF8 [N,C,H,W] -> 4 phase tensors [N,C,H/2,W/2] (dst = phase (0,0), phase_stride elements apart); the phases'
+ * padding must be zero on entry and is not written. */
+int hrnb_phase_split(const void* src, int64_t src_ps, int32_t N, int32_t C, int32_t H, int32_t W, void* dst,
+                     int64_t dst_ps, int64_t phase_stride, void* stream);
 
 /* ---- fuse-layer sum: out = ReLU(sum_k src_k[nearest-upsample by 2^shift_k]) -------------------- */
 /* Replaces HighResolutionModule.forward's summation loop + nn.Upsample(nearest) + ReLU,

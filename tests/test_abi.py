@@ -30,6 +30,7 @@ def test_library_exports_every_declared_symbol():
 def _params(**kw):
     p = _lib.ConvParams()
     base = dict(inp=8, in_ps=1024, wpk=8, bias=8, res=None, res_ps=0, out=8, out_ps=1024, N=2, H=16, W=16,
+                in_phase_stride=0, out_phase_stride=0,
                 in_H=16, in_W=16, cin=64, cout=64, taps=9, stride=1, KC=8, BN=64, MB=1, flags=0)
     base.update(kw)
     for k, v in base.items():
@@ -57,7 +58,7 @@ def test_conv_geometry_validation_and_smem_budget():
             for batch in (1, 64):
                 for hw in (64, 32, 16, 8):
                     P = batch * (hw + 1) * (hw + 1)
-                    bn, mb, kc = pick_tile(P, hw, sp.cin, sp.cout, sp.k * sp.k, sp.stride, True)
+                    bn, mb, kc = pick_tile(P, hw, sp.cin, sp.cout, sp.k * sp.k, 2 if sp.stride == 2 else 1, True)
                     assert mb * bn <= 256
                     p = _params(cin=sp.cin, cout=sp.cout, taps=sp.k * sp.k, stride=sp.stride, KC=kc, BN=bn, MB=mb,
                                 H=hw, W=hw, in_H=hw * sp.stride, in_W=hw * sp.stride, N=batch,

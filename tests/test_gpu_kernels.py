@@ -258,3 +258,62 @@ def test_decode_full_size_properties():
     lhs = get_final_preds(0.3 * hm + 0.7 * q, True)
     rhs = 0.3 * get_final_preds(hm, True) + 0.7 * get_final_preds(q, True)
     assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-1)
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,relu", [(2, 32, 32, 32, 64, False), (2, 64, 64, 64, 64, True), (3, 16, 24, 128, 256, False),
+                                                 (1, 16, 16, 256, 64, True), (2, 24, 16, 48, 96, True)])
+def test_stride2_conv_over_phase_split_input(N, H, W, cin, cout, relu):
+    """3x3 stride-2 conv on the flat-shift path: phase_split -> HRNB_CONV_IN_PHASES conv, against torch."""
+    from hrnet_b200.ops import ConvLayer, PF8, PhasePF8, phase_split
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(N, cin, H, W, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (cin * 9) ** 0.5
+    scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(cout, device="cuda", generator=g) * 0.1
+    xp = PF8.from_nchw(x)
+    ph = PhasePF8(N, cin, H, W)
+    phase_split(xp, ph)
+    assert torch.equal(ph.to_nchw(), _bf16(x)) and ph.padding_is_zero()
+    layer = ConvLayer(w, scale, shift, stride=2, relu=relu)
+    out = PF8(N, cout, H // 2, W // 2)
+    layer(ph, out)
+    ref = F.conv2d(_bf16(x), _bf16(w * scale.view(-1, 1, 1, 1)), None, stride=2, padding=1) + shift.view(1, -1, 1, 1)
+    if relu:
+        ref = F.relu(ref)
+    assert (out.to_nchw() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert out.padding_is_zero()
+
+
+def test_conv_writes_phase_split_output_for_a_following_stride2_conv():
+    from hrnet_b200.ops import ConvLayer, PF8, PhasePF8
+    g = torch.Generator(device="cuda").manual_seed(12)
+    N, C, H, W = 2, 32, 32, 32
+    x = torch.randn(N, C, H, W, device="cuda", generator=g)
+    w1 = torch.randn(C, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5
+    w2 = torch.randn(64, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5
+    ph = PhasePF8(N, C, H, W)
+    ConvLayer(w1, relu=True)(PF8.from_nchw(x), ph)                    # stride-1 conv, OUT_PHASES epilogue
+    y_ref = F.relu(F.conv2d(_bf16(x), _bf16(w1), None, padding=1))
+    assert (ph.to_nchw() - y_ref).abs().max().item() <= 2e-2 * y_ref.abs().max().item()
+    assert ph.padding_is_zero()
+    out = PF8(N, 64, H // 2, W // 2)
+    ConvLayer(w2, stride=2)(ph, out)
+    z_ref = F.conv2d(ph.to_nchw(), _bf16(w2), None, stride=2, padding=1)
+    assert (out.to_nchw() - z_ref).abs().max().item() <= 2e-2 * z_ref.abs().max().item()
+
+
+def test_stem_im2col_then_1x1_equals_conv1():
+    from hrnet_b200.ops import ConvLayer, PF8, stem_im2col
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(2, 3, 64, 96, device="cuda", generator=g)
+    w = torch.randn(64, 3, 3, 3, device="cuda", generator=g) * 0.2
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    cols = PF8(2, 32, 32, 48)
+    stem_im2col(x, cols)
+    assert cols.padding_is_zero()
+    w32 = torch.zeros(64, 32, 1, 1, device="cuda")
+    w32[:, :27, 0, 0] = w.reshape(64, 27)
+    out = PF8(2, 64, 32, 48)
+    ConvLayer(w32, None, b, relu=True)(cols, out)
+    ref = F.relu(F.conv2d(_bf16(x), _bf16(w), b, stride=2, padding=1))
+    assert (out.to_nchw() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
