@@ -161,15 +161,27 @@ def workload_config(args, batch, note=None):
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
 def per_kernel_conv_timing(plan, torch, reps=3):
-    """Eager, single-stream pass with a CUDA-event pair around every launch -> per-launch durations of the
-    dominant kernel (conv_tc_kernel).  Returns (sum_ms_conv, sum_ms_all, n_conv)."""
+    """Eager, single-stream passes, every launch queued behind a parked GPU so that host launch gaps do not count:
+    (1) one CUDA-event pair around the whole pass -> serial step time; (2) an event pair around every launch ->
+    each kernel's SHARE of the step (the pairs themselves add ~2 us per launch, so only the shares are used).
+    Time of the dominant kernel (conv_tc_kernel, all launches) = serial step time x its share.
+    Returns (conv_ms, serial_ms, n_conv, per-launch list)."""
     steps = [s for s in plan.steps if s.kind == "op"]
-    best = None
+    best_tot, best = None, None
     for _ in range(reps):
-        evs = []
         torch.cuda.synchronize()
-        torch.cuda._sleep(int(4e7))     # park the GPU so the whole sequence is queued before it starts:
-        for s in steps:                 # event pairs then measure kernel time, not host launch gaps
+        torch.cuda._sleep(int(4e7))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for s in steps:
+            s.fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = a.elapsed_time(b)
+        best_tot = t if best_tot is None else min(best_tot, t)
+        evs = []
+        torch.cuda._sleep(int(4e7))
+        for s in steps:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); s.fn(); b.record()
             evs.append((s.name, a, b))
@@ -181,8 +193,8 @@ def per_kernel_conv_timing(plan, torch, reps=3):
     d = best[1]
     is_conv = lambda n: (n not in ("conv1.im2col", "softmax_softargmax", "decode_argmax") and ".fuse." not in n
                          and "bilinear" not in n and "split" not in n)
-    conv_ms = sum(t for n, t in d if is_conv(n))
-    return conv_ms, best[0], sum(1 for n, _ in d if is_conv(n)), d
+    share = sum(t for n, t in d if is_conv(n)) / best[0]
+    return best_tot * share, best_tot, sum(1 for n, _ in d if is_conv(n)), d
 
 
 def run_b200(args):
@@ -275,8 +287,8 @@ def run_b200(args):
         achieved = conv_flop_step / (conv_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (all %d launches of one step)" % n_conv,
                 "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
-                "traffic": None, "peak_source": "%s bf16_tflops (burst; kernels timed one by one with CUDA events, "
-                "eager single-stream pass)" % peak_kind,
+                "traffic": None, "peak_source": "%s bf16_tflops (burst); duration = eager single-stream step time (one CUDA-event pair, launches "
+                "pre-queued) x the conv kernels' share from per-launch event pairs" % peak_kind,
                 "avg_launch_us": conv_ms / n_conv * 1e3,
                 "conv_share_of_serial_step": conv_ms / all_ms,
                 "step_frac_of_sustained_peak": (value / world) * flop_img / 1e12 / tf_sust}
