@@ -38,6 +38,7 @@ class ConvParams(C.Structure):
         ("cin", C.c_int32), ("cout", C.c_int32), ("taps", C.c_int32), ("stride", C.c_int32),
         ("KC", C.c_int32), ("BN", C.c_int32), ("MB", C.c_int32), ("flags", C.c_int32),
         ("in_phase_stride", C.c_int64), ("out_phase_stride", C.c_int64),
+        ("out2", C.c_void_p), ("out2_ps", C.c_int64), ("out2_phase_stride", C.c_int64),
     ]
 
 

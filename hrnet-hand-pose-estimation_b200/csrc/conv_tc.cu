@@ -50,6 +50,8 @@ struct ConvK {
   int nsrc;               // 1, or 4 = stride-2 conv over a phase-split input (4 half-resolution PF8 tensors)
   long long src_stride;   // elements between consecutive phase tensors of the input
   long long out_phase_stride;  // elements between phase tensors of the output (HRNB_CONV_OUT_PHASES), else 0
+  __nv_bfloat16* out2;    // optional second, phase-split copy of the output (consumed by stride-2 convs)
+  long long out2_ps, out2_phase_stride;
   int oHp2, oWp2;         // padded dims of the output phase grid
   int lead;               // halo rows in front of the tile's first position
   int lag;                // gather producer: stages issued ahead of the one being published (SA - 2)
@@ -128,8 +130,8 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // everything below reads activations written by earlier kernels of the stream
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Activations written by earlier kernels of the stream may only be touched after griddepcontrol.wait; each role
+  // issues it itself so that the producer can fetch the first WEIGHT stage (never written by a kernel) before it.
 
   const int rowsA = GATHER ? 128 * k.MB : k.halo;  // rows per plane in an A stage
   const int acc_cols = k.MB * k.BN;                // fp32 columns of one accumulator stage
@@ -140,6 +142,17 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
     {
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       const size_t b_elems = k.b_stage_bytes / 2;
+      bool b_prefetched = false;
+      if ((int)blockIdx.x < k.num_tiles && !(k.dbg & 16)) {   // first weight stage of the first tile, ahead of the wait
+        const int nt0 = (int)blockIdx.x % k.n_tiles;
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full_b[0], k.b_stage_bytes);
+          bulk_g2s(b_ring, k.wpk + (size_t)nt0 * k.nchunks * b_elems, k.b_stage_bytes, &full_b[0]);
+        }
+        __syncwarp();
+        b_prefetched = true;
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x) {
         const int mg = tile / k.n_tiles, ntile = tile - mg * k.n_tiles;
         const long long pstart = (long long)mg * k.MB * 128 - k.lead;  // first halo position (may be < 0: guard band)
@@ -168,7 +181,9 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
           }
           // one weight stage per K chunk: all taps of the chunk in a single bulk copy (one hand-off per chunk)
           mbar_wait(&empty_b[b_stage], b_phase ^ 1);
-          if (k.dbg & 16) {
+          if (b_prefetched) {
+            b_prefetched = false;   // stage 0 of the first tile is already in flight
+          } else if (k.dbg & 16) {
             if (elect_one_sync()) mbar_arrive(&full_b[b_stage]);
           } else if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
@@ -281,6 +296,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
     // The epilogue is HBM-latency bound (residual reads), so residuals are prefetched PD 16-channel groups ahead
     // into a register ring; the first PD groups of a tile are requested BEFORE waiting for its accumulator.
     constexpr int PD = 4;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int cs = (warp - 2) >> 2;     // which share of the column groups this warp takes
     constexpr int CS = kEpiWarps / 4;   // warps per quarter
@@ -338,12 +354,13 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
             const bool valid = (validm >> cmb) & 1u, real = (realm >> cmb) & 1u;
             const int p = p0 + cmb * 128;
             long long ph_off = 0;
-            if (k.out_phase_stride != 0 && real) {
+            const long long ph_stride = k.out2 ? k.out2_phase_stride : k.out_phase_stride;
+            if (ph_stride != 0 && real) {
               const int rowi = p / k.Wp;
               const int x = p - rowi * k.Wp - 1;
               const int n = rowi / k.Hp;
               const int y = rowi - n * k.Hp - 1;
-              ph_off = (long long)((y & 1) * 2 + (x & 1)) * k.out_phase_stride +
+              ph_off = (long long)((y & 1) * 2 + (x & 1)) * ph_stride +
                        ((long long)(n * k.oHp2 + (y >> 1) + 1) * k.oWp2 + (x >> 1) + 1) * 8;
             }
             uint32_t v[16];
@@ -406,6 +423,8 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
                   const long long plane = (long long)(cb / 8 + h);
                   if (k.out_phase_stride == 0) {
                     *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(k.out) + (plane * k.out_ps + p) * 8) = o;
+                    if (k.out2 != nullptr && real)
+                      *reinterpret_cast<uint4*>(k.out2 + ph_off + plane * k.out2_ps * 8) = o;
                   } else if (real) {
                     // write the output as 4 half-resolution phase tensors (input of a following stride-2 conv);
                     // their padding is never written and stays zero
@@ -429,6 +448,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_
   } else {
     // =============================== gather producers (GATHER only) ===============================
     if (GATHER) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       const int g = threadIdx.x - kThreadsFS;  // A row handled by this thread (per M block)
       const int LAG = k.lag;
       auto wait_lag = [&]() {   // cp.async.wait_group needs an immediate
@@ -568,6 +588,11 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   k->nsrc = phases_in ? 4 : 1;
   k->src_stride = p->in_phase_stride;
   k->out_phase_stride = (p->flags & HRNB_CONV_OUT_PHASES) ? p->out_phase_stride : 0;
+  k->out2 = (__nv_bfloat16*)p->out2;
+  k->out2_ps = p->out2_ps;
+  k->out2_phase_stride = p->out2_phase_stride;
+  if (p->out2 && ((p->flags & (HRNB_CONV_OUT_NCHW | HRNB_CONV_OUT_PHASES)) || (p->H & 1) || (p->W & 1) || p->out2_phase_stride <= 0))
+    return fail(HRNB_EINVAL, "conv: out2 needs a plain PF8 primary output with even H and W");
   k->oHp2 = p->H / 2 + 1;
   k->oWp2 = p->W / 2 + 1;
   k->lead = 0;

@@ -86,8 +86,8 @@ class Plan:
         self._op(sid, fn, name)
         return dst
 
-    def _conv(self, sid, layer, x, out, res=None, name=""):
-        p = layer.params(x, out, res)
+    def _conv(self, sid, layer, x, out, res=None, name="", out2=None):
+        p = layer.params(x, out, res, out2=out2)
         self.keep.append(p)
         lib = _lib.lib()
         ref = C.byref(p)
@@ -141,12 +141,12 @@ class Plan:
             res = cur
             if b == 0:
                 res = self._conv(0, L[pre + ".downsample.0"], cur, self._buf(256, H4, W4), name=pre + ".downsample")
-            cur = self._conv(0, L[pre + ".conv3"], c2, self._buf(256, H4, W4), res=res, name=pre + ".conv3")
+            cur_ph = self._phases(256, H4, W4) if b == 3 else None     # phase copy for the stride-2 transition conv
+            cur = self._conv(0, L[pre + ".conv3"], c2, self._buf(256, H4, W4), res=res, name=pre + ".conv3", out2=cur_ph)
 
         # transition1
         res_hw = [(H4 >> i, W4 >> i) for i in range(4)]
         xs = [self._conv(0, L["transition1.0.0"], cur, self._buf(ch[0], *res_hw[0]), name="transition1.0")]
-        cur_ph = self._split(0, cur, "transition1.1.split")
         self._wait(1, 0)
         xs.append(self._conv(1, L["transition1.1.0.0"], cur_ph, self._buf(ch[1], *res_hw[1]), name="transition1.1"))
 
@@ -163,14 +163,16 @@ class Plan:
                 pre = "stage%d.%d" % (s, m)
                 last_module = (s == 4 and m == nmod - 1)
                 # branches: 4 BasicBlocks each, branch i on stream i
+                split = {}   # branch outputs that feed stride-2 chains also exist as phases (written by the last conv)
                 for i in range(nb):
                     for b in range(arch.blocks):
                         bp = "%s.branches.%d.%d" % (pre, i, b)
                         y = self._conv(i, L[bp + ".conv1"], xs[i], self._buf(ch[i], *res_hw[i]), name=bp + ".conv1")
+                        ph = None
+                        if b == arch.blocks - 1 and i < nb - 1:
+                            ph = split[i] = self._phases(ch[i], *res_hw[i])
                         xs[i] = self._conv(i, L[bp + ".conv2"], y, self._buf(ch[i], *res_hw[i]), res=xs[i],
-                                           name=bp + ".conv2")
-                # branch outputs that feed stride-2 chains are phase-split once, on their own stream
-                split = {j: self._split(j, xs[j], "%s.split.%d" % (pre, j)) for j in range(nb - 1)}
+                                           name=bp + ".conv2", out2=ph)
                 # every fuse output needs every branch
                 for i in range(nb):
                     for j in range(nb):

@@ -132,7 +132,7 @@ class ConvLayer:
             self.packs[(bn, kc)] = (wpk, bias)
         return self.packs[(bn, kc)]
 
-    def params(self, x, out, res=None, mb=None, bn=None, kc=None):
+    def params(self, x, out, res=None, mb=None, bn=None, kc=None, out2=None):
         in_ph, out_ph = isinstance(x, PhasePF8), isinstance(out, PhasePF8)
         H, W = x.H // self.stride, x.W // self.stride
         P = x.N * (H + 1) * (W + 1)
@@ -166,6 +166,9 @@ class ConvLayer:
             assert out.H == H and out.W == W and out.C == self.cout and out.N == x.N
             p.out, p.out_ps = out.ptr, out.ps
         p.out_phase_stride = out.phase_stride if out_ph else 0
+        if out2 is not None:      # second, phase-split copy of the output
+            assert isinstance(out2, PhasePF8) and not out_ph and (out2.H, out2.W, out2.C) == (H, W, self.cout)
+            p.out2, p.out2_ps, p.out2_phase_stride = out2.ptr, out2.ps, out2.phase_stride
         p.N, p.H, p.W, p.in_H, p.in_W = x.N, H, W, x.H, x.W
         p.cin, p.cout, p.taps, p.stride = self.cin, self.cout, self.taps, self.stride
         p.KC, p.BN, p.MB = kc, bn, mb
@@ -179,9 +182,9 @@ class ConvLayer:
             p.MB //= 2          # tile does not fit in shared memory at this MB
         return p
 
-    def __call__(self, x, out, res=None, mb=None, bn=None):
+    def __call__(self, x, out, res=None, mb=None, bn=None, out2=None):
         assert x.C == self.cin, (x.C, self.cin)
-        p = self.params(x, out, res, mb, bn)
+        p = self.params(x, out, res, mb, bn, out2=out2)
         _lib.check(_lib.lib().hrnb_conv(C.byref(p), _lib.stream_ptr()))
         return out
 

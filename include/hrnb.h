@@ -75,6 +75,9 @@ typedef struct hrnb_conv_params {
    * at offset (-(r==0), -(s==0))), so it runs on the bulk-copy path with ~1.3x instead of 18x input reads. */
   int64_t in_phase_stride;   /* HRNB_CONV_IN_PHASES: `in` is phase (0,0); in_ps is the phases' plane stride */
   int64_t out_phase_stride;  /* HRNB_CONV_OUT_PHASES: `out` is phase (0,0); out_ps the phases' plane stride  */
+  void* out2;                /* optional: ALSO write the output phase-split here (NULL = off)               */
+  int64_t out2_ps;
+  int64_t out2_phase_stride;
 } hrnb_conv_params;
 
 int hrnb_conv(const hrnb_conv_params* p, void* stream);
