@@ -289,7 +289,7 @@ def run_b200(args):
                 "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
                 "traffic": None, "peak_source": "%s bf16_tflops (burst); duration = eager single-stream step time (one CUDA-event pair, launches "
                 "pre-queued) x the conv kernels' share from per-launch event pairs" % peak_kind,
-                "avg_launch_us": conv_ms / n_conv * 1e3,
+                "avg_launch_us": conv_ms / n_conv * 1e3, "serial_step_ms": all_ms,
                 "conv_share_of_serial_step": conv_ms / all_ms,
                 "step_frac_of_sustained_peak": (value / world) * flop_img / 1e12 / tf_sust}
     # ---- CPU baseline (bounded sample) ---------------------------------------------------------------------

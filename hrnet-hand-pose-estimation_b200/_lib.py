@@ -7,7 +7,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhrnb.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("HRNB_LIB", "libhrnb.so"))
 
 _lib = None
 _lock = threading.Lock()

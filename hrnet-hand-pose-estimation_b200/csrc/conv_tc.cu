@@ -77,7 +77,11 @@ constexpr int kBiasBytes = 3072;  // up to 768 fp32 (whole padded bias vector)
 constexpr int kSmemHeader = kBarBytes + kBiasBytes;
 constexpr int kMaxSA = 8, kMaxSB = 4;
 
-constexpr int kEpiWarps = 16;                      // four warps per TMEM lane quarter, splitting the column groups
+#ifndef HRNB_EPI_WARPS
+#define HRNB_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = HRNB_EPI_WARPS;          // warps per CTA draining TMEM (a multiple of 4: k per TMEM lane quarter)
+constexpr int kCtasPerSm = kEpiWarps <= 8 ? 2 : 1;  // 8 epilogue warps leave registers for two co-resident CTAs
 constexpr int kThreadsFS = 64 + 32 * kEpiWarps;    // producer + MMA + epilogue
 constexpr int kThreadsGather = kThreadsFS + 128;   // + gather producers
 
@@ -85,7 +89,7 @@ constexpr int kThreadsGather = kThreadsFS + 128;   // + gather producers
 // the issuing thread can only run about one MMA ahead of the tensor pipe, so every scalar instruction and branch between two
 // tcgen05.mma is tensor-pipe idle time for the thin (N = 32 / 64) layers [measured: 106 cycles/MMA with a runtime loop].
 template <bool GATHER, bool NCHW, int KSTEPS>
-__global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, 1) conv_tc_kernel(const ConvK k) {
+__global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ? 1 : kCtasPerSm) conv_tc_kernel(const ConvK k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_a = full_a + kMaxSA;
@@ -683,7 +687,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
     sm_count[dev] = n;
   }
   // persistent grid: one or two CTAs per SM (two when shared memory and TMEM columns allow it)
-  int per_sm = 1;   // 16 epilogue warps per CTA: one persistent CTA per SM
+  int per_sm = (kCtasPerSm == 2 && !gather && smem <= 110 * 1024 && 2 * k.tmem_cols <= 512) ? 2 : 1;
   if (g_debug[1] > 0) per_sm = g_debug[1] == 1 ? 1 : per_sm;   // debug: force one CTA per SM
   int grid = sm_count[dev] * per_sm;
   if (grid > k.num_tiles) grid = k.num_tiles;

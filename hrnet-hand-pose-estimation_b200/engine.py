@@ -58,11 +58,13 @@ class Plan:
 
     # ---- step recording ---------------------------------------------------------------------------
     def _op(self, sid, fn, name):
+        if self.engine.single_stream:
+            sid = 0
         self.steps.append(_Step("op", sid, fn, name=name))
         self.n_launch += 1
 
     def _wait(self, sid, other):
-        if sid != other:
+        if sid != other and not self.engine.single_stream:
             self.steps.append(_Step("wait", sid, other=other))
 
     def _buf(self, C_, H, W):
@@ -308,6 +310,7 @@ class HRNetEngine:
         self.layers = {}
         self.plans = {}
         self.use_graph = os.environ.get("HRNB_NO_GRAPH", "0") != "1"
+        self.single_stream = os.environ.get("HRNB_SINGLE_STREAM", "0") == "1"
         with torch.cuda.device(self.device):
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
             self._pack(sd)
