@@ -39,6 +39,7 @@ class ConvParams(C.Structure):
         ("KC", C.c_int32), ("BN", C.c_int32), ("MB", C.c_int32), ("flags", C.c_int32),
         ("in_phase_stride", C.c_int64), ("out_phase_stride", C.c_int64),
         ("out2", C.c_void_p), ("out2_ps", C.c_int64), ("out2_phase_stride", C.c_int64),
+        ("ntap_custom", C.c_int32), ("tap_src", C.c_int32 * 9), ("tap_dpos", C.c_int32 * 9),
     ]
 
 
@@ -48,6 +49,52 @@ class FuseParams(C.Structure):
         ("nsrc", C.c_int32),
         ("out", C.c_void_p), ("out_ps", C.c_int64),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("relu", C.c_int32),
+    ]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("dy_ps", C.c_int64), ("x", C.c_void_p), ("x_ps", C.c_int64), ("dw", C.c_void_p),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+        ("ntap", C.c_int32), ("tap_dpos", C.c_int32 * 9), ("tap_id", C.c_int32 * 9),
+        ("NT", C.c_int32), ("TG", C.c_int32), ("KP", C.c_int32), ("ksplit", C.c_int32),
+    ]
+
+
+class PackJob(C.Structure):
+    _fields_ = [
+        ("w", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("wpk_out", C.c_void_p), ("bias_out", C.c_void_p),
+        ("cout", C.c_int32), ("cin", C.c_int32), ("taps_total", C.c_int32), ("transpose", C.c_int32),
+        ("lcout", C.c_int32), ("lcin", C.c_int32), ("ntap", C.c_int32), ("tap_ids", C.c_int32 * 9),
+        ("KC", C.c_int32), ("BN", C.c_int32), ("block0", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
+class BnParams(C.Structure):
+    _fields_ = [
+        ("c", C.c_void_p), ("c_ps", C.c_int64), ("sums", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("res", C.c_void_p), ("res_ps", C.c_int64), ("out", C.c_void_p), ("out_ps", C.c_int64),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+        ("N", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu", C.c_int32),
+        ("eps", C.c_float), ("momentum", C.c_float),
+    ]
+
+
+class BnBwdParams(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("dy_ps", C.c_int64), ("y", C.c_void_p), ("y_ps", C.c_int64),
+        ("c", C.c_void_p), ("c_ps", C.c_int64), ("sums", C.c_void_p), ("gamma", C.c_void_p), ("dsums", C.c_void_p),
+        ("dc", C.c_void_p), ("dc_ps", C.c_int64), ("dres", C.c_void_p), ("dres_ps", C.c_int64), ("dres_mode", C.c_int32),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("N", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu", C.c_int32), ("eps", C.c_float),
+    ]
+
+
+class ParamSeg(C.Structure):
+    _fields_ = [
+        ("p_off", C.c_int64), ("g_off", C.c_int64), ("numel", C.c_int32),
+        ("cout", C.c_int32), ("cin", C.c_int32), ("cin_g", C.c_int32), ("taps", C.c_int32),
+        ("block0", C.c_int32), ("frozen", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -70,6 +117,20 @@ _SIGS = {
     "hrnb_final_preds": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "hrnb_loss_heatmap": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "hrnb_loss_pose2d": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "hrnb_wgrad": (C.c_int, [C.POINTER(WgradParams), _vp]),
+    "hrnb_wgrad_smem_bytes": (_i64, [C.POINTER(WgradParams)]),
+    "hrnb_pack_conv_weights_batch": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "hrnb_bn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hrnb_channel_sum": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hrnb_bn_apply": (C.c_int, [C.POINTER(BnParams), _vp]),
+    "hrnb_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
+    "hrnb_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
+    "hrnb_fuse_sum_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "hrnb_bilinear_up_bwd": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "hrnb_phase_merge": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "hrnb_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "hrnb_adam_tick": (C.c_int, [_vp, _vp, _vp]),
+    "hrnb_grad_to_natural": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "hrnb_last_error": (C.c_char_p, []),
     "hrnb_abi_version": (C.c_int, []),
     "hrnb_launch_count": (_i64, []),
@@ -100,7 +161,7 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if h.hrnb_abi_version() != 1:
+        if h.hrnb_abi_version() != 2:
             raise HrnbError("libhrnb.so ABI version mismatch")
         _lib = h
     return _lib

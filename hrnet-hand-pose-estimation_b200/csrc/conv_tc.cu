@@ -63,6 +63,7 @@ struct ConvK {
   long long* trace;       // debug: per-role timeline of CTA 0 (hrnb_debug_trace)
   int dbg;                // debug bitmask (hrnb_debug_set(3, m)): 1 no residual loads, 2 no stores, 4 no TMEM loads
   unsigned a_stage_bytes, b_stage_bytes;
+  int tap_off[9];         // flat-shift path: row offset of tap t inside an A stage (source * KC * halo + lead + dpos)
 };
 
 // debug timeline: slot = role*64 + 2*tile_iter + {0,1}; written by one lane of CTA 0 only when tracing is on
@@ -215,8 +216,6 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       const uint32_t a_stage16 = k.a_stage_bytes >> 4, b_stage16 = k.b_stage_bytes >> 4;
       const uint32_t a_jstep = 2u * a_lbo16, b_jstep = 2u * b_lbo16;   // K advance of 16 elements = two planes
       const uint32_t b_tap16 = (uint32_t)(k.KC * k.BN);                 // one tap's weight tile in 16-byte units
-      const bool phased = !GATHER && k.nsrc == 4;
-      const bool shifted = !GATHER && k.taps == 9 && !phased;
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
@@ -234,18 +233,14 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           mbar_wait(&full_b[b_stage], b_phase);
           tc_fence_after_sync();
           if (c == 0) HRNB_TRACE(2, it, 1);
-          uint32_t shift = 0;   // row shift of the current tap inside the halo stage (16-byte rows)
-          int scol = 0, srow = 0;
-          const uint32_t src16 = (uint32_t)(k.KC * k.halo);   // one source's planes, in rows
-          if (phased) shift = 0;   // tap (0,0): phase (1,1) at (dy,dx) = (-1,-1) -> row 0 of source 3
-          uint32_t tap_src = phased ? 3u : 0u;
           uint32_t b_lo_tap = b_lo_ring + (uint32_t)b_stage * b_stage16;
           for (int t = 0; t < k.taps; ++t) {
             if (GATHER) {
               mbar_wait(&full_a[a_stage], a_phase);
               tc_fence_after_sync();
             }
-            const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + tap_src * src16 + shift;
+            // tap t reads input position p + dpos[t] of source src[t]: a row offset into the halo stage (host table)
+            const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + (GATHER ? 0u : (uint32_t)k.tap_off[t]);
             uint32_t d = d_base;
             uint32_t a_lo_mb = a_lo_tap;
             for (int mb = 0; mb < k.MB; ++mb) {
@@ -269,15 +264,6 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
               __syncwarp();
               if (elect_one_sync()) umma_commit(&empty_a[a_stage]);
               if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
-            }
-            if (shifted) {   // next tap: (r, s+1) or (r+1, 0)
-              if (++scol == 3) { scol = 0; shift += (uint32_t)k.Wp - 2u; } else { shift += 1u; }
-            } else if (phased) {
-              // stride 2 over phases: tap (r,s) reads phase (r != 1, s != 1) at (dy,dx) = (-(r == 0), -(s == 0))
-              if (++scol == 3) { scol = 0; ++srow; }
-              const uint32_t pr = srow != 1, pc = scol != 1;
-              tap_src = pr * 2u + pc;
-              shift = (srow == 0 ? 0u : (uint32_t)k.Wp) + (scol == 0 ? 0u : 1u);
             }
           }
           __syncwarp();
@@ -540,7 +526,11 @@ struct Launch {
 static long long derive(const hrnb_conv_params* p, ConvK* k) {
   if (!p || !p->in || !p->wpk || !p->bias || !p->out) return fail(HRNB_EINVAL, "conv: null pointer");
   const bool gather = (p->flags & HRNB_CONV_GATHER) != 0;
-  if (p->taps != 1 && p->taps != 9) return fail(HRNB_EINVAL, "conv: taps must be 1 or 9");
+  const bool custom = p->ntap_custom > 0;
+  if (custom) {
+    if (gather || p->stride != 1 || p->taps != p->ntap_custom || p->ntap_custom > 9 || (p->flags & HRNB_CONV_IN_PHASES))
+      return fail(HRNB_EINVAL, "conv: custom taps need the flat-shift path, stride 1 and taps == ntap_custom <= 9");
+  } else if (p->taps != 1 && p->taps != 9) return fail(HRNB_EINVAL, "conv: taps must be 1 or 9");
   if (p->stride != 1 && p->stride != 2) return fail(HRNB_EINVAL, "conv: stride must be 1 or 2");
   const bool phases_in = (p->flags & HRNB_CONV_IN_PHASES) != 0;
   if (p->stride == 2 && !gather && !phases_in) return fail(HRNB_EINVAL, "conv: stride 2 needs HRNB_CONV_GATHER or HRNB_CONV_IN_PHASES");
@@ -589,8 +579,8 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   const int mblocks = (k->P + 127) / 128;
   k->num_tiles = ((mblocks + p->MB - 1) / p->MB) * k->n_tiles;
   k->tmem_cols = next_pow2_cols(2 * p->MB * p->BN);
-  k->nsrc = phases_in ? 4 : 1;
   k->src_stride = p->in_phase_stride;
+  for (int t = 0; t < 9; ++t) k->tap_off[t] = 0;
   k->out_phase_stride = (p->flags & HRNB_CONV_OUT_PHASES) ? p->out_phase_stride : 0;
   k->out2 = (__nv_bfloat16*)p->out2;
   k->out2_ps = p->out2_ps;
@@ -603,18 +593,41 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   if (phases_in && p->in_phase_stride <= 0) return fail(HRNB_EINVAL, "conv: in_phase_stride missing");
   if ((p->flags & HRNB_CONV_OUT_PHASES) && p->out_phase_stride <= 0) return fail(HRNB_EINVAL, "conv: out_phase_stride missing");
   k->b_stage_bytes = (unsigned)(p->taps * p->KC * p->BN * 16);   // all taps of one K chunk
+  // tap table: tap t reads source tsrc[t] at position p + tdpos[t]
+  int tsrc[9] = {0}, tdpos[9] = {0};
+  k->nsrc = 1;
+  if (custom) {
+    for (int t = 0; t < p->taps; ++t) {
+      tsrc[t] = p->tap_src[t];
+      tdpos[t] = p->tap_dpos[t];
+      if (tsrc[t] < 0 || tsrc[t] > 3) return fail(HRNB_EINVAL, "conv: tap_src out of range");
+      if (tsrc[t] + 1 > k->nsrc) k->nsrc = tsrc[t] + 1;
+    }
+    if (k->nsrc > 1 && p->in_phase_stride <= 0) return fail(HRNB_EINVAL, "conv: in_phase_stride missing");
+  } else if (phases_in) {     // tap (r,s) reads phase (r != 1, s != 1) at (dy,dx) = (-(r == 0), -(s == 0)) on the half grid
+    k->nsrc = 4;
+    for (int t = 0; t < 9; ++t) {
+      const int r = t / 3, s = t % 3;
+      tsrc[t] = (r != 1) * 2 + (s != 1);
+      tdpos[t] = -(r == 0) * k->Wp - (s == 0);
+    }
+  } else if (p->taps == 9) {
+    for (int t = 0; t < 9; ++t) tdpos[t] = (t / 3 - 1) * k->Wp + (t % 3 - 1);
+  }
   if (gather) {
     k->halo = 128 * p->MB;
     k->a_stage_bytes = (unsigned)(p->KC * 128 * p->MB * 16);
     k->SA = 8;   // deep ring: the gather is latency bound, the producer runs SA - 2 taps ahead
   } else {
-    if (phases_in) {          // taps reach (dy,dx) in {-1,0}^2 on the half-resolution phase grid
-      k->lead = k->Wp + 1;
-      k->halo = 128 * p->MB + k->Wp + 1;
-    } else {
-      k->lead = p->taps == 9 ? k->Wp + 1 : 0;
-      k->halo = 128 * p->MB + (p->taps == 9 ? 2 * (k->Wp + 1) : 0);
+    int lo = 0, hi = 0;
+    for (int t = 0; t < p->taps; ++t) {
+      if (tdpos[t] < lo) lo = tdpos[t];
+      if (tdpos[t] > hi) hi = tdpos[t];
     }
+    if (-lo > HRNB_GUARD_LEAD(k->Wp) || hi > HRNB_GUARD_LEAD(k->Wp)) return fail(HRNB_EINVAL, "conv: tap offset exceeds the PF8 guard band");
+    k->lead = -lo;
+    k->halo = 128 * p->MB + hi - lo;
+    for (int t = 0; t < p->taps; ++t) k->tap_off[t] = tsrc[t] * p->KC * k->halo + k->lead + tdpos[t];
     k->a_stage_bytes = (unsigned)(k->nsrc * p->KC * k->halo * 16);
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }

@@ -4,19 +4,9 @@
 // so consecutive lanes touch consecutive 16-byte words (fully coalesced).
 #include "ptx.cuh"
 #include "common.h"
+#include "geo.cuh"
 
 namespace hrnb {
-
-struct Geo {  // padded-flat geometry of one PF8 tensor
-  int N, H, W, Hp, Wp;
-  long long P;
-};
-__host__ __device__ inline Geo make_geo(int N, int H, int W) {
-  Geo g;
-  g.N = N; g.H = H; g.W = W; g.Hp = H + 1; g.Wp = W + 1;
-  g.P = (long long)N * g.Hp * g.Wp;
-  return g;
-}
 
 // ------------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> [ntile][chunk][tap][KC][BN][8] bf16, scale folded
@@ -217,22 +207,6 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseK k) {
 // ------------------------------------------------------------------------------------------------
 // bilinear up-sample (PyTorch upsample_bilinear2d index rules, fp32 index math) PF8 -> PF8
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bil_index(int d, int in, int out, bool align, int& i0, int& i1, float& l1) {
-  float src;
-  if (align) {
-    const float sc = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
-    src = sc * (float)d;
-  } else {
-    const float sc = (float)in / (float)out;
-    src = sc * ((float)d + 0.5f) - 0.5f;
-    if (src < 0.f) src = 0.f;
-  }
-  i0 = (int)src;
-  if (i0 > in - 1) i0 = in - 1;
-  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
-  l1 = src - (float)i0;
-}
-
 __global__ void __launch_bounds__(256) bilinear_kernel(const __nv_bfloat16* __restrict__ src, long long src_ps, Geo sg,
                                                       __nv_bfloat16* __restrict__ dst, long long dst_ps, Geo dg,
                                                       int align) {

@@ -1,0 +1,642 @@
+// HBM-bound kernels of the TRAINING path: batch-statistics BatchNorm forward / backward, the backward of the
+// fuse-layer sum, of the head's bilinear up-sampling and of the phase split, batched weight re-packing, fused Adam.
+//
+// Reference semantics (file:line relative to the reference repo):
+//   nn.BatchNorm2d(momentum 0.1, eps 1e-5) in train mode   lib/models/pose_hrnet.py:18,36 (and every other BN of the file)
+//   HighResolutionModule.forward sum + nearest up-sampling  lib/models/pose_hrnet.py:199-207,257-266   (backward = autograd)
+//   F.interpolate(bilinear)                                lib/models/pose_hrnet_softmax.py:499-502 / pose_hrnet.py:561-563
+//   Adam(lr, L2 weight_decay)                              lib/utils/utils.py:71-92  (torch.optim.Adam semantics)
+// All activations / activation gradients are PF8 bf16; thread = one 16-byte position of one plane.
+#include "ptx.cuh"
+#include "common.h"
+#include "geo.cuh"
+
+namespace hrnb {
+
+// ------------------------------------------------------------------------------------------------
+// block-level reduction of NV per-thread values -> atomicAdd into global (one atomic per value per block)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float* __restrict__ dst, int dst_stride) {
+  __shared__ float red[8][NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[warp][i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float s = 0.f;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) s += red[w][threadIdx.x];
+    atomicAdd(dst + (long long)threadIdx.x * dst_stride, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN forward, batch statistics
+// ------------------------------------------------------------------------------------------------
+// sums[c][0] += sum_p x, sums[c][1] += sum_p x^2 (padding positions are zero and add nothing)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ c, long long c_ps, long long P,
+                                                      float* __restrict__ sums) {
+  const int plane = blockIdx.y;
+  const __nv_bfloat16* base = c + (long long)plane * c_ps * 8;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    float a[8];
+    unpack8(ldg_nc_v4(base + p * 8), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[2 * i] += a[i];
+      v[2 * i + 1] = fmaf(a[i], a[i], v[2 * i + 1]);
+    }
+  }
+  block_reduce_atomic<16>(v, sums + (long long)plane * 16, 1);   // [channel][2] interleaved
+}
+
+// per-channel sum only (bias gradient of the BN-less final conv): out[c] += sum_p x
+__global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* __restrict__ c, long long c_ps, long long P,
+                                                         int C, float* __restrict__ out) {
+  const int plane = blockIdx.y;
+  const __nv_bfloat16* base = c + (long long)plane * c_ps * 8;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    float a[8];
+    unpack8(ldg_nc_v4(base + p * 8), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += a[i];
+  }
+  __shared__ float red[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && plane * 8 + (int)threadIdx.x < C) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(out + plane * 8 + threadIdx.x, s);
+  }
+}
+
+struct BnK {
+  const __nv_bfloat16* c; long long c_ps;
+  const float* sums; const float* gamma; const float* beta;
+  const __nv_bfloat16* res; long long res_ps;
+  __nv_bfloat16* out; long long out_ps;
+  float* running_mean; float* running_var;
+  Geo g;
+  int relu;
+  float eps, momentum, count;
+};
+
+// y = [relu]( gamma*(c-mean)*invstd + beta [+ res] ), zeros at padding; block (0, plane) also updates the running stats
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnK k) {
+  __shared__ float sa[8], sb[8];
+  const int plane = blockIdx.y;
+  if (threadIdx.x < 8) {
+    const int ch = plane * 8 + threadIdx.x;
+    const float mean = k.sums[2 * ch] / k.count;
+    float var = k.sums[2 * ch + 1] / k.count - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float a = k.gamma[ch] * rsqrtf(var + k.eps);
+    sa[threadIdx.x] = a;
+    sb[threadIdx.x] = k.beta[ch] - mean * a;
+    if (blockIdx.x == 0 && k.running_mean != nullptr) {
+      const float unbiased = k.count > 1.f ? var * k.count / (k.count - 1.f) : var;
+      k.running_mean[ch] = (1.f - k.momentum) * k.running_mean[ch] + k.momentum * mean;
+      k.running_var[ch] = (1.f - k.momentum) * k.running_var[ch] + k.momentum * unbiased;
+    }
+  }
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= k.g.P) return;
+  const Pos q = decode_pos(k.g, p);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (q.px > 0 && q.py > 0) {
+    float x[8];
+    unpack8(ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8), x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], sa[i], sb[i]);
+    if (k.res != nullptr) {
+      float r[8];
+      unpack8(ldg_nc_v4(k.res + ((long long)plane * k.res_ps + p) * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] += r[i];
+    }
+    if (k.relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+    }
+    o = pack8(x);
+  }
+  *reinterpret_cast<uint4*>(k.out + ((long long)plane * k.out_ps + p) * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN backward
+// ------------------------------------------------------------------------------------------------
+struct BnBwdK {
+  const __nv_bfloat16* dy; long long dy_ps;
+  const __nv_bfloat16* y; long long y_ps;
+  const __nv_bfloat16* c; long long c_ps;
+  const float* sums; const float* gamma;
+  float* dsums;
+  __nv_bfloat16* dc; long long dc_ps;
+  __nv_bfloat16* dres; long long dres_ps; int dres_mode;
+  float* dgamma; float* dbeta;
+  Geo g;
+  int relu;
+  float eps, count;
+};
+
+__device__ __forceinline__ void bn_channel_stats(const float* sums, int ch, float count, float eps, float& mean, float& invstd) {
+  mean = sums[2 * ch] / count;
+  float var = sums[2 * ch + 1] / count - mean * mean;
+  var = fmaxf(var, 0.f);
+  invstd = rsqrtf(var + eps);
+}
+
+// dsums[c][0] += sum g, dsums[c][1] += sum g*xhat with g = dy * (y > 0)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
+  __shared__ float sm[8], si[8];
+  const int plane = blockIdx.y;
+  if (threadIdx.x < 8) bn_channel_stats(k.sums, plane * 8 + threadIdx.x, k.count, k.eps, sm[threadIdx.x], si[threadIdx.x]);
+  __syncthreads();
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < k.g.P; p += (long long)gridDim.x * blockDim.x) {
+    float g[8], x[8];
+    unpack8(ldg_nc_v4(k.dy + ((long long)plane * k.dy_ps + p) * 8), g);
+    if (k.relu) {
+      float yy[8];
+      unpack8(ldg_nc_v4(k.y + ((long long)plane * k.y_ps + p) * 8), yy);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = yy[i] > 0.f ? g[i] : 0.f;
+    }
+    unpack8(ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8), x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[2 * i] += g[i];
+      v[2 * i + 1] = fmaf(g[i], (x[i] - sm[i]) * si[i], v[2 * i + 1]);   // padding: g == 0
+    }
+  }
+  block_reduce_atomic<16>(v, k.dsums + (long long)plane * 16, 1);
+}
+
+// dc = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dres (+)= g; block (0, plane) writes dgamma / dbeta
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdK k) {
+  __shared__ float sm[8], si[8], sa[8], s0[8], s1[8];
+  const int plane = blockIdx.y;
+  if (threadIdx.x < 8) {
+    const int ch = plane * 8 + threadIdx.x;
+    float mean, invstd;
+    bn_channel_stats(k.sums, ch, k.count, k.eps, mean, invstd);
+    sm[threadIdx.x] = mean;
+    si[threadIdx.x] = invstd;
+    sa[threadIdx.x] = k.gamma[ch] * invstd;
+    const float d0 = k.dsums[2 * ch], d1 = k.dsums[2 * ch + 1];
+    s0[threadIdx.x] = d0 / k.count;
+    s1[threadIdx.x] = d1 / k.count;
+    if (blockIdx.x == 0) {
+      if (k.dgamma) k.dgamma[ch] = d1;
+      if (k.dbeta) k.dbeta[ch] = d0;
+    }
+  }
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= k.g.P) return;
+  const Pos q = decode_pos(k.g, p);
+  const bool real = q.px > 0 && q.py > 0;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  uint4 gres = make_uint4(0u, 0u, 0u, 0u);
+  if (real) {
+    float g[8], x[8];
+    unpack8(*reinterpret_cast<const uint4*>(k.dy + ((long long)plane * k.dy_ps + p) * 8), g);
+    if (k.relu) {
+      float yy[8];
+      unpack8(ldg_nc_v4(k.y + ((long long)plane * k.y_ps + p) * 8), yy);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = yy[i] > 0.f ? g[i] : 0.f;
+    }
+    unpack8(ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8), x);
+    if (k.dres_mode == 2) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] += g[i];
+      gres = pack8(r);
+    } else if (k.dres_mode == 1) {
+      gres = pack8(g);
+    }
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = sa[i] * (g[i] - s0[i] - (x[i] - sm[i]) * si[i] * s1[i]);
+    o = pack8(d);
+  }
+  *reinterpret_cast<uint4*>(k.dc + ((long long)plane * k.dc_ps + p) * 8) = o;
+  if (k.dres_mode != 0) *reinterpret_cast<uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8) = gres;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fuse-sum backward: dsrc[q] (+)= sum over the 2^shift x 2^shift block of dy * (y > 0)
+// ------------------------------------------------------------------------------------------------
+struct FuseBwdK {
+  const __nv_bfloat16* dy; long long dy_ps;
+  const __nv_bfloat16* y; long long y_ps;
+  __nv_bfloat16* dsrc; long long dsrc_ps;
+  Geo og, sg;   // output (dy) and source geometry
+  int shift, mode, relu;
+};
+
+__global__ void __launch_bounds__(256) fuse_sum_bwd_kernel(const FuseBwdK k) {
+  const int plane = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= k.sg.P) return;
+  const Pos q = decode_pos(k.sg, p);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (q.px > 0 && q.py > 0) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int f = 1 << k.shift;
+    const int oy0 = (q.py - 1) << k.shift, ox0 = (q.px - 1) << k.shift;
+    for (int dy_ = 0; dy_ < f; ++dy_) {
+      const long long rowp = ((long long)q.n * k.og.Hp + oy0 + dy_ + 1) * k.og.Wp + ox0 + 1;
+      for (int dx_ = 0; dx_ < f; ++dx_) {
+        float g[8];
+        unpack8(ldg_nc_v4(k.dy + ((long long)plane * k.dy_ps + rowp + dx_) * 8), g);
+        if (k.relu) {
+          float yy[8];
+          unpack8(ldg_nc_v4(k.y + ((long long)plane * k.y_ps + rowp + dx_) * 8), yy);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = yy[i] > 0.f ? g[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] += g[i];
+      }
+    }
+    if (k.mode == 2) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(k.dsrc + ((long long)plane * k.dsrc_ps + p) * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += r[i];
+    }
+    o = pack8(a);
+  }
+  *reinterpret_cast<uint4*>(k.dsrc + ((long long)plane * k.dsrc_ps + p) * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear up-sampling backward (gather form: every source pixel collects the destination pixels it fed)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dd, long long dd_ps, Geo dg,
+                                                          __nv_bfloat16* __restrict__ ds, long long ds_ps, Geo sg, int align,
+                                                          int mode) {
+  const int plane = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= sg.P) return;
+  const Pos q = decode_pos(sg, p);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (q.px > 0 && q.py > 0) {
+    const int sy = q.py - 1, sx = q.px - 1;
+    // destination rows / columns whose interpolation window can contain this source index
+    const int fy = (dg.H + sg.H - 1) / sg.H, fx = (dg.W + sg.W - 1) / sg.W;
+    const int ylo = max(0, (sy - 1) * fy - fy), yhi = min(dg.H - 1, (sy + 1) * fy + fy);
+    const int xlo = max(0, (sx - 1) * fx - fx), xhi = min(dg.W - 1, (sx + 1) * fx + fx);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int y = ylo; y <= yhi; ++y) {
+      int i0, i1;
+      float l1;
+      bil_index(y, sg.H, dg.H, align != 0, i0, i1, l1);
+      const float wy = (i0 == sy ? 1.f - l1 : 0.f) + (i1 == sy ? l1 : 0.f);
+      if (wy == 0.f) continue;
+      const long long rowp = ((long long)q.n * dg.Hp + y + 1) * dg.Wp + 1;
+      for (int x = xlo; x <= xhi; ++x) {
+        int j0, j1;
+        float m1;
+        bil_index(x, sg.W, dg.W, align != 0, j0, j1, m1);
+        const float wx = (j0 == sx ? 1.f - m1 : 0.f) + (j1 == sx ? m1 : 0.f);
+        if (wx == 0.f) continue;
+        float g[8];
+        unpack8(ldg_nc_v4(dd + ((long long)plane * dd_ps + rowp + x) * 8), g);
+        const float w = wy * wx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaf(w, g[i], a[i]);
+      }
+    }
+    if (mode == 2) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(ds + ((long long)plane * ds_ps + p) * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += r[i];
+    }
+    o = pack8(a);
+  }
+  *reinterpret_cast<uint4*>(ds + ((long long)plane * ds_ps + p) * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase merge (inverse of phase_split, optionally accumulating): 4 x PF8 [N,C,H/2,W/2] -> PF8 [N,C,H,W]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) phase_merge_kernel(const __nv_bfloat16* __restrict__ src, long long src_ps,
+                                                         long long phase_stride, __nv_bfloat16* __restrict__ dst,
+                                                         long long dst_ps, Geo g, int mode) {
+  const int plane = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.P) return;
+  const Pos q = decode_pos(g, p);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (q.px > 0 && q.py > 0) {
+    const int y = q.py - 1, x = q.px - 1;
+    const int Hp2 = g.H / 2 + 1, Wp2 = g.W / 2 + 1;
+    const long long sp = ((long long)q.n * Hp2 + (y >> 1) + 1) * Wp2 + (x >> 1) + 1;
+    o = ldg_nc_v4(src + (long long)((y & 1) * 2 + (x & 1)) * phase_stride + ((long long)plane * src_ps + sp) * 8);
+    if (mode == 2) {
+      float a[8], r[8];
+      unpack8(o, a);
+      unpack8(*reinterpret_cast<const uint4*>(dst + ((long long)plane * dst_ps + p) * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += r[i];
+      o = pack8(a);
+    }
+  }
+  *reinterpret_cast<uint4*>(dst + ((long long)plane * dst_ps + p) * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched weight packing (one launch re-packs every conv of the net after an optimizer step)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_batch_kernel(const hrnb_pack_job* __restrict__ jobs,
+                                                        const int32_t* __restrict__ block_job) {
+  const hrnb_pack_job& j = jobs[block_job[blockIdx.x]];
+  const long long i = (long long)(blockIdx.x - j.block0) * blockDim.x + threadIdx.x;
+  const int ntiles = (j.lcout + j.BN - 1) / j.BN;
+  const long long total = (long long)ntiles * j.BN * j.ntap * j.lcin;
+  float* bias = reinterpret_cast<float*>(j.bias_out);
+  if (bias != nullptr && i < (long long)ntiles * j.BN) {
+    const float* shift = reinterpret_cast<const float*>(j.shift);
+    bias[i] = (i < j.lcout && shift) ? shift[i] : 0.f;
+  }
+  if (i >= total) return;
+  // i = ((((nt*nch + c)*ntap + t)*KC + jj)*BN + n)*8 + e
+  long long r = i;
+  const int e = (int)(r % 8); r /= 8;
+  const int n = (int)(r % j.BN); r /= j.BN;
+  const int jj = (int)(r % j.KC); r /= j.KC;
+  const int t = (int)(r % j.ntap); r /= j.ntap;
+  const int nch = (j.lcin / 8) / j.KC;
+  const int c = (int)(r % nch); r /= nch;
+  const int nt = (int)r;
+  const int lco = nt * j.BN + n;
+  const int lci = (c * j.KC + jj) * 8 + e;
+  const int co = j.transpose ? lci : lco, ci = j.transpose ? lco : lci;
+  float v = 0.f;
+  if (lco < j.lcout && co < j.cout && ci < j.cin) {
+    const float* w = reinterpret_cast<const float*>(j.w);
+    v = w[((long long)co * j.cin + ci) * j.taps_total + j.tap_ids[t]];
+    const float* scale = reinterpret_cast<const float*>(j.scale);
+    if (scale) v *= scale[co];
+  }
+  reinterpret_cast<__nv_bfloat16*>(j.wpk_out)[i] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused Adam over the flat parameter buffer (torch.optim.Adam semantics, L2 weight decay added to the gradient)
+// hyper = [lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, grad_scale]
+// ------------------------------------------------------------------------------------------------
+constexpr int kSegBlockElems = 1024;
+
+__device__ __forceinline__ long long grad_index(const hrnb_param_seg& s, int i) {
+  if (s.taps == 0) return s.g_off + i;
+  const int per_co = s.cin * s.taps;
+  const int co = i / per_co;
+  const int rem = i - co * per_co;
+  const int ci = rem / s.taps;
+  const int t = rem - ci * s.taps;
+  return s.g_off + ((long long)t * s.cin_g + ci) * s.cout + co;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
+                                                  const float* __restrict__ grads, const hrnb_param_seg* __restrict__ segs,
+                                                  const int32_t* __restrict__ block_seg, const float* __restrict__ hyper) {
+  const hrnb_param_seg s = segs[block_seg[blockIdx.x]];
+  if (s.frozen) return;
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6],
+              gs = hyper[7];
+  const int base = (blockIdx.x - s.block0) * kSegBlockElems;
+#pragma unroll
+  for (int u = 0; u < kSegBlockElems / 256; ++u) {
+    const int i = base + u * 256 + threadIdx.x;
+    if (i < s.numel) {
+      const long long pi = s.p_off + i;
+      float p = params[pi];
+      float g = grads[grad_index(s, i)] * gs;
+      g = fmaf(wd, p, g);
+      const float mm = fmaf(b1, m[pi], (1.f - b1) * g);
+      const float vv = fmaf(b2, v[pi], (1.f - b2) * g * g);
+      m[pi] = mm;
+      v[pi] = vv;
+      const float denom = sqrtf(vv) / sqrtf(bc2) + eps;
+      params[pi] = p - (lr / bc1) * (mm / denom);
+    }
+  }
+}
+
+__global__ void adam_tick_kernel(float* hyper, long long* step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long t = *step + 1;
+    *step = t;
+    hyper[5] = (float)(1.0 - pow((double)hyper[1], (double)t));
+    hyper[6] = (float)(1.0 - pow((double)hyper[2], (double)t));
+  }
+}
+
+__global__ void __launch_bounds__(256) grad_to_natural_kernel(const float* __restrict__ grads, float* __restrict__ out,
+                                                             const hrnb_param_seg* __restrict__ segs,
+                                                             const int32_t* __restrict__ block_seg) {
+  const hrnb_param_seg s = segs[block_seg[blockIdx.x]];
+  const int base = (blockIdx.x - s.block0) * kSegBlockElems;
+#pragma unroll
+  for (int u = 0; u < kSegBlockElems / 256; ++u) {
+    const int i = base + u * 256 + threadIdx.x;
+    if (i < s.numel) out[s.p_off + i] = s.frozen ? 0.f : grads[grad_index(s, i)];
+  }
+}
+
+}  // namespace hrnb
+
+using namespace hrnb;
+
+static unsigned reduce_blocks(long long P) {
+  long long b = (P + 256 * 8 - 1) / (256 * 8);   // ~8 positions per thread
+  if (b < 1) b = 1;
+  if (b > 296) b = 296;
+  return (unsigned)b;
+}
+
+extern "C" int hrnb_bn_stats(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* sums,
+                             void* stream) {
+  if (!c || !sums || C % 8 || C <= 0) return fail(HRNB_EINVAL, "bn_stats: bad params");
+  const Geo g = make_geo(N, H, W);
+  dim3 grid(reduce_blocks(g.P), C / 8);
+  bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)c, c_ps, g.P, sums);
+  count_launch();
+  return check_launch("bn_stats_kernel");
+}
+
+extern "C" int hrnb_channel_sum(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* out,
+                                void* stream) {
+  if (!c || !out || C <= 0) return fail(HRNB_EINVAL, "channel_sum: bad params");
+  const Geo g = make_geo(N, H, W);
+  dim3 grid(reduce_blocks(g.P), (C + 7) / 8);
+  channel_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)c, c_ps, g.P, C, out);
+  count_launch();
+  return check_launch("channel_sum_kernel");
+}
+
+extern "C" int hrnb_bn_apply(const hrnb_bn_params* p, void* stream) {
+  if (!p || !p->c || !p->sums || !p->gamma || !p->beta || !p->out || p->C % 8 || p->C <= 0)
+    return fail(HRNB_EINVAL, "bn_apply: bad params");
+  BnK k;
+  k.c = (const __nv_bfloat16*)p->c; k.c_ps = p->c_ps;
+  k.sums = p->sums; k.gamma = p->gamma; k.beta = p->beta;
+  k.res = (const __nv_bfloat16*)p->res; k.res_ps = p->res_ps;
+  k.out = (__nv_bfloat16*)p->out; k.out_ps = p->out_ps;
+  k.running_mean = p->running_mean; k.running_var = p->running_var;
+  if ((k.running_mean == nullptr) != (k.running_var == nullptr)) return fail(HRNB_EINVAL, "bn_apply: running stats must come in pairs");
+  k.g = make_geo(p->N, p->H, p->W);
+  k.relu = p->relu; k.eps = p->eps; k.momentum = p->momentum;
+  k.count = (float)((long long)p->N * p->H * p->W);
+  dim3 grid((unsigned)((k.g.P + 255) / 256), p->C / 8);
+  bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  count_launch();
+  return check_launch("bn_apply_kernel");
+}
+
+static int make_bwd(const hrnb_bn_bwd_params* p, BnBwdK* k) {
+  if (!p || !p->dy || !p->c || !p->sums || !p->gamma || !p->dsums || p->C % 8 || p->C <= 0)
+    return fail(HRNB_EINVAL, "bn_bwd: bad params");
+  if (p->relu && !p->y) return fail(HRNB_EINVAL, "bn_bwd: relu needs the unit output y");
+  k->dy = (const __nv_bfloat16*)p->dy; k->dy_ps = p->dy_ps;
+  k->y = (const __nv_bfloat16*)p->y; k->y_ps = p->y_ps;
+  k->c = (const __nv_bfloat16*)p->c; k->c_ps = p->c_ps;
+  k->sums = p->sums; k->gamma = p->gamma; k->dsums = p->dsums;
+  k->dc = (__nv_bfloat16*)p->dc; k->dc_ps = p->dc_ps;
+  k->dres = (__nv_bfloat16*)p->dres; k->dres_ps = p->dres_ps; k->dres_mode = p->dres ? p->dres_mode : 0;
+  k->dgamma = p->dgamma; k->dbeta = p->dbeta;
+  k->g = make_geo(p->N, p->H, p->W);
+  k->relu = p->relu; k->eps = p->eps;
+  k->count = (float)((long long)p->N * p->H * p->W);
+  return HRNB_OK;
+}
+
+extern "C" int hrnb_bn_bwd_reduce(const hrnb_bn_bwd_params* p, void* stream) {
+  BnBwdK k;
+  const int rc = make_bwd(p, &k);
+  if (rc) return rc;
+  dim3 grid(reduce_blocks(k.g.P), p->C / 8);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  count_launch();
+  return check_launch("bn_bwd_reduce_kernel");
+}
+
+extern "C" int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream) {
+  BnBwdK k;
+  const int rc = make_bwd(p, &k);
+  if (rc) return rc;
+  if (!p->dc) return fail(HRNB_EINVAL, "bn_bwd_apply: dc missing");
+  dim3 grid((unsigned)((k.g.P + 255) / 256), p->C / 8);
+  bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  count_launch();
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int hrnb_fuse_sum_bwd(const void* dy, int64_t dy_ps, const void* y, int64_t y_ps, void* dsrc, int64_t dsrc_ps,
+                                 int32_t N, int32_t H, int32_t W, int32_t C, int32_t shift, int32_t relu, int32_t mode,
+                                 void* stream) {
+  if (!dy || !dsrc || (relu && !y) || C % 8 || shift < 0 || shift > 3 || (mode != 1 && mode != 2) ||
+      (H % (1 << shift)) || (W % (1 << shift)))
+    return fail(HRNB_EINVAL, "fuse_sum_bwd: bad params");
+  FuseBwdK k;
+  k.dy = (const __nv_bfloat16*)dy; k.dy_ps = dy_ps;
+  k.y = (const __nv_bfloat16*)y; k.y_ps = y_ps;
+  k.dsrc = (__nv_bfloat16*)dsrc; k.dsrc_ps = dsrc_ps;
+  k.og = make_geo(N, H, W);
+  k.sg = make_geo(N, H >> shift, W >> shift);
+  k.shift = shift; k.mode = mode; k.relu = relu;
+  dim3 grid((unsigned)((k.sg.P + 255) / 256), C / 8);
+  fuse_sum_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  count_launch();
+  return check_launch("fuse_sum_bwd_kernel");
+}
+
+extern "C" int hrnb_bilinear_up_bwd(const void* d_dst, int64_t d_dst_ps, int32_t N, int32_t C, int32_t dH, int32_t dW,
+                                    void* d_src, int64_t d_src_ps, int32_t sH, int32_t sW, int32_t align_corners,
+                                    int32_t mode, void* stream) {
+  if (!d_dst || !d_src || C % 8 || (mode != 1 && mode != 2)) return fail(HRNB_EINVAL, "bilinear_bwd: bad params");
+  const Geo dg = make_geo(N, dH, dW), sg = make_geo(N, sH, sW);
+  dim3 grid((unsigned)((sg.P + 255) / 256), C / 8);
+  bilinear_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_dst, d_dst_ps, dg,
+                                                               (__nv_bfloat16*)d_src, d_src_ps, sg, align_corners, mode);
+  count_launch();
+  return check_launch("bilinear_bwd_kernel");
+}
+
+extern "C" int hrnb_phase_merge(const void* src, int64_t src_ps, int64_t phase_stride, void* dst, int64_t dst_ps, int32_t N,
+                                int32_t C, int32_t H, int32_t W, int32_t mode, void* stream) {
+  if (!src || !dst || C % 8 || (H & 1) || (W & 1) || phase_stride <= 0 || (mode != 1 && mode != 2))
+    return fail(HRNB_EINVAL, "phase_merge: bad params");
+  const Geo g = make_geo(N, H, W);
+  dim3 grid((unsigned)((g.P + 255) / 256), C / 8);
+  phase_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ps, phase_stride,
+                                                              (__nv_bfloat16*)dst, dst_ps, g, mode);
+  count_launch();
+  return check_launch("phase_merge_kernel");
+}
+
+extern "C" int hrnb_pack_conv_weights_batch(const hrnb_pack_job* jobs_dev, const int32_t* block_job_dev, int32_t nblocks,
+                                            void* stream) {
+  if (!jobs_dev || !block_job_dev || nblocks <= 0) return fail(HRNB_EINVAL, "pack_batch: bad params");
+  pack_batch_kernel<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, block_job_dev);
+  count_launch();
+  return check_launch("pack_batch_kernel");
+}
+
+extern "C" int hrnb_adam_step(float* params, float* m, float* v, const float* grads, const hrnb_param_seg* segs_dev,
+                              const int32_t* block_seg_dev, int32_t nblocks, const float* hyper_dev, void* stream) {
+  if (!params || !m || !v || !grads || !segs_dev || !block_seg_dev || !hyper_dev || nblocks <= 0)
+    return fail(HRNB_EINVAL, "adam: bad params");
+  adam_kernel<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(params, m, v, grads, segs_dev, block_seg_dev, hyper_dev);
+  count_launch();
+  return check_launch("adam_kernel");
+}
+
+extern "C" int hrnb_adam_tick(float* hyper_dev, int64_t* step_dev, void* stream) {
+  if (!hyper_dev || !step_dev) return fail(HRNB_EINVAL, "adam_tick: null pointer");
+  adam_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hyper_dev, (long long*)step_dev);
+  count_launch();
+  return check_launch("adam_tick_kernel");
+}
+
+extern "C" int hrnb_grad_to_natural(const float* grads, float* out, const hrnb_param_seg* segs_dev,
+                                    const int32_t* block_seg_dev, int32_t nblocks, void* stream) {
+  if (!grads || !out || !segs_dev || !block_seg_dev || nblocks <= 0) return fail(HRNB_EINVAL, "grad_to_natural: bad params");
+  grad_to_natural_kernel<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(grads, out, segs_dev, block_seg_dev);
+  count_launch();
+  return check_launch("grad_to_natural_kernel");
+}

@@ -1,0 +1,109 @@
+"""Flat fp32 parameter / gradient / Adam-moment buffers of the training path.
+
+Every nn.Parameter of the network becomes a view into ONE flat fp32 buffer (so the optimizer is a single kernel and
+the data-parallel gradient exchange a single all-reduce); gradients live in a second flat buffer in the layout the
+wgrad kernel produces ([tap][cin][cout] for conv weights, natural for 1-D tensors) and are mapped back to the natural
+parameter layout only when the nn.Module's `.grad` is asked for.  Optimizer semantics: torch.optim.Adam with L2
+weight decay, as `get_optimizer` builds it in the reference (lib/utils/utils.py:71-92, lr 1e-3, wd 1e-4)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ParamSeg
+
+SEG_BLOCK = 1024
+
+
+class FlatParams:
+    def __init__(self, params, conv_meta=None, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+        """params: list of nn.Parameter (CUDA fp32); conv_meta: {index: (cout, cin, cin_g, taps)} for conv weights
+        whose gradient is produced in [tap][cin_g][cout] layout (natural layout [cout][cin][taps])."""
+        self.params = list(params)
+        conv_meta = conv_meta or {}
+        dev = self.params[0].device
+        self.device = dev
+        p_off, g_off, block0 = 0, 0, 0
+        segs = (ParamSeg * len(self.params))()
+        block_seg = []
+        self.p_offs, self.g_offs, self.g_shapes = [], [], []
+        for i, p in enumerate(self.params):
+            assert p.is_cuda and p.dtype == torch.float32
+            n = p.numel()
+            s = segs[i]
+            s.p_off, s.g_off, s.numel = p_off, g_off, n
+            if i in conv_meta:
+                cout, cin, cin_g, taps = conv_meta[i]
+                assert cout * cin * taps == n, (i, conv_meta[i], n)
+                s.cout, s.cin, s.cin_g, s.taps = cout, cin, cin_g, taps
+                gn, gshape = taps * cin_g * cout, (taps, cin_g, cout)
+            else:
+                s.cout = s.cin = s.cin_g = s.taps = 0
+                gn, gshape = n, tuple(p.shape)
+            s.block0 = block0
+            s.frozen = 0 if p.requires_grad else 1
+            nb = max(1, (n + SEG_BLOCK - 1) // SEG_BLOCK)
+            block_seg.append(np.full(nb, i, dtype=np.int32))
+            block0 += nb
+            self.p_offs.append(p_off)
+            self.g_offs.append(g_off)
+            self.g_shapes.append(gshape)
+            p_off += (n + 3) // 4 * 4
+            g_off += (gn + 3) // 4 * 4
+        self.n_params, self.n_grads, self.nblocks = p_off, g_off, block0
+        self.data = torch.zeros(p_off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.data)
+        self.v = torch.zeros_like(self.data)
+        self.grads = torch.zeros(g_off, dtype=torch.float32, device=dev)
+        self._natural = None
+        with torch.no_grad():
+            for p, off in zip(self.params, self.p_offs):
+                view = self.data[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        raw = np.frombuffer(bytes(segs), dtype=np.uint8).copy()
+        self.segs_dev = torch.from_numpy(raw).to(dev)
+        self.block_seg_dev = torch.from_numpy(np.concatenate(block_seg)).to(dev)
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 1.0, 1.0, grad_scale], dtype=torch.float32,
+                                  device=dev)
+        self.step = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    # ---- views ----------------------------------------------------------------------------------------------
+    def grad_view(self, i):
+        """the gradient segment of parameter i in the layout the kernels write"""
+        shape = self.g_shapes[i]
+        n = int(np.prod(shape)) if len(shape) else 1
+        return self.grads[self.g_offs[i]:self.g_offs[i] + n].view(shape)
+
+    def set_lr(self, lr):
+        self.hyper[0] = lr
+
+    def set_grad_scale(self, s):
+        self.hyper[7] = s
+
+    def set_grad_from_natural(self, i, g):
+        """test helper: store a natural-layout gradient into the kernel layout"""
+        gv = self.grad_view(i)
+        s = ParamSeg.from_buffer_copy(self.segs_dev[i * C.sizeof(ParamSeg):(i + 1) * C.sizeof(ParamSeg)].cpu().numpy().tobytes())
+        if s.taps == 0:
+            gv.copy_(g.reshape(gv.shape))
+        else:
+            gv.zero_()
+            gv[:, :s.cin, :].copy_(g.reshape(s.cout, s.cin, s.taps).permute(2, 1, 0))
+
+    # ---- kernels --------------------------------------------------------------------------------------------
+    def adam_step(self):
+        lib = _lib.lib()
+        _lib.check(lib.hrnb_adam_tick(self.hyper.data_ptr(), self.step.data_ptr(), _lib.stream_ptr()))
+        _lib.check(lib.hrnb_adam_step(self.data.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.grads.data_ptr(),
+                                      self.segs_dev.data_ptr(), self.block_seg_dev.data_ptr(), self.nblocks,
+                                      self.hyper.data_ptr(), _lib.stream_ptr()))
+
+    def natural_grads(self):
+        """list of gradient tensors in the parameters' own layout (views of one flat buffer, overwritten per call)"""
+        if self._natural is None:
+            self._natural = torch.zeros_like(self.data)
+        _lib.check(_lib.lib().hrnb_grad_to_natural(self.grads.data_ptr(), self._natural.data_ptr(), self.segs_dev.data_ptr(),
+                                                   self.block_seg_dev.data_ptr(), self.nblocks, _lib.stream_ptr()))
+        return [self._natural[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.p_offs)]

@@ -6,7 +6,7 @@ import torch
 
 from . import _lib
 from ._lib import (ConvParams, FuseParams, HRNB_CONV_GATHER, HRNB_CONV_IN_PHASES, HRNB_CONV_OUT_NCHW,
-                   HRNB_CONV_OUT_PHASES, HRNB_CONV_RELU)
+                   HRNB_CONV_OUT_PHASES, HRNB_CONV_RELU, PackJob)
 from .pf8 import PF8, PhasePF8
 
 NUM_SMS = 148
@@ -37,10 +37,13 @@ def pick_bn(cout):
     return bn_candidates(cout)[0]
 
 
-def _smem_bytes(W, taps, mode, bn, mb, kc):
-    """mode: 1 flat-shift, 2 gather (stride 2 or forced), 4 flat-shift over 4 input phases (stride 2)"""
+def _smem_bytes(W, taps, mode, bn, mb, kc, custom=None):
+    """mode: 1 flat-shift, 2 gather (stride 2 or forced), 4 flat-shift over 4 input phases (stride 2);
+    custom = (extra halo rows, sources) of a custom tap table"""
     gather = mode == 2
-    if mode == 4:
+    if custom is not None:
+        halo, nsrc = 128 * mb + custom[0], custom[1]
+    elif mode == 4:
         halo, nsrc = 128 * mb + W + 2, 4
     else:
         halo, nsrc = 128 * mb + (2 * (W + 2) if (taps == 9 and not gather) else 0), 1
@@ -49,20 +52,22 @@ def _smem_bytes(W, taps, mode, bn, mb, kc):
     return 3328 + (5 if gather else 2) * a_stage + 2 * b_stage
 
 
-def _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kc):
+def _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kc, custom=None):
     """Rough cycle model of one conv launch for tile shape (bn, mb, kc): per-tile cost = max(tensor pipe incl. the
     shared-memory operand fetch and the per-chunk hand-off stalls, HBM/L2 bytes), times the tile rounds on 148 SMs."""
     mblocks = (P + 127) // 128
     tiles = (mblocks + mb - 1) // mb * (cout // bn if cout % 16 == 0 else 1)
     gather = mode == 2
-    smem = _smem_bytes(W, taps, mode, bn, mb, kc)
+    smem = _smem_bytes(W, taps, mode, bn, mb, kc, custom)
     if smem > 200 * 1024:
         return None
     ksteps = taps * cin // 16
     nchunks = (cin // 8) // kc
     handoffs = nchunks * (taps if gather else 1)
     mma = ksteps * mb * max(bn / 2.0, (4096 + bn * 32) / 128.0) * 1.3 + 300.0 * handoffs + 400.0
-    if mode == 4:
+    if custom is not None:
+        a_bytes = custom[1] * (128 * mb + custom[0]) * cin * 2
+    elif mode == 4:
         a_bytes = 4 * (128 * mb + W + 2) * cin * 2
     elif gather:
         a_bytes = 128 * mb * taps * cin * 2 * 2        # 9 taps, half-used 32-byte sectors
@@ -74,7 +79,7 @@ def _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kc):
     return rounds * cost + 4500.0
 
 
-def pick_tile(P, W, cin, cout, taps, mode, has_res, kc=None):
+def pick_tile(P, W, cin, cout, taps, mode, has_res, kc=None, custom=None):
     """-> (BN, MB, KC) minimising the launch-time model"""
     env_mb, env_bn, env_kc = os.environ.get("HRNB_MB"), os.environ.get("HRNB_BN"), os.environ.get("HRNB_KC")
     best = None
@@ -88,7 +93,7 @@ def pick_tile(P, W, cin, cout, taps, mode, has_res, kc=None):
             if mb * bn > 256 or (env_mb and mb != int(env_mb) and int(env_mb) * bn <= 256):
                 continue
             for kcc in kcs:
-                t = _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kcc)
+                t = _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kcc, custom)
                 if t is not None and (best is None or t < best[0]):
                     best = (t, bn, mb, kcc)
     if best is None:
@@ -103,15 +108,31 @@ class ConvLayer:
     Weights are packed lazily per N-tile width (the tile shape depends on the batch/resolution it runs at).
     """
 
-    def __init__(self, weight, scale=None, shift=None, stride=1, relu=False, out_nchw=False, kc=None, bn=None):
+    def __init__(self, weight, scale=None, shift=None, stride=1, relu=False, out_nchw=False, kc=None, bn=None,
+                 transpose=False, tap_ids=None, custom_taps=None, cin_pad=None, repacker=None):
+        """General form (training path): `transpose` swaps the channel roles (data-gradient conv), `tap_ids` selects /
+        reorders source taps, `custom_taps` = [(src, dpos)] gives the flat-shift geometry per logical tap
+        (include/hrnb.h: ntap_custom), `cin_pad` zero-pads the logical input channels to a multiple of 16.  `weight`
+        is NOT copied in the general form: packs are refreshed from it by `repacker.run()` after optimizer steps."""
         assert weight.is_cuda and weight.dtype == torch.float32
         cout, cin, kh, kw = weight.shape
         assert kh == kw and kh in (1, 3)
-        self.cout, self.cin, self.taps, self.stride = cout, cin, kh * kw, stride
+        self.src_cout, self.src_cin, self.src_taps = cout, cin, kh * kw
+        self.transpose, self.tap_ids, self.custom_taps, self.repacker = transpose, tap_ids, custom_taps, repacker
+        self.general = transpose or tap_ids is not None or custom_taps is not None or cin_pad is not None or repacker is not None
+        if transpose:
+            cout, cin = cin, cout
+        if cin_pad is not None:
+            cin = cin_pad
+        ntap = len(tap_ids) if tap_ids is not None else kh * kw
+        if custom_taps is not None:
+            assert len(custom_taps) == ntap and stride == 1
+        self.cout, self.cin, self.taps, self.stride = cout, cin, ntap, stride
         self.relu, self.out_nchw = relu, out_nchw
         self.fixed_kc = kc
         self.fixed_bn = bn
-        self.w = weight.contiguous()
+        self.w = weight if self.general else weight.contiguous()
+        assert self.w.is_contiguous()
         self.sc = scale.contiguous().float() if scale is not None else None
         self.sh = shift.contiguous().float() if shift is not None else None
         self.packs = {}
@@ -125,6 +146,22 @@ class ConvLayer:
             dev = self.w.device
             wpk = torch.empty(n_tiles * bn * self.taps * self.cin, dtype=torch.bfloat16, device=dev)
             bias = torch.empty(n_tiles * bn, dtype=torch.float32, device=dev)
+            if self.general:
+                job = PackJob()
+                job.w, job.scale = self.w.data_ptr(), (self.sc.data_ptr() if self.sc is not None else None)
+                job.shift = self.sh.data_ptr() if self.sh is not None else None
+                job.wpk_out, job.bias_out = wpk.data_ptr(), bias.data_ptr()
+                job.cout, job.cin, job.taps_total = self.src_cout, self.src_cin, self.src_taps
+                job.transpose, job.lcout, job.lcin, job.ntap = int(self.transpose), self.cout, self.cin, self.taps
+                for t in range(self.taps):
+                    job.tap_ids[t] = self.tap_ids[t] if self.tap_ids is not None else t
+                job.KC, job.BN = kc, bn
+                rp = self.repacker or Repacker(dev)
+                rp.add(job, n_tiles * bn * self.taps * self.cin)
+                if self.repacker is None:
+                    rp.run()
+                self.packs[(bn, kc)] = (wpk, bias)
+                return self.packs[(bn, kc)]
             _lib.check(_lib.lib().hrnb_pack_conv_weights(
                 self.w.data_ptr(), self.sc.data_ptr() if self.sc is not None else None,
                 self.sh.data_ptr() if self.sh is not None else None, self.cout, self.cin, self.taps, kc, bn,
@@ -141,7 +178,11 @@ class ConvLayer:
             mode = 4
         else:
             mode = 2 if (self.stride == 2 or self.force_gather) else 1
-        tbn, tmb, tkc = pick_tile(P, W, self.cin, self.cout, self.taps, mode, res is not None, kc or self.fixed_kc)
+        custom = None
+        if self.custom_taps is not None:
+            dps = [d for _, d in self.custom_taps]
+            custom = (max(0, max(dps)) - min(0, min(dps)), max(s_ for s_, _ in self.custom_taps) + 1)
+        tbn, tmb, tkc = pick_tile(P, W, self.cin, self.cout, self.taps, mode, res is not None, kc or self.fixed_kc, custom)
         bn = bn or self.fixed_bn or tbn
         if mb is None:
             mb = tmb if bn == tbn else 1
@@ -151,7 +192,7 @@ class ConvLayer:
         lib = _lib.lib()
         if bn != tbn or mb != tmb:      # forced shape: take the largest K chunk that fits
             for cand in ([kc] if (kc and self.fixed_kc) else kc_candidates(self.cin)):
-                if _smem_bytes(W, self.taps, mode, bn, mb, cand) <= 200 * 1024:
+                if _smem_bytes(W, self.taps, mode, bn, mb, cand, custom) <= 200 * 1024:
                     kc = cand
                     break
         wpk, bias = self.pack(bn, kc)
@@ -177,6 +218,10 @@ class ConvLayer:
             flags = (flags & ~HRNB_CONV_GATHER) | HRNB_CONV_IN_PHASES
         if out_ph:
             flags |= HRNB_CONV_OUT_PHASES
+        if self.custom_taps is not None:
+            p.ntap_custom = self.taps
+            for t, (src, dpos) in enumerate(self.custom_taps):
+                p.tap_src[t], p.tap_dpos[t] = src, dpos
         p.flags = flags
         while p.MB > 1 and lib.hrnb_conv_smem_bytes(C.byref(p)) < 0:
             p.MB //= 2          # tile does not fit in shared memory at this MB
@@ -187,6 +232,41 @@ class ConvLayer:
         p = self.params(x, out, res, mb, bn, out2=out2)
         _lib.check(_lib.lib().hrnb_conv(C.byref(p), _lib.stream_ptr()))
         return out
+
+
+class Repacker:
+    """Collects hrnb_pack_job records and (re)packs all of them with ONE launch of hrnb_pack_conv_weights_batch."""
+
+    def __init__(self, device):
+        self.device = device
+        self.jobs, self.sizes = [], []
+        self._dev = None
+
+    def add(self, job, total_elems):
+        self.jobs.append(job)
+        self.sizes.append(int(total_elems))
+        self._dev = None
+
+    def _upload(self):
+        import numpy as np
+        block_job, b0 = [], 0
+        arr = (PackJob * len(self.jobs))()
+        for i, (job, n) in enumerate(zip(self.jobs, self.sizes)):
+            nb = (n + 255) // 256
+            job.block0 = b0
+            C.memmove(C.byref(arr, i * C.sizeof(PackJob)), C.byref(job), C.sizeof(PackJob))
+            block_job.append(np.full(nb, i, dtype=np.int32))
+            b0 += nb
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self._dev = (torch.from_numpy(raw).to(self.device), torch.from_numpy(np.concatenate(block_job)).to(self.device), b0)
+
+    def run(self):
+        if not self.jobs:
+            return
+        if self._dev is None:
+            self._upload()
+        jobs, bmap, nb = self._dev
+        _lib.check(_lib.lib().hrnb_pack_conv_weights_batch(jobs.data_ptr(), bmap.data_ptr(), nb, _lib.stream_ptr()))
 
 
 def fuse_sum(srcs, shifts, out, relu=True):

@@ -29,7 +29,7 @@ extern "C" {
 #define HRNB_EINVAL (-1)  /* bad argument / unsupported shape */
 #define HRNB_ECUDA (-2)   /* CUDA runtime error (message in hrnb_last_error) */
 
-#define HRNB_ABI_VERSION 1
+#define HRNB_ABI_VERSION 2
 
 /* guard bands (in positions) a PF8 plane must carry around [0, P) */
 #define HRNB_GUARD_LEAD(Wp) ((((Wp) + 2) + 7) / 8 * 8)
@@ -78,6 +78,14 @@ typedef struct hrnb_conv_params {
   void* out2;                /* optional: ALSO write the output phase-split here (NULL = off)               */
   int64_t out2_ps;
   int64_t out2_phase_stride;
+  /* Custom tap table (flat-shift path only; ntap_custom == 0 = the standard 1x1 / 3x3 geometry above).
+   * The conv becomes out[p] = sum_t W_t * in_{tap_src[t]}[p + tap_dpos[t]] on the OUTPUT position grid
+   * (stride must be 1, taps == ntap_custom, 1..9); source s is the tensor `in + s*in_phase_stride`.
+   * This is how the data-gradient of a 3x3 stride-2 conv is expressed per input phase (transposed weights
+   * packed with hrnb_pack_conv_weights_batch). */
+  int32_t ntap_custom;
+  int32_t tap_src[9];
+  int32_t tap_dpos[9];
 } hrnb_conv_params;
 
 int hrnb_conv(const hrnb_conv_params* p, void* stream);
@@ -177,6 +185,138 @@ int hrnb_loss_heatmap(const float* pred, const float* gt, int32_t BJ, int32_t hw
  * is NULL.  d_pred (NULL to skip) [B*J*2]. */
 int hrnb_loss_pose2d(const float* pred, const float* gt, const float* vis, int32_t B, int32_t J, float* loss,
                      float* d_pred, void* stream);
+
+
+/* =============================== training path ================================================= */
+/* The reference trains through autograd (loss.backward() + optimizer.step(), lib/core/function.py:101-106).
+ * The functions below are the hand-written forward (batch-statistics BN) and backward of the same layers. */
+
+/* ---- weight gradient of a conv (tcgen05, both operands straight from PF8) ---------------------- */
+/* dw[tap_id[t]][ci][co] += sum_p dy[p][co] * x[p + tap_dpos[t]][ci]   for t < ntap  (fp32, accumulated with
+ * red.global.add: zero dw before the first launch of a step).  The gradient layout is [taps_total][cin][cout];
+ * hrnb_adam_step / hrnb_grad_to_natural read it through hrnb_param_seg.  dy: PF8 with ceil(cout/8) planes on the
+ * conv's OUTPUT grid [N,H,W] (zero padding / guards as always); x: PF8 input on the SAME grid: the conv input itself
+ * for stride 1 (3x3: tap_dpos = (r-1)*(W+1) + (s-1)), one phase tensor of it for stride-2 convs (tap (r,s) of a
+ * 3x3 stride-2 conv reads phase (r != 1, s != 1) at dpos = -(r == 0)*(W+1) - (s == 0): one launch per phase).
+ * Replaces the weight-gradient half of nn.Conv2d's backward for lib/models/pose_hrnet.py:28-98,187-242,335-350,419-458. */
+typedef struct hrnb_wgrad_params {
+  const void* dy;
+  int64_t dy_ps;
+  const void* x;
+  int64_t x_ps;
+  float* dw;
+  int32_t N, H, W;
+  int32_t cin;           /* multiple of 16 (gradient rows per tap)                                  */
+  int32_t cout;          /* real output channels (row length of dw)                                 */
+  int32_t ntap;
+  int32_t tap_dpos[9];
+  int32_t tap_id[9];
+  int32_t NT, TG, KP, ksplit; /* tile overrides: cin tile, taps per CTA, positions per stage, K splits; 0 = auto */
+} hrnb_wgrad_params;
+int hrnb_wgrad(const hrnb_wgrad_params* p, void* stream);
+int64_t hrnb_wgrad_smem_bytes(const hrnb_wgrad_params* p);
+
+/* ---- batched weight packing (forward and data-gradient orientation) ---------------------------- */
+/* One job = one packed copy of one OIHW fp32 weight tensor w[cout][cin][taps_total].  The logical conv it feeds has
+ * lcout x lcin channels (lcin a multiple of 16, zero padded) and ntap taps, logical tap t = source tap tap_ids[t];
+ * transpose != 0 swaps the channel roles (logical cout = source cin): with tap_ids reversed this is the
+ * data-gradient conv of a stride-1 3x3 conv.  Output order as hrnb_pack_conv_weights ([ntile][chunk][tap][KC][BN][8]).
+ * `jobs` and `block_job` (job index of every 256-thread block; job j owns blocks [block0, block0 + ceil(total/256)))
+ * live in DEVICE memory.  All pointers inside a job are device pointers. */
+typedef struct hrnb_pack_job {
+  const void* w;
+  const void* scale;     /* per source-cout scale or NULL                                            */
+  const void* shift;     /* bias source [lcout] or NULL (-> zeros)                                   */
+  void* wpk_out;
+  void* bias_out;        /* [ntiles*BN] fp32 or NULL                                                 */
+  int32_t cout, cin, taps_total;
+  int32_t transpose;
+  int32_t lcout, lcin;
+  int32_t ntap;
+  int32_t tap_ids[9];
+  int32_t KC, BN;
+  int32_t block0;
+  int32_t pad_;
+} hrnb_pack_job;
+int hrnb_pack_conv_weights_batch(const hrnb_pack_job* jobs_dev, const int32_t* block_job_dev, int32_t nblocks,
+                                 void* stream);
+
+/* ---- BatchNorm2d, train mode (momentum / eps as nn.BatchNorm2d) -------------------------------- */
+/* sums[c][0] += sum x, sums[c][1] += sum x^2 over the N*H*W real positions of PF8 tensor c (zero sums first). */
+int hrnb_bn_stats(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* sums, void* stream);
+/* out[c] += sum over positions (bias gradient of the BN-less final conv). */
+int hrnb_channel_sum(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);
+
+typedef struct hrnb_bn_params {
+  const void* c;          /* conv output (pre-BN), PF8                                               */
+  int64_t c_ps;
+  const float* sums;      /* [C][2] from hrnb_bn_stats                                                */
+  const float* gamma;     /* [C]                                                                      */
+  const float* beta;      /* [C]                                                                      */
+  const void* res;        /* optional residual added after the normalisation, PF8 (NULL = none)       */
+  int64_t res_ps;
+  void* out;              /* PF8: [relu](bn(c) + res), zeros at padding                               */
+  int64_t out_ps;
+  float* running_mean;    /* updated in place with the batch mean / unbiased variance (NULL = skip)   */
+  float* running_var;
+  int32_t N, C, H, W;
+  int32_t relu;
+  float eps, momentum;
+} hrnb_bn_params;
+int hrnb_bn_apply(const hrnb_bn_params* p, void* stream);
+
+typedef struct hrnb_bn_bwd_params {
+  const void* dy;         /* gradient of the unit output, PF8                                         */
+  int64_t dy_ps;
+  const void* y;          /* unit output (ReLU mask y > 0); NULL when relu == 0                       */
+  int64_t y_ps;
+  const void* c;          /* conv output saved by the forward pass                                    */
+  int64_t c_ps;
+  const float* sums;      /* forward statistics [C][2]                                                */
+  const float* gamma;
+  float* dsums;           /* [C][2] workspace, zeroed by the caller, filled by hrnb_bn_bwd_reduce     */
+  void* dc;               /* gradient w.r.t. the conv output (may alias dy)                           */
+  int64_t dc_ps;
+  void* dres;             /* gradient buffer of the residual input or NULL                            */
+  int64_t dres_ps;
+  int32_t dres_mode;      /* 1 = write g, 2 = accumulate g   (g = dy * relu mask)                     */
+  float* dgamma;          /* [C] written (sum g*xhat)                                                 */
+  float* dbeta;           /* [C] written (sum g)                                                      */
+  int32_t N, C, H, W;
+  int32_t relu;
+  float eps;
+} hrnb_bn_bwd_params;
+int hrnb_bn_bwd_reduce(const hrnb_bn_bwd_params* p, void* stream);
+int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream);
+
+/* ---- backward of hrnb_fuse_sum / hrnb_bilinear_up / hrnb_phase_split ---------------------------- */
+/* dsrc[q] (=|+=) sum over the 2^shift x 2^shift block of dy * (y > 0) (mode 1 write, 2 accumulate); dy, y on the
+ * fused output grid [N,H,W], dsrc on [N, H>>shift, W>>shift]. */
+int hrnb_fuse_sum_bwd(const void* dy, int64_t dy_ps, const void* y, int64_t y_ps, void* dsrc, int64_t dsrc_ps, int32_t N,
+                      int32_t H, int32_t W, int32_t C, int32_t shift, int32_t relu, int32_t mode, void* stream);
+int hrnb_bilinear_up_bwd(const void* d_dst, int64_t d_dst_ps, int32_t N, int32_t C, int32_t dH, int32_t dW, void* d_src,
+                         int64_t d_src_ps, int32_t sH, int32_t sW, int32_t align_corners, int32_t mode, void* stream);
+int hrnb_phase_merge(const void* src_phase00, int64_t src_ps, int64_t phase_stride, void* dst, int64_t dst_ps, int32_t N,
+                     int32_t C, int32_t H, int32_t W, int32_t mode, void* stream);
+
+/* ---- fused Adam over flat fp32 parameter / moment buffers (lib/utils/utils.py:71-92: torch.optim.Adam, L2 decay) */
+typedef struct hrnb_param_seg {
+  int64_t p_off;          /* offset of the tensor in the flat param / m / v buffers (natural layout)  */
+  int64_t g_off;          /* offset of its gradient in the flat gradient buffer                       */
+  int32_t numel;
+  int32_t cout, cin, cin_g, taps; /* conv weights: natural [cout][cin][taps], gradient [taps][cin_g][cout]; taps == 0: 1-D */
+  int32_t block0;         /* first 1024-element block of this tensor in the block map                 */
+  int32_t frozen;         /* requires_grad == False                                                   */
+  int32_t pad_;
+} hrnb_param_seg;
+/* hyper_dev = [lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, grad_scale] (device floats) */
+int hrnb_adam_step(float* params, float* m, float* v, const float* grads, const hrnb_param_seg* segs_dev,
+                   const int32_t* block_seg_dev, int32_t nblocks, const float* hyper_dev, void* stream);
+/* step += 1 and refresh bias_corr1/2 in hyper_dev */
+int hrnb_adam_tick(float* hyper_dev, int64_t* step_dev, void* stream);
+/* gradient buffer ([tap][cin][cout] conv layout) -> natural parameter layout (for .grad of the nn.Module) */
+int hrnb_grad_to_natural(const float* grads, float* out, const hrnb_param_seg* segs_dev, const int32_t* block_seg_dev,
+                         int32_t nblocks, void* stream);
 
 /* ---- misc --------------------------------------------------------------------------------------- */
 const char* hrnb_last_error(void);
