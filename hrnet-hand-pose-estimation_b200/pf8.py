@@ -5,10 +5,27 @@ p = (n*(H+1) + y+1)*(W+1) + x+1 ; row 0 / column 0 of every image are shared zer
 Each plane carries zero guard bands so the conv's halo loads never leave the allocation.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
+
+_CANARY = int(os.environ.get("HRNB_CANARY", "0"))    # debug: NaN margins (elements) around every PF8 allocation
+
+
+def _alloc(shape, device):
+    """zero-filled bf16 buffer; with HRNB_CANARY=n it sits between two n-element NaN margins so that any kernel
+    reading outside a PF8 allocation produces NaNs deterministically (debug aid, tools/train_small.py)"""
+    if not _CANARY:
+        return torch.zeros(shape, dtype=torch.bfloat16, device=device)
+    n = 1
+    for d in shape:
+        n *= d
+    raw = torch.full((n + 2 * _CANARY,), float("nan"), dtype=torch.bfloat16, device=device)
+    body = raw[_CANARY:_CANARY + n]
+    body.zero_()
+    return body.view(shape)
 
 
 class PF8:
@@ -24,7 +41,7 @@ class PF8:
         tail = _lib.guard_tail(self.Wp)
         self.ps = self.lead + (self.P + 7) // 8 * 8 + tail
         if buf is None:
-            buf = torch.zeros((planes_total or self.planes, self.ps, 8), dtype=torch.bfloat16, device=device)
+            buf = _alloc((planes_total or self.planes, self.ps, 8), device)
         self.buf = buf
         self._ptr = buf.data_ptr() + (plane_offset * self.ps + self.lead) * 16
 
@@ -93,7 +110,7 @@ class PhasePF8:
         g.lead = _lib.guard_lead(g.Wp)
         g.ps = g.lead + (g.P + 7) // 8 * 8 + _lib.guard_tail(g.Wp)
         self.half = g
-        self.buf = torch.zeros((4, g.planes, g.ps, 8), dtype=torch.bfloat16, device=device)
+        self.buf = _alloc((4, g.planes, g.ps, 8), device)
         self.phase_stride = g.planes * g.ps * 8
         self._ptr = self.buf.data_ptr() + g.lead * 16
 

@@ -1,0 +1,580 @@
+"""Training engine: forward with batch-statistics BatchNorm, the fused heat-map / pose2d losses, the full backward
+pass (data- and weight-gradients of all 307 convs, BN / fuse / bilinear / softmax backward) and the fused Adam step,
+as launch plans over libhrnb.so.  Host side only: every number is produced by the CUDA kernels.
+
+What it replaces in the reference (file:line relative to the reference repo):
+  model.train() forward            lib/models/pose_hrnet.py:511-568 / pose_hrnet_softmax.py:449-528 (BN in train mode)
+  get_final_preds(use_softmax)     lib/utils/heatmap_decoding.py:87-101 (soft-argmax inside the step)
+  AverageMeter.computeLosses       lib/core/function.py:1334-1344  (total = f_hm * HeatmapLoss + f_p2d * JointsMSELoss)
+  total_loss.backward()            lib/core/function.py:101-106    (autograd; here hand-written kernels)
+  optimizer.step() (Adam, L2 wd)   lib/utils/utils.py:71-92
+
+A `TrainPlan` is built for one (batch, H, W): forward ops are recorded in order together with a "tape" of backward
+builders; the backward launch list is generated from the tape in reverse, deciding per gradient buffer whether a
+kernel writes (first contribution) or accumulates (later ones).  Each unit conv -> BN -> (+residual) -> ReLU keeps its
+conv output `c` and its output `y` (bf16 PF8) for the backward pass; gradients are bf16 PF8, parameter gradients fp32.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, arch as A, tops
+from .flat import FlatParams
+from .ops import ConvLayer, PF8, PhasePF8, Repacker
+
+
+class T:
+    """activation node: value + (lazily allocated) gradient buffer"""
+    __slots__ = ("v", "g", "ginit")
+
+    def __init__(self, v, g=None):
+        self.v, self.g, self.ginit = v, g, False
+
+
+def _like(v, device):
+    if isinstance(v, PhasePF8):
+        return PhasePF8(v.N, v.C, v.H, v.W, device=device)
+    return PF8(v.N, v.C, v.H, v.W, device=device)
+
+
+def _phase_view(ph, i):
+    g = ph.half
+    return PF8(g.N, g.C, g.H, g.W, buf=ph.buf[i])
+
+
+class TrainPlan:
+    def __init__(self, eng, B, H, W):
+        self.eng, self.B, self.H, self.W = eng, B, H, W
+        self.dev = eng.device
+        self.fwd, self.loss_steps, self.bwd = [], [], []
+        self.bwd_names, self.fwd_names, self._ctx = [], [], ""
+        self.all_bufs = []      # every activation / gradient buffer of the plan: the launch parameter structs hold raw
+                                # device pointers only, so the plan must own the tensors for as long as it can be replayed
+        self.tape = []
+        self.keep = []
+        self.n_launch = {"fwd": 0, "loss": 0, "bwd": 0}
+        self.act_bytes = 0
+        self.x = torch.zeros((B, 3, H, W), dtype=torch.float32, device=self.dev)
+        self.graphs = {}
+        self.conv_out = {}      # conv key -> PF8 conv output (pre-BN) kept for the backward pass
+        self._build()
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    def _buf(self, C_, H, W):
+        t = PF8(self.B, C_, H, W, device=self.dev)
+        self.act_bytes += t.buf.numel() * 2
+        self.all_bufs.append(t)
+        return t
+
+    def _grad(self, t):
+        if t.g is None:
+            t.g = _like(t.v, self.dev)
+            self.act_bytes += t.g.buf.numel() * 2
+            self.all_bufs.append(t.g)
+        return t.g
+
+    def _f(self, fn, name=""):
+        self.fwd.append(fn)
+        self.fwd_names.append(name or self._ctx)
+        self.n_launch["fwd"] += 1
+
+    def _b(self, fn, name=""):
+        self.bwd.append(fn)
+        self.bwd_names.append(name or self._ctx)
+        self.n_launch["bwd"] += 1
+
+    def _conv_fn(self, layer, x, out, res=None):
+        p = layer.params(x, out, res)
+        self.keep.append(p)
+        lib, ref = _lib.lib(), C.byref(p)
+        return lambda: _lib.check(lib.hrnb_conv(ref, _lib.stream_ptr()))
+
+    def _wgrad_fn(self, dy, x_ptr, x_ps, dw, cin, cout, taps):
+        p = tops.wgrad_params(dy, x_ptr, x_ps, dw, cin, cout, taps)
+        self.keep.append(p)
+        lib, ref = _lib.lib(), C.byref(p)
+        return lambda: _lib.check(lib.hrnb_wgrad(ref, _lib.stream_ptr()))
+
+    # ---- ops ----------------------------------------------------------------------------------------------
+    def split(self, x):
+        """PF8 -> PhasePF8 copy for the stride-2 convs reading x (one split serves all of them)"""
+        ph = T(PhasePF8(self.B, x.v.C, x.v.H, x.v.W, device=self.dev))
+        self.act_bytes += ph.v.buf.numel() * 2
+        self.all_bufs.append(ph.v)
+        lib, s, d = _lib.lib(), x.v, ph.v
+        self._f(lambda: _lib.check(lib.hrnb_phase_split(s.ptr, s.ps, s.N, s.C, s.H, s.W, d.ptr, d.ps, d.phase_stride,
+                                                        _lib.stream_ptr())))
+
+        def back():
+            assert ph.ginit
+            self._ctx = "phase_merge"
+            g, dst = ph.g, self._grad(x)
+            mode = 2 if x.ginit else 1
+            x.ginit = True
+            self._b(lambda: tops.phase_merge(g, dst, mode))
+        self.tape.append(back)
+        return ph
+
+    def unit(self, key, x, relu, res=None, need_dx=True):
+        """conv `key` -> BatchNorm (batch statistics) -> (+ res) -> (ReLU); x: T of PF8 (stride 1) / PhasePF8 (stride 2)"""
+        e = self.eng
+        L = e.units[key]
+        sp = L["spec"]
+        stride, k = sp.stride, sp.k
+        Ho, Wo = x.v.H // stride, x.v.W // stride
+        self._ctx = key
+        c = self._buf(sp.cout, Ho, Wo)
+        y = T(self._buf(sp.cout, Ho, Wo))
+        self._f(self._conv_fn(L["fwd"], x.v, c))
+        self.conv_out[key] = c
+        sums, dsums = L["sums"], L["dsums"]
+        self._f(lambda: tops.bn_stats(c, sums))
+        bp = tops.bn_params(c, sums, L["gamma"], L["beta"], y.v, res=res.v if res is not None else None, relu=relu,
+                            running_mean=L["rm"], running_var=L["rv"])
+        self.keep.append(bp)
+        lib, bref = _lib.lib(), C.byref(bp)
+        self._f(lambda: _lib.check(lib.hrnb_bn_apply(bref, _lib.stream_ptr())))
+
+        def back():
+            assert y.ginit, key
+            self._ctx = key
+            dy = y.g
+            dres, dmode = None, 0
+            if res is not None:
+                dres = self._grad(res)
+                dmode = 2 if res.ginit else 1
+                res.ginit = True
+            bb = tops.bn_bwd_params(dy, y.v, c, sums, L["gamma"], dsums, dy, L["dgamma"], L["dbeta"], relu=relu,
+                                    dres=dres, dres_mode=dmode)
+            self.keep.append(bb)
+            r = C.byref(bb)
+            self._b(lambda: _lib.check(lib.hrnb_bn_bwd_reduce(r, _lib.stream_ptr())))
+            self._b(lambda: _lib.check(lib.hrnb_bn_bwd_apply(r, _lib.stream_ptr())))
+            self._conv_backward(L, x, dy, need_dx)
+        self.tape.append(back)
+        return y
+
+    def _conv_backward(self, L, x, dc, need_dx):
+        """weight gradient of conv L from (dc, x) and, if asked, the data gradient into x.g"""
+        sp = L["spec"]
+        dw = L["dw"]
+        cin_g = dw.shape[1]
+        if sp.stride == 1:
+            self._b(self._wgrad_fn(dc, x.v.ptr, x.v.ps, dw, cin_g, sp.cout, tops.fwd_taps_s1(sp.k, dc.Wp)))
+            if need_dx:
+                gx = self._grad(x)
+                fn = self._conv_fn(L["dgrad"], dc, gx, res=gx if x.ginit else None)
+                x.ginit = True
+                self._b(fn)
+        else:
+            for ph, taps in tops.fwd_taps_s2(dc.Wp).items():
+                self._b(self._wgrad_fn(dc, x.v.ptr + ph * x.v.phase_stride * 2, x.v.ps, dw, cin_g, sp.cout, taps))
+            if need_dx:
+                gx = self._grad(x)
+                for ph in range(4):
+                    out = _phase_view(gx, ph)
+                    self.keep.append(out)
+                    self._b(self._conv_fn(L["dgrad"][ph], dc, out, res=out if x.ginit else None))
+                x.ginit = True
+
+    def fuse(self, srcs, shifts, out_v=None, out_g=None):
+        ch, (H, W) = srcs[0].v.C, (srcs[0].v.H << shifts[0], srcs[0].v.W << shifts[0])
+        out = T(out_v if out_v is not None else self._buf(ch, H, W), out_g)
+        p = _lib.FuseParams()
+        for i, (s, sh) in enumerate(zip(srcs, shifts)):
+            p.src[i], p.src_ps[i], p.shift[i] = s.v.ptr, s.v.ps, sh
+        p.nsrc = len(srcs)
+        p.out, p.out_ps = out.v.ptr, out.v.ps
+        p.N, p.H, p.W, p.C, p.relu = self.B, H, W, ch, 1
+        self.keep.append(p)
+        lib, ref = _lib.lib(), C.byref(p)
+        self._f(lambda: _lib.check(lib.hrnb_fuse_sum(ref, _lib.stream_ptr())))
+
+        def back():
+            assert out.ginit
+            self._ctx = "fuse"
+            for s, sh in zip(srcs, shifts):
+                g = self._grad(s)
+                mode = 2 if s.ginit else 1
+                s.ginit = True
+                self._b(lambda g=g, sh=sh, mode=mode: tops.fuse_sum_bwd(out.g, out.v, g, sh, True, mode))
+        self.tape.append(back)
+        return out
+
+    # ---- the network --------------------------------------------------------------------------------------
+    def _build(self):
+        e, B = self.eng, self.B
+        arch, lib = e.arch, _lib.lib()
+        ch = arch.channels
+        if self.H % 32 or self.W % 32:
+            raise ValueError("input H and W must be multiples of 32 (four resolutions, each halving)")
+        H2, W2, H4, W4 = self.H // 2, self.W // 2, self.H // 4, self.W // 4
+        J = arch.num_joints
+
+        # per-step zeroing of the statistics workspace and the parameter gradients
+        self._f(lambda: e.stats.zero_())
+        self._f(lambda: e.flat.grads.zero_())
+        self._f(lambda: torch._foreach_add_(e.nbt, 1))
+
+        cols = T(self._buf(32, H2, W2))
+        x = self.x
+        self._f(lambda: _lib.check(lib.hrnb_stem_im2col(x.data_ptr(), cols.v.ptr, cols.v.ps, B, self.H, self.W,
+                                                        _lib.stream_ptr())))
+        t = self.unit("conv1", cols, True, need_dx=False)
+        cur = self.unit("conv2", self.split(t), True)
+
+        for b in range(4):
+            pre = "layer1.%d" % b
+            c1 = self.unit(pre + ".conv1", cur, True)
+            c2 = self.unit(pre + ".conv2", c1, True)
+            res = self.unit(pre + ".downsample.0", cur, False) if b == 0 else cur
+            cur = self.unit(pre + ".conv3", c2, True, res=res)
+
+        xs = [self.unit("transition1.0.0", cur, True), self.unit("transition1.1.0.0", self.split(cur), True)]
+        stage3_b0 = None
+        cat = T(None)
+        for s, nmod in zip((2, 3, 4), arch.modules):
+            nb = s
+            if s > 2:
+                xs.append(self.unit("transition%d.%d.0.0" % (s - 1, nb - 1), self.split(xs[-1]), True))
+            for m in range(nmod):
+                pre = "stage%d.%d" % (s, m)
+                last_module = (s == 4 and m == nmod - 1)
+                for i in range(nb):
+                    for b in range(arch.blocks):
+                        bp = "%s.branches.%d.%d" % (pre, i, b)
+                        y = self.unit(bp + ".conv1", xs[i], True)
+                        xs[i] = self.unit(bp + ".conv2", y, True, res=xs[i])
+                splits = {}
+                outs = []
+                for i in range(nb):
+                    srcs, shifts = [], []
+                    for j in range(nb):
+                        if j == i:
+                            srcs.append(xs[j]); shifts.append(0)
+                        elif j > i:
+                            srcs.append(self.unit("%s.fuse_layers.%d.%d.0" % (pre, i, j), xs[j], False))
+                            shifts.append(j - i)
+                        else:
+                            if j not in splits:
+                                splits[j] = self.split(xs[j])
+                            t = splits[j]
+                            for k in range(i - j):
+                                last = k == i - j - 1
+                                t = self.unit("%s.fuse_layers.%d.%d.%d.0" % (pre, i, j, k), t, not last)
+                                if not last:
+                                    t = self.split(t)
+                            srcs.append(t); shifts.append(0)
+                    if last_module and i == 0:
+                        cat.v = self._buf(arch.head_channels, H4, W4)
+                        cat.g = self._grad(cat)
+                        outs.append(self.fuse(srcs, shifts, cat.v.view_planes(0, ch[0] // 8), cat.g.view_planes(0, ch[0] // 8)))
+                        cat_b0 = outs[-1]
+                    else:
+                        outs.append(self.fuse(srcs, shifts))
+                xs = outs
+            if s == 3:
+                stage3_b0 = xs[0]
+
+        # head: bilinear up-sampling of branches 1..3 into the concat buffer
+        align = 1 if e.variant == "softmax" else 0
+        plane0 = ch[0] // 8
+        ups = []
+        for i in range(1, 4):
+            dst = cat.v.view_planes(plane0, ch[i] // 8)
+            gdst = cat.g.view_planes(plane0, ch[i] // 8)
+            plane0 += ch[i] // 8
+            src = xs[i]
+            self.keep += [dst, gdst]
+            self._f(lambda src=src, dst=dst: _lib.check(lib.hrnb_bilinear_up(
+                src.v.ptr, src.v.ps, src.v.N, src.v.C, src.v.H, src.v.W, dst.ptr, dst.ps, dst.H, dst.W, align, _lib.stream_ptr())))
+            ups.append((src, gdst))
+
+        def back_head():
+            assert cat.ginit
+            cat_b0.ginit = True
+            for src, gdst in ups:
+                g = self._grad(src)
+                mode = 2 if src.ginit else 1
+                src.ginit = True
+                self._b(lambda g=g, gdst=gdst, mode=mode: tops.bilinear_up_bwd(gdst, g, align, mode))
+        self.tape.append(back_head)
+
+        hid = self.unit("last_layer.0", cat, True)
+
+        # final conv (+bias, no BN) -> fp32 NCHW logits
+        F3 = e.final
+        logits = torch.empty((B, J, H4, W4), dtype=torch.float32, device=self.dev)
+        self._f(self._conv_fn(F3["fwd"], hid.v, logits))
+        d_logits = torch.zeros((B, J, H4, W4), dtype=torch.float32, device=self.dev)
+        dlog = self._buf(32 if J <= 32 else (J + 15) // 16 * 16, H4, W4)
+
+        def back_final():
+            self._b(lambda: _lib.check(lib.hrnb_nchw_f32_to_pf8(d_logits.data_ptr(), B, J, H4, W4, dlog.ptr, dlog.ps,
+                                                                _lib.stream_ptr())))
+            if F3["dbias"] is not None:
+                self._b(lambda: tops.channel_sum(dlog, F3["dbias"], J))
+            k = F3["spec"].k
+            self._b(self._wgrad_fn(dlog, hid.v.ptr, hid.v.ps, F3["dw"], arch.head_channels, J, tops.fwd_taps_s1(k, dlog.Wp)))
+            gx = self._grad(hid)
+            self._b(self._conv_fn(F3["dgrad"], dlog, gx))
+            hid.ginit = True
+        self.tape.append(back_final)
+        self.out = {"logits": logits}
+        self.d_logits = d_logits
+        self.cat, self.stage3_b0 = cat, stage3_b0
+
+        # decode + losses (fused path): softmax -> heat-map + soft-argmax -> HeatmapLoss + JointsMSELoss -> d_logits
+        self.gt_heat = torch.zeros((B, J, H4, W4), dtype=torch.float32, device=self.dev)
+        self.gt_xy = torch.zeros((B, J, 2), dtype=torch.float32, device=self.dev)
+        self.vis = torch.ones((B, J), dtype=torch.float32, device=self.dev)
+        self.losses = torch.zeros(3, dtype=torch.float32, device=self.dev)     # total, heat-map, pose2d
+        ws = torch.empty(1024, dtype=torch.float32, device=self.dev)
+        f_hm, f_p2d = e.loss_factors
+        hm_scale = torch.tensor([f_hm], dtype=torch.float32, device=self.dev)
+        BJ = B * J
+        if e.variant == "softmax":
+            heat = torch.empty_like(logits)
+            coords = torch.empty((B, J, 2), dtype=torch.float32, device=self.dev)
+            self.d_heat = torch.zeros_like(logits)
+            self.d_coords = torch.zeros_like(coords)
+            temp = e.temp_param
+            self._f(lambda: _lib.check(lib.hrnb_softmax_softargmax(logits.data_ptr(), temp.data_ptr(), BJ, H4, W4,
+                                                                   heat.data_ptr(), coords.data_ptr(), _lib.stream_ptr())))
+            self.out["heatmap"], self.out["coords"] = heat, coords
+
+            def loss_fused():
+                _lib.check(lib.hrnb_loss_heatmap(heat.data_ptr(), self.gt_heat.data_ptr(), BJ, H4 * W4, 0,
+                                                 self.losses[1:2].data_ptr(), self.d_heat.data_ptr(), hm_scale.data_ptr(),
+                                                 ws.data_ptr(), _lib.stream_ptr()))
+                _lib.check(lib.hrnb_loss_pose2d(coords.data_ptr(), self.gt_xy.data_ptr(), self.vis.data_ptr(), B, J,
+                                                self.losses[2:3].data_ptr(), self.d_coords.data_ptr(), _lib.stream_ptr()))
+                self.d_coords.mul_(f_p2d)
+                torch.add(self.losses[1] * f_hm, self.losses[2], alpha=f_p2d, out=self.losses[0])
+            self.loss_steps.append(loss_fused)
+            self.n_launch["loss"] += 5
+
+            dtemp = e.dtemp
+
+            def softmax_back():
+                _lib.check(lib.hrnb_softmax_softargmax_bwd(logits.data_ptr(), temp.data_ptr(), heat.data_ptr(),
+                                                           self.d_heat.data_ptr(), self.d_coords.data_ptr(), BJ, H4, W4,
+                                                           d_logits.data_ptr(), dtemp.data_ptr() if dtemp is not None else None,
+                                                           _lib.stream_ptr()))
+            self.softmax_back = softmax_back
+        else:
+            def loss_fused():
+                _lib.check(lib.hrnb_loss_heatmap(logits.data_ptr(), self.gt_heat.data_ptr(), BJ, H4 * W4, 0,
+                                                 self.losses[1:2].data_ptr(), d_logits.data_ptr(), hm_scale.data_ptr(),
+                                                 ws.data_ptr(), _lib.stream_ptr()))
+                torch.mul(self.losses[1], f_hm, out=self.losses[0])
+            self.loss_steps.append(loss_fused)
+            self.n_launch["loss"] += 3
+            self.softmax_back = None
+
+        # feature output (NCHW fp32) as the reference returns it
+        feat_src = cat.v if e.variant == "softmax" else stage3_b0.v
+        self.feat = torch.empty((B, feat_src.C, feat_src.H, feat_src.W), dtype=torch.float32, device=self.dev)
+        self.feat_fn = lambda: _lib.check(lib.hrnb_pf8_to_nchw_f32(feat_src.ptr, feat_src.ps, feat_src.N, feat_src.C,
+                                                                   feat_src.H, feat_src.W, self.feat.data_ptr(),
+                                                                   _lib.stream_ptr()))
+
+        # backward launch list from the tape
+        if self.softmax_back is not None:
+            self._b(self.softmax_back)
+        for back in reversed(self.tape):
+            back()
+        self.tape = None
+
+    # ---- execution ------------------------------------------------------------------------------------------
+    def run_forward(self, want_features=False):
+        for fn in self.fwd:
+            fn()
+        if want_features:
+            self.feat_fn()
+
+    def run_loss(self):
+        for fn in self.loss_steps:
+            fn()
+
+    def run_backward(self):
+        for fn in self.bwd:
+            fn()
+
+    def _graphed(self, name, body):
+        if not self.eng.use_graph:
+            body()
+            return
+        if name not in self.graphs:
+            body()                       # warm-up outside capture (function attributes, lazy module loads)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self.graphs[name] = g
+            return                       # the warm-up run already produced this step's results ... replay for state parity
+        self.graphs[name].replay()
+
+
+class TrainEngine:
+    """Owns the flat parameter buffers, the per-layer packed weights (forward and data-gradient orientation) and the
+    per-shape TrainPlans of one network on one device."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, loss_factors=(1.0, 0.1),
+                 use_graph=True):
+        self.model = model
+        self.arch, self.variant = model.arch, model.variant
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("the B200 HRNet trains on CUDA only (no CPU fallback): call .cuda() first")
+        self.loss_factors = tuple(float(f) for f in loss_factors)
+        self.use_graph = use_graph
+        self.plans = {}
+        with torch.cuda.device(self.device):
+            self._setup(lr, betas, eps, weight_decay)
+
+    def _setup(self, lr, betas, eps, weight_decay):
+        model, dev = self.model, self.device
+        named = list(model.named_parameters())
+        index = {n: i for i, (n, _) in enumerate(named)}
+        specs = A.layer_specs(self.arch)
+        convs = [sp for sp in specs if isinstance(sp, A.Conv)]
+        conv_meta = {}
+        for sp in convs:
+            i = index[sp.key + ".weight"]
+            if sp.key == "conv1":
+                conv_meta[i] = (64, 27, 32, 1)
+            else:
+                conv_meta[i] = (sp.cout, sp.cin, sp.cin, sp.k * sp.k)
+        self.flat = FlatParams([p for _, p in named], conv_meta, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        params = dict(named)           # .data now views of the flat buffer
+        buffers = dict(model.named_buffers())
+        self.nbt = [b for n, b in buffers.items() if n.endswith("num_batches_tracked")]
+        bn_after = {}
+        for a, b in zip(specs[:-1], specs[1:]):
+            if isinstance(a, A.Conv) and isinstance(b, A.BN):
+                bn_after[a.key] = b
+        total_c = sum(b.ch for b in bn_after.values())
+        self.stats = torch.zeros(total_c * 4, dtype=torch.float32, device=dev)    # per BN: sums [C][2] + dsums [C][2]
+        self.repacker = Repacker(dev)
+        self.units = {}
+        off = 0
+        gv = self.flat.grad_view
+        for sp in convs:
+            w = params[sp.key + ".weight"].data
+            bias = params[sp.key + ".bias"].data if sp.bias else None
+            if sp.key == "conv1":
+                w4 = w.view(64, 27, 1, 1)
+                fwd = ConvLayer(w4, None, bias, stride=1, cin_pad=32, repacker=self.repacker)
+                spec = A.Conv(sp.key, 32, 64, 1, 1, False)
+                dgrad = None
+            else:
+                spec = sp
+                out_nchw = sp.key not in bn_after
+                fwd = ConvLayer(w, None, bias, stride=sp.stride, out_nchw=out_nchw, repacker=self.repacker)
+                if sp.stride == 1:
+                    tap_ids, _ = tops.dgrad_taps_s1(sp.k, 0)
+                    cpad = 32 if (out_nchw and sp.cout <= 32) else (sp.cout + 15) // 16 * 16
+                    dgrad = ConvLayer(w, transpose=True, tap_ids=tap_ids, cin_pad=cpad, repacker=self.repacker)
+                else:
+                    dgrad = None       # geometry depends on the resolution: built per plan (see dgrad_s2)
+            d = {"spec": spec, "fwd": fwd, "dgrad": dgrad, "dw": gv(index[sp.key + ".weight"]), "w": w}
+            if sp.key in bn_after:
+                bn = bn_after[sp.key]
+                d["gamma"], d["beta"] = params[bn.key + ".weight"].data, params[bn.key + ".bias"].data
+                d["dgamma"], d["dbeta"] = gv(index[bn.key + ".weight"]), gv(index[bn.key + ".bias"])
+                d["rm"], d["rv"] = buffers[bn.key + ".running_mean"], buffers[bn.key + ".running_var"]
+                d["sums"] = self.stats[off:off + 2 * bn.ch]
+                d["dsums"] = self.stats[off + 2 * bn.ch:off + 4 * bn.ch]
+                off += 4 * bn.ch
+                self.units[sp.key] = d
+            else:
+                d["dbias"] = gv(index[sp.key + ".bias"]) if sp.bias else None
+                self.final = d
+        if self.variant == "softmax":
+            self.temp_param = params["trainable_temp"].data.view(1)
+            tp = dict(named)["trainable_temp"]
+            self.dtemp = gv(index["trainable_temp"]).view(1) if tp.requires_grad else None
+        self._s2_cache = {}
+
+    def dgrad_s2(self, key, Wp_half):
+        """the four per-phase data-gradient convs of stride-2 conv `key` on a half grid of padded width Wp_half"""
+        ck = (key, Wp_half)
+        if ck not in self._s2_cache:
+            w = self.units[key]["w"]
+            layers = {}
+            for ph, (tap_ids, taps) in tops.dgrad_taps_s2(Wp_half).items():
+                layers[ph] = ConvLayer(w, transpose=True, tap_ids=tap_ids, custom_taps=taps, repacker=self.repacker)
+            self._s2_cache[ck] = layers
+        return self._s2_cache[ck]
+
+    def plan(self, B, H, W):
+        key = (B, H, W)
+        if key not in self.plans:
+            with torch.cuda.device(self.device):
+                self._prepare_s2(H, W)     # stride-2 units: per-resolution data-gradient layers
+                p = TrainPlan(self, B, H, W)
+                self.repacker.run()
+                torch.cuda.synchronize(self.device)
+                self.plans[key] = p
+        return self.plans[key]
+
+    def _prepare_s2(self, H, W):
+        """resolve the `dgrad` entry of every stride-2 unit for this input size"""
+        H4, W4 = H // 4, W // 4
+        for key, d in self.units.items():
+            sp = d["spec"]
+            if sp.stride != 2:
+                continue
+            if key == "conv2":
+                wo = W4
+            elif key.startswith("transition"):
+                br = int(key.split(".")[1])
+                wo = W4 >> br
+            else:                                   # stageS.M.fuse_layers.I.J.K.0 : output width of chain step K
+                parts = key.split(".")
+                j, k = int(parts[4]), int(parts[5])
+                wo = W4 >> (j + k + 1)
+            d["dgrad"] = self.dgrad_s2(key, wo + 1)
+
+    # ---- public steps ---------------------------------------------------------------------------------------
+    def repack(self):
+        self.repacker.run()
+
+    def forward(self, x, want_features=False):
+        B, _, H, W = x.shape
+        p = self.plan(B, H, W)
+        p.x.copy_(x, non_blocking=True)
+        p._graphed("fwd%d" % int(want_features), lambda: p.run_forward(want_features))
+        return p
+
+    def backward(self, p):
+        """d_logits (raw) or d_heat / d_coords (softmax) must be in the plan's buffers"""
+        p._graphed("bwd", p.run_backward)
+
+    def train_step(self, x, gt_heat, gt_xy=None, vis=None, optimizer_step=True, allreduce=None):
+        """One fused training step: forward, losses, backward, (gradient all-reduce), Adam, weight re-pack.
+        Returns the plan (losses in plan.losses = [total, heat-map, pose2d])."""
+        B, _, H, W = x.shape
+        p = self.plan(B, H, W)
+        p.x.copy_(x, non_blocking=True)
+        p.gt_heat.copy_(gt_heat, non_blocking=True)
+        if gt_xy is not None:
+            p.gt_xy.copy_(gt_xy, non_blocking=True)
+        if vis is not None:
+            p.vis.copy_(vis, non_blocking=True)
+
+        def body():
+            p.run_forward(False)
+            p.run_loss()
+            p.run_backward()
+        p._graphed("step", body)
+        if allreduce is not None:
+            allreduce(self.flat.grads)
+        if optimizer_step:
+            def opt():
+                self.flat.adam_step()
+                self.repacker.run()
+            p._graphed("opt", opt)
+            self.model._engine = None          # folded inference weights are stale now
+        return p

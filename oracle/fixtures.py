@@ -55,3 +55,9 @@ def targets(B, J=21, h=64, w=64, seed=2, sigma=2.0):
 
 def tensor_checksums(sd, keys):
     return {k: float(sd[k].double().abs().sum()) for k in keys}
+
+
+def sample(t, limit=4096, stride=37):
+    """flattened tensor, strided down when it has more than `limit` elements (keeps golden files small)"""
+    f = t.detach().reshape(-1)
+    return f if f.numel() <= limit else f[::stride][:limit * 4].contiguous()

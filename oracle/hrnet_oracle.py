@@ -41,13 +41,20 @@ W32 = Arch((32, 64, 128, 256))
 W48 = Arch((48, 96, 192, 384))
 
 
+_BN_TRAIN = False     # forward_train() switches the BatchNorms to batch statistics (nn.BatchNorm2d in train mode)
+
+
 def _bn(sd, key, x):
     return F.batch_norm(x, sd[key + ".running_mean"], sd[key + ".running_var"], sd[key + ".weight"],
-                        sd[key + ".bias"], False, 0.1, EPS)
+                        sd[key + ".bias"], _BN_TRAIN, 0.1, EPS)
+
+
+_CONV_HOOK = None     # tests only: fn(key, conv_output) -> tensor used instead (see train_oracle.train_step(conv_hook=))
 
 
 def _conv(sd, key, x, stride=1, pad=0):
-    return F.conv2d(x, sd[key + ".weight"], sd.get(key + ".bias"), stride=stride, padding=pad)
+    y = F.conv2d(x, sd[key + ".weight"], sd.get(key + ".bias"), stride=stride, padding=pad)
+    return _CONV_HOOK(key, y) if _CONV_HOOK is not None else y
 
 
 def _basic_block(sd, pre, x):
@@ -121,17 +128,33 @@ def forward(sd, x, arch=W32, variant="softmax"):
        (logits are returned additionally for testing)."""
     sd = {k: v.detach().float() for k, v in sd.items() if torch.is_tensor(v)}
     with torch.no_grad():
-        xs, s3b0 = backbone(sd, x.float(), arch)
-        h, w = xs[0].shape[2:]
-        align = variant == "softmax"
-        ups = [xs[0]] + [F.interpolate(t, size=(h, w), mode="bilinear", align_corners=align) for t in xs[1:]]
-        cat = torch.cat(ups, 1)
-        y = F.relu(_bn(sd, "last_layer.1", _conv(sd, "last_layer.0", cat)))
-        kf = sd["last_layer.3.weight"].shape[-1]
-        logits = _conv(sd, "last_layer.3", y, 1, 1 if kf == 3 else 0)
-        if variant == "raw":
-            return logits, s3b0
-        temp = sd["trainable_temp"]
-        B, J = logits.shape[:2]
-        heat = F.softmax(logits.reshape(B, J, -1) * temp, dim=2).reshape(logits.shape)
-        return heat, cat, temp, logits
+        return _forward(sd, x, arch, variant)
+
+
+def forward_train(sd, x, arch=W32, variant="softmax"):
+    """model.train() forward with autograd enabled: `sd` maps state_dict keys to tensors; parameters that should
+    receive gradients are leaf tensors with requires_grad=True, running statistics are updated IN PLACE
+    (momentum 0.1, unbiased variance), exactly as nn.BatchNorm2d does in train mode.  Same return as forward()."""
+    global _BN_TRAIN
+    _BN_TRAIN = True
+    try:
+        return _forward(sd, x, arch, variant)
+    finally:
+        _BN_TRAIN = False
+
+
+def _forward(sd, x, arch, variant):
+    xs, s3b0 = backbone(sd, x.float(), arch)
+    h, w = xs[0].shape[2:]
+    align = variant == "softmax"
+    ups = [xs[0]] + [F.interpolate(t, size=(h, w), mode="bilinear", align_corners=align) for t in xs[1:]]
+    cat = torch.cat(ups, 1)
+    y = F.relu(_bn(sd, "last_layer.1", _conv(sd, "last_layer.0", cat)))
+    kf = sd["last_layer.3.weight"].shape[-1]
+    logits = _conv(sd, "last_layer.3", y, 1, 1 if kf == 3 else 0)
+    if variant == "raw":
+        return logits, s3b0
+    temp = sd["trainable_temp"]
+    B, J = logits.shape[:2]
+    heat = F.softmax(logits.reshape(B, J, -1) * temp, dim=2).reshape(logits.shape)
+    return heat, cat, temp, logits

@@ -163,7 +163,87 @@ def loss_fixture():
     print("loss ok; oracle == reference")
 
 
+TRAIN_KEYS = ["conv1.weight", "bn1.weight", "conv2.weight", "layer1.0.downsample.0.weight", "layer1.0.conv2.weight",
+              "layer1.3.bn3.bias", "transition1.0.0.weight", "transition1.1.0.0.weight", "stage2.0.branches.0.0.conv1.weight",
+              "stage2.0.fuse_layers.0.1.0.weight", "stage2.0.fuse_layers.1.0.0.0.weight", "stage3.1.branches.2.3.conv2.weight",
+              "stage3.3.fuse_layers.2.0.1.0.weight", "stage4.0.branches.3.0.conv1.weight", "stage4.2.fuse_layers.0.3.0.weight",
+              "stage4.2.fuse_layers.3.0.0.0.weight", "stage4.2.fuse_layers.0.2.1.weight", "last_layer.0.weight",
+              "last_layer.1.weight", "last_layer.3.weight", "last_layer.3.bias"]
+
+
+def train_fixture(name, yaml_rel, variant, B=2, H=256, W=256, trainable_temp=False):
+    """One training step of the UNMODIFIED reference (model.train(), its own losses / decode, torch Adam as
+    utils.get_optimizer builds it): losses, gradients, running stats and updated parameters."""
+    from oracle import train_oracle
+    pose_hrnet, pose_hrnet_softmax, hd, _, loss = ref_shim.modules()
+    cfg = ref_shim.load_cfg(yaml_rel)
+    if variant == "softmax":
+        cfg.MODEL["TRAINABLE_SOFTMAX"] = trainable_temp
+    mod = pose_hrnet_softmax if variant == "softmax" else pose_hrnet
+    torch.manual_seed(0)
+    ref = mod.get_pose_net(cfg, is_train=False)
+    sd0 = copy.deepcopy(ref.state_dict())
+    fixtures.perturb_state_dict(sd0)          # non-trivial gamma / beta
+    ref.load_state_dict(sd0)
+    ref.train()
+    x = fixtures.images(B, H, W)
+    gt, xy, vis = fixtures.targets(B, 21, H // 4, W // 4)
+    torch.set_num_threads(8)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, ref.parameters()), lr=1e-3, weight_decay=1e-4)
+    out = ref(x)
+    if variant == "softmax":
+        heat = out[0]
+        l_hm = loss.HeatmapLoss()(heat, gt)
+        l_p2d = loss.JointsMSELoss()(hd.get_final_preds(heat, True), xy, vis)
+        total = 1.0 * l_hm + 0.1 * l_p2d
+    else:
+        l_hm = loss.HeatmapLoss()(out[0], gt)
+        l_p2d = torch.zeros(())
+        total = 1.0 * l_hm
+    opt.zero_grad()
+    total.backward()
+    grads = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
+    opt.step()
+    after = ref.state_dict()
+    arch = hrnet_oracle.Arch.from_cfg(cfg)
+    o = train_oracle.train_step(sd0, x, gt, xy, vis, arch, variant, trainable_temp=trainable_temp)
+    assert np.allclose(o["losses"], (float(total), float(l_hm), float(l_p2d)), rtol=1e-5), (o["losses"], float(total))
+    worst = 0.0
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    for k, g in grads.items():
+        og = o["grads"][k]
+        # (a conv bias followed by BatchNorm has a mathematically zero gradient: only rounding noise, hence the floor)
+        err = float((og - g).abs().max() / max(float(g.abs().max()), 1e-4 * gmax))
+        worst = max(worst, err)
+        assert err < 2e-3, (k, err)
+    for k, v in after.items():
+        if v.dtype.is_floating_point:
+            # the first Adam step moves every element by ~lr*sign(g): elements whose gradient is rounding noise may
+            # flip, so the check is "all within 2*lr + almost all identical"
+            d = (o["state"][k] - v).abs()
+            assert float(d.max()) <= 2.1e-3 and float((d > 1e-5).float().mean()) < 0.02, (k, float(d.max()), float((d > 1e-5).float().mean()))
+    rec = {"losses": np.array([float(total), float(l_hm), float(l_p2d)]), "B": np.array(B), "H": np.array(H), "W": np.array(W),
+           "keys": np.array(TRAIN_KEYS), "trainable_temp": np.array(int(trainable_temp))}
+    for k in TRAIN_KEYS:          # big tensors are stored as a strided sample (fixtures.sample) + their L2 norm
+        rec["grad/" + k] = fixtures.sample(grads[k]).numpy()
+        rec["gnorm/" + k] = np.array(float(grads[k].double().norm()))
+        rec["after/" + k] = fixtures.sample(after[k]).numpy()
+    for k in ("bn1", "stage3.0.branches.1.2.bn1", "last_layer.1"):
+        rec["after/" + k + ".running_mean"] = after[k + ".running_mean"].numpy()
+        rec["after/" + k + ".running_var"] = after[k + ".running_var"].numpy()
+    rec["grad_l2_all"] = np.array([float(g.double().norm()) for _, g in sorted(grads.items())])
+    if "trainable_temp" in grads:
+        rec["grad/trainable_temp"] = grads["trainable_temp"].numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print(name, "ok; oracle train step == reference; worst grad rel err %.2e; losses" % worst, rec["losses"])
+
+
 if __name__ == "__main__":
+    if "--train-only" in sys.argv:
+        train_fixture("train_w32_softmax", "experiments/RHD/RHD_HRNet_w32_softmax_hm-pose2dloss_v1.yaml", "softmax",
+                      trainable_temp=True)
+        train_fixture("train_w32_raw", "experiments/RHD/RHD_HRNet_w32_max_hmloss_v1.yaml", "raw")
+        sys.exit(0)
     os.makedirs(GOLD, exist_ok=True)
     decode_fixture()
     loss_fixture()
@@ -175,3 +255,5 @@ if __name__ == "__main__":
     net_fixture("hrnet_w32_raw", YR, "raw")
     net_fixture("hrnet_w48_softmax_rect", "experiments/RHD/RHD_HRNet_w48_trainable_softmax_hm-pose2dloss_v1.yaml",
                 "softmax", H=128, W=96, B=2)
+    train_fixture("train_w32_softmax", Y, "softmax", trainable_temp=True)
+    train_fixture("train_w32_raw", YR, "raw")

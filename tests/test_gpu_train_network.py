@@ -1,0 +1,162 @@
+"""-m gpu: one whole training step of the CUDA path (forward with batch-stat BN, fused losses, full backward, fused
+Adam) against the reference-generated golden vectors (tests/golden/train_*.npz) and the CPU train oracle.
+
+Gradient tolerances: the CUDA path keeps activations and activation-gradients in bf16 (fp32 accumulation, fp32
+parameter gradients); the reference is fp32.  Per tensor we bound the relative L2 error and require the cosine with
+the reference gradient to be close to 1 (measured values are written to gpurun_out/parity_report.jsonl)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# Whole-network gradients at random init are chaotic in the forward pass: rounding activations to bf16 moves the
+# logits of the 2-image golden case by ~35 % (max-rel) and decorrelates early-layer gradients from the fp32 reference
+# (cosine 0.3) - measured identically with the CPU oracle when its conv outputs are rounded to bf16, i.e. a property
+# of the problem, not of the kernels.  The tests therefore split parity in two:
+#   forward  : losses, batch statistics and gradient NORMS against the fp32 reference (golden) within documented bounds;
+#   backward : every parameter gradient against the LINEARISED oracle (train_oracle.train_step(conv_values=...)), which
+#              differentiates around the activations the CUDA path actually produced - backward is linear given the
+#              forward values, so this comparison is tight.
+# Measured on B200 (profiles/r1_parity_report.jsonl): worst tensor 0.164 rel-L2 / cosine 0.9865 (stage-2 BN weights, i.e.
+# after ~250 bf16-rounded backward ops), head tensors ~1e-2.
+LIN_L2_TOL = 0.25       # relative L2 error per parameter tensor vs the linearised oracle (bf16 gradient storage)
+LIN_COS_TOL = 0.97
+
+
+def _report(name, **kv):
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+        f.write(json.dumps(dict(case=name, **kv)) + "\n")
+
+
+def _setup(variant, trainable, B, H, W, width=32):
+    from oracle import fixtures
+    from hrnet_b200.config import make_cfg
+    from hrnet_b200.models import pose_hrnet, pose_hrnet_softmax
+    cfg = make_cfg(width, softmax=(variant == "softmax"), trainable_softmax=trainable, image_size=(H, W))
+    torch.manual_seed(0)
+    m = (pose_hrnet_softmax if variant == "softmax" else pose_hrnet).get_pose_net(cfg, is_train=False)
+    sd = m.state_dict()
+    fixtures.perturb_state_dict(sd)
+    m.load_state_dict(sd)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = fixtures.images(B, H, W)
+    gt, xy, vis = fixtures.targets(B, 21, H // 4, W // 4)
+    return m.cuda().train(), cfg, sd, x, gt, xy, vis
+
+
+def _cmp(got, ref):
+    got, ref = got.double().reshape(-1), ref.double().reshape(-1)
+    l2 = float((got - ref).norm() / (ref.norm() + 1e-30))
+    cos = float((got * ref).sum() / (got.norm() * ref.norm() + 1e-30))
+    return l2, cos
+
+
+@pytest.mark.parametrize("name,variant", [("train_w32_softmax", "softmax"), ("train_w32_raw", "raw")])
+def test_train_step_against_reference_golden(golden_dir, name, variant):
+    from oracle import fixtures
+    from hrnet_b200.train import TrainEngine
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    m, cfg, sd, x, gt, xy, vis = _setup(variant, bool(g["trainable_temp"]), B, H, W)
+    eng = TrainEngine(m, lr=1e-3, weight_decay=1e-4, loss_factors=(1.0, 0.1), use_graph=False)
+    p = eng.train_step(x.cuda(), gt.cuda(), xy.cuda(), vis.cuda(), optimizer_step=False)
+    torch.cuda.synchronize()
+    losses = p.losses.cpu().numpy()
+    assert np.allclose(losses[: (3 if variant == "softmax" else 2)], g["losses"][: (3 if variant == "softmax" else 2)], rtol=2e-2), (losses, g["losses"])
+    names = [n for n, _ in m.named_parameters()]
+    nat = dict(zip(names, eng.flat.natural_grads()))
+    gmax = max(float(np.abs(g["grad/" + str(k)]).max()) for k in g["keys"])
+    bad = []
+    for k in g["keys"]:
+        k = str(k)
+        ref = torch.from_numpy(g["grad/" + k])
+        if float(ref.abs().max()) <= 1e-4 * gmax:
+            continue                                   # mathematically-zero gradients (noise in the reference)
+        got = fixtures.sample(nat[k].cpu())
+        l2, cos = _cmp(got, ref)
+        ratio = float(nat[k].double().norm()) / float(g["gnorm/" + k])
+        _report(name + ":" + k, grad_rel_l2=l2, grad_cos=cos, norm_ratio=ratio)
+        if not (0.8 < ratio < 1.25) or (k.startswith("last_layer") and cos < 0.85):
+            bad.append((k, round(l2, 4), round(cos, 4), round(ratio, 3)))
+    assert not bad, bad
+    _report(name, loss_total=float(losses[0]), loss_ref=float(g["losses"][0]))
+    # running statistics after the step (momentum 0.1, unbiased variance)
+    bufs = dict(m.named_buffers())
+    for k in ("bn1", "stage3.0.branches.1.2.bn1", "last_layer.1"):
+        for s in (".running_mean", ".running_var"):
+            ref = g["after/" + k + s]
+            got = bufs[k + s].cpu().numpy()
+            tol = 2e-2 if k == "bn1" else 0.2          # forward noise grows with depth (see the header comment)
+            assert np.abs(got - ref).max() <= tol * max(1e-3, np.abs(ref).max()), (k + s, np.abs(got - ref).max())
+    assert int(bufs["bn1.num_batches_tracked"]) == 1
+    # optimizer: the fused Adam step on the real parameter layout == torch.optim.Adam fed with the same gradients
+    keys = ("conv1.weight", "stage2.0.branches.0.0.conv1.weight", "stage4.2.fuse_layers.3.0.0.0.weight", "last_layer.1.weight",
+            "last_layer.3.weight", "last_layer.3.bias")
+    before = {k: dict(m.named_parameters())[k].detach().clone() for k in keys}
+    grads = {k: nat[k].clone() for k in keys}
+    eng.flat.adam_step()
+    torch.cuda.synchronize()
+    after = dict(m.named_parameters())
+    for k in keys:
+        ref = torch.nn.Parameter(before[k].clone())
+        ref.grad = grads[k]
+        torch.optim.Adam([ref], lr=1e-3, weight_decay=1e-4).step()
+        assert torch.allclose(after[k].detach(), ref.detach(), rtol=1e-5, atol=1e-7), k
+
+
+@pytest.mark.parametrize("variant,B,H,W", [("softmax", 2, 256, 256), ("raw", 3, 128, 96)])
+def test_backward_against_linearised_oracle(variant, B, H, W):
+    """Every parameter gradient of the network against torch autograd differentiating around the CUDA path's own
+    forward activations (all conv outputs injected into the CPU oracle)."""
+    from oracle import hrnet_oracle, train_oracle
+    from hrnet_b200.train import TrainEngine
+    m, cfg, sd, x, gt, xy, vis = _setup(variant, True, B, H, W)
+    eng = TrainEngine(m, use_graph=False)
+    p = eng.train_step(x.cuda(), gt.cuda(), xy.cuda(), vis.cuda(), optimizer_step=False)
+    torch.cuda.synchronize()
+    conv_values = {k: c.to_nchw().cpu() for k, c in p.conv_out.items()}
+    conv_values["last_layer.3"] = p.out["logits"].cpu()
+    o = train_oracle.train_step(sd, x, gt, xy, vis, hrnet_oracle.Arch.from_cfg(cfg), variant, trainable_temp=True,
+                                adam=False, conv_values=conv_values)
+    assert np.allclose(p.losses.cpu().numpy()[:2], o["losses"][:2], rtol=2e-3), (p.losses, o["losses"])
+    names = [n for n, _ in m.named_parameters()]
+    nat = dict(zip(names, eng.flat.natural_grads()))
+    gmax = max(float(v.abs().max()) for v in o["grads"].values())
+    bad, worst = [], (0.0, "", 1.0)
+    for k, ref in o["grads"].items():
+        if float(ref.abs().max()) <= 1e-4 * gmax:
+            continue
+        l2, cos = _cmp(nat[k].cpu(), ref)
+        if l2 > worst[0]:
+            worst = (l2, k, cos)
+        if not (l2 < LIN_L2_TOL and cos > LIN_COS_TOL):
+            bad.append((k, round(l2, 4), round(cos, 5)))
+    _report("train_linearised_%s_%dx%dx%d" % (variant, B, H, W), worst_rel_l2=worst[0], worst_key=worst[1], worst_cos=worst[2],
+            n_checked=len(o["grads"]), n_bad=len(bad))
+    assert not bad, (len(bad), bad[:20])
+
+
+def test_graph_replay_equals_eager_and_loss_decreases():
+    """CUDA-graph replay of the step gives the same losses as eager launches, and a few Adam steps on a fixed batch
+    reduce the loss."""
+    from hrnet_b200.train import TrainEngine
+    B, H, W = 4, 128, 128
+    m, cfg, sd, x, gt, xy, vis = _setup("softmax", False, B, H, W)
+    eng = TrainEngine(m, lr=1e-3, use_graph=True)
+    xs, gts, xys, viss = x.cuda(), gt.cuda(), xy.cuda(), vis.cuda()
+    hist = []
+    for it in range(8):
+        p = eng.train_step(xs, gts, xys, viss)
+        hist.append(float(p.losses[0]))
+    assert all(np.isfinite(hist)), hist
+    assert hist[-1] < hist[0], hist
+    m2, *_ = _setup("softmax", False, B, H, W)
+    eng2 = TrainEngine(m2, lr=1e-3, use_graph=False)
+    h2 = [float(eng2.train_step(xs, gts, xys, viss).losses[0]) for _ in range(3)]
+    assert np.allclose(hist[:3], h2, rtol=5e-3), (hist[:3], h2)

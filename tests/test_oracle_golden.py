@@ -116,3 +116,41 @@ def test_loss_oracle_matches_reference_golden(golden_dir):
             assert np.isclose(loss_oracle.pose2d_loss(g[tag + "_pp"], g[tag + "_xy"], v), g["%s_p2d_%s" % (tag, vtag)], rtol=1e-5)
             assert np.allclose(loss_oracle.pose2d_loss_grad(g[tag + "_pp"], g[tag + "_xy"], v),
                                g["%s_p2d_%s_grad" % (tag, vtag)], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,variant", [("train_w32_softmax", "softmax"), ("train_w32_raw", "raw")])
+def test_train_oracle_reproduces_reference_training_step(golden_dir, name, variant):
+    """oracle/train_oracle.py (torch-CPU autograd restatement of one reference training step) against the losses,
+    gradients, running statistics and Adam-updated parameters the UNMODIFIED reference produced
+    (oracle/make_golden.py train_fixture)."""
+    import numpy as np
+    import torch
+    from oracle import fixtures, hrnet_oracle, train_oracle
+    from hrnet_b200.config import make_cfg
+    from hrnet_b200.models import pose_hrnet, pose_hrnet_softmax
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    cfg = make_cfg(32, softmax=(variant == "softmax"), trainable_softmax=bool(g["trainable_temp"]))
+    torch.manual_seed(0)
+    m = (pose_hrnet_softmax if variant == "softmax" else pose_hrnet).get_pose_net(cfg, is_train=False)
+    sd = m.state_dict()
+    fixtures.perturb_state_dict(sd)
+    x = fixtures.images(B, H, W)
+    gt, xy, vis = fixtures.targets(B, 21, H // 4, W // 4)
+    o = train_oracle.train_step(sd, x, gt, xy, vis, hrnet_oracle.Arch.from_cfg(cfg), variant,
+                                trainable_temp=bool(g["trainable_temp"]))
+    assert np.allclose(o["losses"], g["losses"], rtol=1e-4)
+    gmax = max(float(np.abs(g["grad/" + str(k)]).max()) for k in g["keys"])
+    for k in g["keys"]:
+        k = str(k)
+        ref = g["grad/" + k]
+        got = fixtures.sample(o["grads"][k]).numpy()
+        # floor: gradients that are mathematically zero (a bias in front of BatchNorm / softmax) are rounding noise
+        assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1e-4 * gmax), k
+        if np.abs(ref).max() > 1e-4 * gmax:
+            assert np.isclose(float(o["grads"][k].double().norm()), float(g["gnorm/" + k]), rtol=1e-3)
+        d = np.abs(fixtures.sample(o["state"][k]).numpy() - g["after/" + k])
+        assert d.max() <= 2.1e-3 and (d > 1e-5).mean() < 0.02, k          # first Adam step: +-lr per element
+    for k in ("bn1", "stage3.0.branches.1.2.bn1", "last_layer.1"):
+        for s in (".running_mean", ".running_var"):
+            assert np.allclose(o["state"][k + s].numpy(), g["after/" + k + s], rtol=1e-4, atol=1e-6), k + s
