@@ -84,7 +84,7 @@ class BnBwdParams(C.Structure):
     _fields_ = [
         ("dy", C.c_void_p), ("dy_ps", C.c_int64), ("y", C.c_void_p), ("y_ps", C.c_int64),
         ("c", C.c_void_p), ("c_ps", C.c_int64), ("sums", C.c_void_p), ("gamma", C.c_void_p), ("dsums", C.c_void_p),
-        ("dc", C.c_void_p), ("dc_ps", C.c_int64), ("dres", C.c_void_p), ("dres_ps", C.c_int64), ("dres_mode", C.c_int32),
+        ("ws", C.c_void_p), ("dc", C.c_void_p), ("dc_ps", C.c_int64), ("dres", C.c_void_p), ("dres_ps", C.c_int64), ("dres_mode", C.c_int32),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("N", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu", C.c_int32), ("eps", C.c_float),
     ]
@@ -120,8 +120,9 @@ _SIGS = {
     "hrnb_wgrad": (C.c_int, [C.POINTER(WgradParams), _vp]),
     "hrnb_wgrad_smem_bytes": (_i64, [C.POINTER(WgradParams)]),
     "hrnb_pack_conv_weights_batch": (C.c_int, [_vp, _vp, _i32, _vp]),
-    "hrnb_bn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "hrnb_channel_sum": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hrnb_bn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hrnb_channel_sum": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hrnb_reduce_ws_floats": (_i64, []),
     "hrnb_bn_apply": (C.c_int, [C.POINTER(BnParams), _vp]),
     "hrnb_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
     "hrnb_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwdParams), _vp]),

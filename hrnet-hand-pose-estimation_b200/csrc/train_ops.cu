@@ -14,11 +14,23 @@
 namespace hrnb {
 
 // ------------------------------------------------------------------------------------------------
-// block-level reduction of NV per-thread values -> atomicAdd into global (one atomic per value per block)
+// Deterministic grid reduction of NV per-thread values per plane (blockIdx.y): every block stores its partial sums,
+// the LAST block of the plane to arrive (ticket counter) adds all partials in block order and writes dst[plane*NV + i].
+// fp32 atomics would make the batch statistics depend on the block scheduling order; through ~150 BatchNorm layers
+// of a random-init network that 1e-7 noise grows to O(1) differences in the logits [measured], so run-to-run
+// reproducibility needs a fixed summation order.  Workspace: kMaxPlanes counters (self-resetting, zero-initialised
+// once) followed by [plane][kMaxRedBlocks][16] floats; kernels sharing it must be stream-ordered.
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxPlanes = 1024;
+constexpr int kMaxRedBlocks = 296;
+
 template <int NV>
-__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float* __restrict__ dst, int dst_stride) {
+__device__ __forceinline__ void grid_reduce_ordered(float (&v)[NV], float* __restrict__ dst, float* __restrict__ ws) {
   __shared__ float red[8][NV];
+  __shared__ unsigned ticket_s;
+  const int plane = blockIdx.y;
+  unsigned* counter = reinterpret_cast<unsigned*>(ws) + plane;
+  float* partials = ws + kMaxPlanes + (size_t)plane * kMaxRedBlocks * 16;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
 #pragma unroll
@@ -34,16 +46,29 @@ __device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float* __res
     float s = 0.f;
     const int nw = (blockDim.x + 31) >> 5;
     for (int w = 0; w < nw; ++w) s += red[w][threadIdx.x];
-    atomicAdd(dst + (long long)threadIdx.x * dst_stride, s);
+    partials[(size_t)blockIdx.x * 16 + threadIdx.x] = s;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ticket_s = atomicAdd(counter, 1u);
+  __syncthreads();
+  if (ticket_s == gridDim.x - 1) {      // last block of this plane: all partials are visible
+    __threadfence();
+    if (threadIdx.x < NV) {
+      float s = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partials + (size_t)b * 16 + threadIdx.x);
+      dst[(size_t)plane * NV + threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // BN forward, batch statistics
 // ------------------------------------------------------------------------------------------------
-// sums[c][0] += sum_p x, sums[c][1] += sum_p x^2 (padding positions are zero and add nothing)
+// sums[c][0] = sum_p x, sums[c][1] = sum_p x^2 (padding positions are zero and add nothing)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ c, long long c_ps, long long P,
-                                                      float* __restrict__ sums) {
+                                                      float* __restrict__ sums, float* __restrict__ ws) {
   const int plane = blockIdx.y;
   const __nv_bfloat16* base = c + (long long)plane * c_ps * 8;
   float v[16];
@@ -58,12 +83,12 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
       v[2 * i + 1] = fmaf(a[i], a[i], v[2 * i + 1]);
     }
   }
-  block_reduce_atomic<16>(v, sums + (long long)plane * 16, 1);   // [channel][2] interleaved
+  grid_reduce_ordered<16>(v, sums, ws);   // [channel][2] interleaved
 }
 
-// per-channel sum only (bias gradient of the BN-less final conv): out[c] += sum_p x
+// per-channel sum only (bias gradient of the BN-less final conv): out[c] = sum_p x  (out padded to 8 * planes floats)
 __global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* __restrict__ c, long long c_ps, long long P,
-                                                         int C, float* __restrict__ out) {
+                                                         float* __restrict__ out8, float* __restrict__ ws) {
   const int plane = blockIdx.y;
   const __nv_bfloat16* base = c + (long long)plane * c_ps * 8;
   float v[8];
@@ -75,23 +100,12 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* _
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += a[i];
   }
-  __shared__ float red[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) red[warp][i] = v[i];
-  }
-  __syncthreads();
-  if (threadIdx.x < 8 && plane * 8 + (int)threadIdx.x < C) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    atomicAdd(out + plane * 8 + threadIdx.x, s);
-  }
+  grid_reduce_ordered<8>(v, out8, ws);
+}
+
+__global__ void copy_floats_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
 }
 
 struct BnK {
@@ -157,6 +171,7 @@ struct BnBwdK {
   const __nv_bfloat16* c; long long c_ps;
   const float* sums; const float* gamma;
   float* dsums;
+  float* ws;
   __nv_bfloat16* dc; long long dc_ps;
   __nv_bfloat16* dres; long long dres_ps; int dres_mode;
   float* dgamma; float* dbeta;
@@ -172,7 +187,7 @@ __device__ __forceinline__ void bn_channel_stats(const float* sums, int ch, floa
   invstd = rsqrtf(var + eps);
 }
 
-// dsums[c][0] += sum g, dsums[c][1] += sum g*xhat with g = dy * (y > 0)
+// dsums[c][0] = sum g, dsums[c][1] = sum g*xhat with g = dy * (y > 0)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
   __shared__ float sm[8], si[8];
   const int plane = blockIdx.y;
@@ -197,7 +212,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
       v[2 * i + 1] = fmaf(g[i], (x[i] - sm[i]) * si[i], v[2 * i + 1]);   // padding: g == 0
     }
   }
-  block_reduce_atomic<16>(v, k.dsums + (long long)plane * 16, 1);
+  grid_reduce_ordered<16>(v, k.dsums, k.ws);
 }
 
 // dc = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dres (+)= g; block (0, plane) writes dgamma / dbeta
@@ -485,28 +500,39 @@ using namespace hrnb;
 static unsigned reduce_blocks(long long P) {
   long long b = (P + 256 * 8 - 1) / (256 * 8);   // ~8 positions per thread
   if (b < 1) b = 1;
-  if (b > 296) b = 296;
+  if (b > kMaxRedBlocks) b = kMaxRedBlocks;
   return (unsigned)b;
 }
 
+extern "C" int64_t hrnb_reduce_ws_floats(void) {
+  return (int64_t)kMaxPlanes + (int64_t)kMaxPlanes * kMaxRedBlocks * 16 + (int64_t)kMaxPlanes * 8;
+}
+
 extern "C" int hrnb_bn_stats(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* sums,
-                             void* stream) {
-  if (!c || !sums || C % 8 || C <= 0) return fail(HRNB_EINVAL, "bn_stats: bad params");
+                             float* ws, void* stream) {
+  if (!c || !sums || !ws || C % 8 || C <= 0 || C / 8 > kMaxPlanes) return fail(HRNB_EINVAL, "bn_stats: bad params");
   const Geo g = make_geo(N, H, W);
   dim3 grid(reduce_blocks(g.P), C / 8);
-  bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)c, c_ps, g.P, sums);
+  bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)c, c_ps, g.P, sums, ws);
   count_launch();
   return check_launch("bn_stats_kernel");
 }
 
 extern "C" int hrnb_channel_sum(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* out,
-                                void* stream) {
-  if (!c || !out || C <= 0) return fail(HRNB_EINVAL, "channel_sum: bad params");
+                                float* ws, void* stream) {
+  if (!c || !out || !ws || C <= 0 || (C + 7) / 8 > kMaxPlanes) return fail(HRNB_EINVAL, "channel_sum: bad params");
   const Geo g = make_geo(N, H, W);
-  dim3 grid(reduce_blocks(g.P), (C + 7) / 8);
-  channel_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)c, c_ps, g.P, C, out);
+  const int planes = (C + 7) / 8;
+  dim3 grid(reduce_blocks(g.P), planes);
+  // the ordered reduction writes 8 floats per plane: stage them behind the partials, then copy the C real channels
+  float* out8 = ws + kMaxPlanes + (size_t)kMaxPlanes * kMaxRedBlocks * 16;
+  channel_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)c, c_ps, g.P, out8, ws);
   count_launch();
-  return check_launch("channel_sum_kernel");
+  int rc = check_launch("channel_sum_kernel");
+  if (rc) return rc;
+  copy_floats_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out8, out, C);
+  count_launch();
+  return check_launch("copy_floats_kernel");
 }
 
 extern "C" int hrnb_bn_apply(const hrnb_bn_params* p, void* stream) {
@@ -529,13 +555,13 @@ extern "C" int hrnb_bn_apply(const hrnb_bn_params* p, void* stream) {
 }
 
 static int make_bwd(const hrnb_bn_bwd_params* p, BnBwdK* k) {
-  if (!p || !p->dy || !p->c || !p->sums || !p->gamma || !p->dsums || p->C % 8 || p->C <= 0)
+  if (!p || !p->dy || !p->c || !p->sums || !p->gamma || !p->dsums || !p->ws || p->C % 8 || p->C <= 0 || p->C / 8 > kMaxPlanes)
     return fail(HRNB_EINVAL, "bn_bwd: bad params");
   if (p->relu && !p->y) return fail(HRNB_EINVAL, "bn_bwd: relu needs the unit output y");
   k->dy = (const __nv_bfloat16*)p->dy; k->dy_ps = p->dy_ps;
   k->y = (const __nv_bfloat16*)p->y; k->y_ps = p->y_ps;
   k->c = (const __nv_bfloat16*)p->c; k->c_ps = p->c_ps;
-  k->sums = p->sums; k->gamma = p->gamma; k->dsums = p->dsums;
+  k->sums = p->sums; k->gamma = p->gamma; k->dsums = p->dsums; k->ws = p->ws;
   k->dc = (__nv_bfloat16*)p->dc; k->dc_ps = p->dc_ps;
   k->dres = (__nv_bfloat16*)p->dres; k->dres_ps = p->dres_ps; k->dres_mode = p->dres ? p->dres_mode : 0;
   k->dgamma = p->dgamma; k->dbeta = p->dbeta;

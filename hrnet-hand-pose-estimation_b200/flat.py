@@ -100,10 +100,15 @@ class FlatParams:
                                       self.segs_dev.data_ptr(), self.block_seg_dev.data_ptr(), self.nblocks,
                                       self.hyper.data_ptr(), _lib.stream_ptr()))
 
-    def natural_grads(self):
-        """list of gradient tensors in the parameters' own layout (views of one flat buffer, overwritten per call)"""
-        if self._natural is None:
-            self._natural = torch.zeros_like(self.data)
-        _lib.check(_lib.lib().hrnb_grad_to_natural(self.grads.data_ptr(), self._natural.data_ptr(), self.segs_dev.data_ptr(),
+    def natural_grads(self, fresh=False):
+        """list of gradient tensors in the parameters' own layout: views of one flat buffer that is overwritten by the
+        next call, or of a newly allocated one when fresh=True (what autograd's .grad accumulation gets)"""
+        if fresh:
+            nat = torch.zeros_like(self.data)
+        else:
+            if self._natural is None:
+                self._natural = torch.zeros_like(self.data)
+            nat = self._natural
+        _lib.check(_lib.lib().hrnb_grad_to_natural(self.grads.data_ptr(), nat.data_ptr(), self.segs_dev.data_ptr(),
                                                    self.block_seg_dev.data_ptr(), self.nblocks, _lib.stream_ptr()))
-        return [self._natural[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.p_offs)]
+        return [nat[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.p_offs)]

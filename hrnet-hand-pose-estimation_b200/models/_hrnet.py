@@ -51,6 +51,44 @@ def _materialise(root, specs):
         node.add_module(parts[-1], leaf)
 
 
+class _TrainForward(torch.autograd.Function):
+    """model.train() forward/backward through the CUDA training engine (train.TrainEngine): forward runs the
+    batch-statistics network, backward the hand-written data-/weight-gradient kernels; parameter gradients come back
+    in the parameters' own layout so that any torch optimizer (the reference builds Adam, lib/utils/utils.py:71-92)
+    and loss (core/loss.py) can be used unchanged."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        eng = model.train_engine()
+        want = model.return_features
+        p = eng.forward(x, want_features=want)
+        ctx.model, ctx.plan = model, p
+        ctx.set_materialize_grads(False)
+        out = p.out["heatmap"] if model.variant == "softmax" else p.out["logits"]
+        feat = p.feat.clone() if want else x.new_zeros(())
+        ctx.mark_non_differentiable(feat) if not want else None
+        return out.clone(), feat
+
+    @staticmethod
+    def backward(ctx, d_out, d_feat):
+        model, p = ctx.model, ctx.plan
+        eng = model.train_engine()
+        if d_feat is not None and bool((d_feat != 0).any()):
+            raise NotImplementedError("gradients through the inter_feat output are not supported by the B200 training engine")
+        if d_out is None:
+            d_out = torch.zeros_like(p.out["logits"])
+        with torch.cuda.device(eng.device):
+            if model.variant == "softmax":
+                p.d_heat.copy_(d_out)
+                p.d_coords.zero_()       # the soft-argmax is its own autograd node on the returned heat map
+            else:
+                p.d_logits.copy_(d_out)
+            eng.backward(p)
+            grads = eng.flat.natural_grads(fresh=True)
+        out = [g if prm.requires_grad else None for g, prm in zip(grads, eng.flat.params)]
+        return (None, None) + tuple(out)
+
+
 class PoseHighResolutionNet(nn.Module):
     """variant 'raw'     : forward -> (logits, stage3_branch0)                  [pose_hrnet.py:568]
        variant 'softmax' : forward -> (heatmap, concat_feat, trainable_temp)    [pose_hrnet_softmax.py:528]"""
@@ -71,6 +109,8 @@ class PoseHighResolutionNet(nn.Module):
         self._engine = None
         self._engine_key = None
         self._tensors = None
+        self._train_engine = None
+        self._train_key = None
         self.return_features = True   # set False to skip materialising the NCHW fp32 feature output
         self.static_outputs = False   # True: return the engine's static buffers (overwritten by the next call)
 
@@ -102,6 +142,8 @@ class PoseHighResolutionNet(nn.Module):
         self._engine = None
         self._engine_key = None
         self._tensors = None
+        self._train_engine = None
+        self._train_key = None
 
     def _apply(self, fn, *a, **k):
         self.invalidate()
@@ -116,6 +158,10 @@ class PoseHighResolutionNet(nn.Module):
             self._tensors = list(self.parameters()) + list(self.buffers())
         return sum(t._version for t in self._tensors), len(self._tensors)
 
+    def _weights_version(self):
+        """version counter of the parameters only (buffers are updated by the training kernels themselves)"""
+        return sum(p._version for p in self.parameters())
+
     def engine(self):
         from ..engine import HRNetEngine
         key = self._param_versions()
@@ -128,13 +174,32 @@ class PoseHighResolutionNet(nn.Module):
             self._engine_key = key
         return self._engine
 
+    def train_engine(self, **kw):
+        """the CUDA training engine of this module (created on first use; parameters become views of its flat fp32
+        buffer).  After parameters were changed by a torch optimizer the packed bf16 weights are refreshed."""
+        from ..train import TrainEngine
+        if self._train_engine is None:
+            if next(self.parameters()).device.type != "cuda":
+                raise RuntimeError("the B200 HRNet runs on CUDA only (no CPU fallback): call .cuda() first")
+            self._train_engine = TrainEngine(self, **kw)
+            self._tensors = None
+            self._train_key = self._weights_version()
+        elif self._train_key != self._weights_version():
+            with torch.cuda.device(self._train_engine.device):
+                self._train_engine.repack()
+            self._train_key = self._weights_version()
+        return self._train_engine
+
     def forward(self, x):
-        if self.training:
-            raise NotImplementedError(
-                "training-mode forward/backward (batch-stat BN, dgrad/wgrad kernels) is not built yet; "
-                "call model.eval() - there is deliberately no PyTorch/cuDNN fallback")
         if not x.is_cuda:
             raise RuntimeError("input must be a CUDA tensor (no CPU fallback)")
+        if self.training:
+            params = list(self.parameters())
+            out, feat = _TrainForward.apply(self, x, *params)
+            feat = feat if self.return_features else None
+            if self.variant == "softmax":
+                return out, feat, self.trainable_temp
+            return out, feat
         eng = self.engine()
         out = eng.forward(x, want_features=self.return_features)
         # the engine's outputs are static CUDA-graph buffers; hand out copies unless told otherwise

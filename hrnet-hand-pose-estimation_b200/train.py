@@ -103,7 +103,7 @@ class TrainPlan:
         self.all_bufs.append(ph.v)
         lib, s, d = _lib.lib(), x.v, ph.v
         self._f(lambda: _lib.check(lib.hrnb_phase_split(s.ptr, s.ps, s.N, s.C, s.H, s.W, d.ptr, d.ps, d.phase_stride,
-                                                        _lib.stream_ptr())))
+                                                        _lib.stream_ptr())), "phase_split")
 
         def back():
             assert ph.ginit
@@ -111,7 +111,7 @@ class TrainPlan:
             g, dst = ph.g, self._grad(x)
             mode = 2 if x.ginit else 1
             x.ginit = True
-            self._b(lambda: tops.phase_merge(g, dst, mode))
+            self._b(lambda: tops.phase_merge(g, dst, mode), "phase_merge")
         self.tape.append(back)
         return ph
 
@@ -125,15 +125,15 @@ class TrainPlan:
         self._ctx = key
         c = self._buf(sp.cout, Ho, Wo)
         y = T(self._buf(sp.cout, Ho, Wo))
-        self._f(self._conv_fn(L["fwd"], x.v, c))
+        self._f(self._conv_fn(L["fwd"], x.v, c), "conv:" + key)
         self.conv_out[key] = c
         sums, dsums = L["sums"], L["dsums"]
-        self._f(lambda: tops.bn_stats(c, sums))
+        self._f(lambda: tops.bn_stats(c, sums), "bn_stats:" + key)
         bp = tops.bn_params(c, sums, L["gamma"], L["beta"], y.v, res=res.v if res is not None else None, relu=relu,
                             running_mean=L["rm"], running_var=L["rv"])
         self.keep.append(bp)
         lib, bref = _lib.lib(), C.byref(bp)
-        self._f(lambda: _lib.check(lib.hrnb_bn_apply(bref, _lib.stream_ptr())))
+        self._f(lambda: _lib.check(lib.hrnb_bn_apply(bref, _lib.stream_ptr())), "bn_apply:" + key)
 
         def back():
             assert y.ginit, key
@@ -148,8 +148,8 @@ class TrainPlan:
                                     dres=dres, dres_mode=dmode)
             self.keep.append(bb)
             r = C.byref(bb)
-            self._b(lambda: _lib.check(lib.hrnb_bn_bwd_reduce(r, _lib.stream_ptr())))
-            self._b(lambda: _lib.check(lib.hrnb_bn_bwd_apply(r, _lib.stream_ptr())))
+            self._b(lambda: _lib.check(lib.hrnb_bn_bwd_reduce(r, _lib.stream_ptr())), "bn_bwd_reduce:" + key)
+            self._b(lambda: _lib.check(lib.hrnb_bn_bwd_apply(r, _lib.stream_ptr())), "bn_bwd_apply:" + key)
             self._conv_backward(L, x, dy, need_dx)
         self.tape.append(back)
         return y
@@ -160,21 +160,21 @@ class TrainPlan:
         dw = L["dw"]
         cin_g = dw.shape[1]
         if sp.stride == 1:
-            self._b(self._wgrad_fn(dc, x.v.ptr, x.v.ps, dw, cin_g, sp.cout, tops.fwd_taps_s1(sp.k, dc.Wp)))
+            self._b(self._wgrad_fn(dc, x.v.ptr, x.v.ps, dw, cin_g, sp.cout, tops.fwd_taps_s1(sp.k, dc.Wp)), "wgrad:" + sp.key)
             if need_dx:
                 gx = self._grad(x)
                 fn = self._conv_fn(L["dgrad"], dc, gx, res=gx if x.ginit else None)
                 x.ginit = True
-                self._b(fn)
+                self._b(fn, "dgrad:" + sp.key)
         else:
             for ph, taps in tops.fwd_taps_s2(dc.Wp).items():
-                self._b(self._wgrad_fn(dc, x.v.ptr + ph * x.v.phase_stride * 2, x.v.ps, dw, cin_g, sp.cout, taps))
+                self._b(self._wgrad_fn(dc, x.v.ptr + ph * x.v.phase_stride * 2, x.v.ps, dw, cin_g, sp.cout, taps), "wgrad:" + sp.key)
             if need_dx:
                 gx = self._grad(x)
                 for ph in range(4):
                     out = _phase_view(gx, ph)
                     self.keep.append(out)
-                    self._b(self._conv_fn(L["dgrad"][ph], dc, out, res=out if x.ginit else None))
+                    self._b(self._conv_fn(L["dgrad"][ph], dc, out, res=out if x.ginit else None), "dgrad:" + sp.key)
                 x.ginit = True
 
     def fuse(self, srcs, shifts, out_v=None, out_g=None):
@@ -188,7 +188,7 @@ class TrainPlan:
         p.N, p.H, p.W, p.C, p.relu = self.B, H, W, ch, 1
         self.keep.append(p)
         lib, ref = _lib.lib(), C.byref(p)
-        self._f(lambda: _lib.check(lib.hrnb_fuse_sum(ref, _lib.stream_ptr())))
+        self._f(lambda: _lib.check(lib.hrnb_fuse_sum(ref, _lib.stream_ptr())), "fuse")
 
         def back():
             assert out.ginit
@@ -197,7 +197,7 @@ class TrainPlan:
                 g = self._grad(s)
                 mode = 2 if s.ginit else 1
                 s.ginit = True
-                self._b(lambda g=g, sh=sh, mode=mode: tops.fuse_sum_bwd(out.g, out.v, g, sh, True, mode))
+                self._b(lambda g=g, sh=sh, mode=mode: tops.fuse_sum_bwd(out.g, out.v, g, sh, True, mode), "fuse_bwd")
         self.tape.append(back)
         return out
 
@@ -212,9 +212,9 @@ class TrainPlan:
         J = arch.num_joints
 
         # per-step zeroing of the statistics workspace and the parameter gradients
-        self._f(lambda: e.stats.zero_())
-        self._f(lambda: e.flat.grads.zero_())
-        self._f(lambda: torch._foreach_add_(e.nbt, 1))
+        self._f(lambda: e.stats.zero_(), "zero")
+        self._f(lambda: e.flat.grads.zero_(), "zero")
+        self._f(lambda: torch._foreach_add_(e.nbt, 1), "zero")
 
         cols = T(self._buf(32, H2, W2))
         x = self.x
@@ -297,7 +297,7 @@ class TrainPlan:
                 g = self._grad(src)
                 mode = 2 if src.ginit else 1
                 src.ginit = True
-                self._b(lambda g=g, gdst=gdst, mode=mode: tops.bilinear_up_bwd(gdst, g, align, mode))
+                self._b(lambda g=g, gdst=gdst, mode=mode: tops.bilinear_up_bwd(gdst, g, align, mode), "bilinear_bwd")
         self.tape.append(back_head)
 
         hid = self.unit("last_layer.0", cat, True)
@@ -305,7 +305,7 @@ class TrainPlan:
         # final conv (+bias, no BN) -> fp32 NCHW logits
         F3 = e.final
         logits = torch.empty((B, J, H4, W4), dtype=torch.float32, device=self.dev)
-        self._f(self._conv_fn(F3["fwd"], hid.v, logits))
+        self._f(self._conv_fn(F3["fwd"], hid.v, logits), "conv:last_layer.3")
         d_logits = torch.zeros((B, J, H4, W4), dtype=torch.float32, device=self.dev)
         dlog = self._buf(32 if J <= 32 else (J + 15) // 16 * 16, H4, W4)
 
@@ -315,9 +315,9 @@ class TrainPlan:
             if F3["dbias"] is not None:
                 self._b(lambda: tops.channel_sum(dlog, F3["dbias"], J))
             k = F3["spec"].k
-            self._b(self._wgrad_fn(dlog, hid.v.ptr, hid.v.ps, F3["dw"], arch.head_channels, J, tops.fwd_taps_s1(k, dlog.Wp)))
+            self._b(self._wgrad_fn(dlog, hid.v.ptr, hid.v.ps, F3["dw"], arch.head_channels, J, tops.fwd_taps_s1(k, dlog.Wp)), "wgrad:last_layer.3")
             gx = self._grad(hid)
-            self._b(self._conv_fn(F3["dgrad"], dlog, gx))
+            self._b(self._conv_fn(F3["dgrad"], dlog, gx), "dgrad:last_layer.3")
             hid.ginit = True
         self.tape.append(back_final)
         self.out = {"logits": logits}
@@ -578,3 +578,7 @@ class TrainEngine:
             p._graphed("opt", opt)
             self.model._engine = None          # folded inference weights are stale now
         return p
+
+    def launches_per_step(self, p, optimizer_step=True):
+        """kernel launches of libhrnb.so in one train_step (CUDA-graph replays do not pass through the library's counter)"""
+        return p.n_launch["fwd"] - 3 + p.n_launch["loss"] - 3 + p.n_launch["bwd"] + (3 if optimizer_step else 0)

@@ -242,10 +242,17 @@ int hrnb_pack_conv_weights_batch(const hrnb_pack_job* jobs_dev, const int32_t* b
                                  void* stream);
 
 /* ---- BatchNorm2d, train mode (momentum / eps as nn.BatchNorm2d) -------------------------------- */
-/* sums[c][0] += sum x, sums[c][1] += sum x^2 over the N*H*W real positions of PF8 tensor c (zero sums first). */
-int hrnb_bn_stats(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* sums, void* stream);
-/* out[c] += sum over positions (bias gradient of the BN-less final conv). */
-int hrnb_channel_sum(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);
+/* Reductions over positions are DETERMINISTIC: blocks store partial sums into the workspace `ws` and the last block
+ * of a channel plane adds them in block order (no fp32 atomics, whose ordering noise a deep BatchNorm network
+ * amplifies chaotically).  ws: hrnb_reduce_ws_floats() floats, zero-initialised once by the caller; calls sharing a
+ * workspace must be ordered on one stream. */
+int64_t hrnb_reduce_ws_floats(void);
+/* sums[c][0] = sum x, sums[c][1] = sum x^2 over the N*H*W real positions of PF8 tensor c. */
+int hrnb_bn_stats(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* sums, float* ws,
+                  void* stream);
+/* out[c] = sum over positions, c < C (bias gradient of the BN-less final conv). */
+int hrnb_channel_sum(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* out, float* ws,
+                     void* stream);
 
 typedef struct hrnb_bn_params {
   const void* c;          /* conv output (pre-BN), PF8                                               */
@@ -274,7 +281,8 @@ typedef struct hrnb_bn_bwd_params {
   int64_t c_ps;
   const float* sums;      /* forward statistics [C][2]                                                */
   const float* gamma;
-  float* dsums;           /* [C][2] workspace, zeroed by the caller, filled by hrnb_bn_bwd_reduce     */
+  float* dsums;           /* [C][2] written by hrnb_bn_bwd_reduce (sum g, sum g*xhat)                */
+  float* ws;              /* reduction workspace (hrnb_reduce_ws_floats)                              */
   void* dc;               /* gradient w.r.t. the conv output (may alias dy)                           */
   int64_t dc_ps;
   void* dres;             /* gradient buffer of the residual input or NULL                            */
