@@ -429,8 +429,10 @@ def run_b200_train(args):
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert float(lo) == float(hi), "ranks start from different weights"
-        eng.flat.set_grad_scale(1.0 / world)
-    allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    from hrnet_b200.parallel import GradAllReduce
+    allreduce = GradAllReduce(eng.flat.grads.numel(), n_buckets=1) if world > 1 else None
+    if world > 1:
+        eng.flat.set_grad_scale(allreduce.mean_scale)
     plan = eng.plan(B, H, W)
     pool = []
     for i in range(4):
@@ -500,7 +502,7 @@ def run_b200_train(args):
         return
 
     # ---- roofline of the dominant kernels: every tensor-pipe launch of one step (conv fwd, dgrad, wgrad) ----
-    fns = plan.fwd + plan.loss_steps + plan.bwd
+    fns = plan.fwd_fns + plan.loss_steps + plan.bwd_fns
     names = plan.fwd_names + ["loss"] * len(plan.loss_steps) + plan.bwd_names
     serial_ms, kinds, detail = timed_kinds(fns, names, torch)
     tshare = sum(kinds.get(k, [0.0, 0])[0] for k in ("conv", "dgrad", "wgrad"))

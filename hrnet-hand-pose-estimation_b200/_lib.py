@@ -17,6 +17,7 @@ HRNB_CONV_OUT_NCHW = 2
 HRNB_CONV_GATHER = 4
 HRNB_CONV_IN_PHASES = 8
 HRNB_CONV_OUT_PHASES = 16
+HRNB_CONV_NO_PDL = 32
 
 
 def guard_lead(Wp):
@@ -164,6 +165,8 @@ def lib():
             fn.argtypes = args
         if h.hrnb_abi_version() != 2:
             raise HrnbError("libhrnb.so ABI version mismatch")
+        if os.environ.get("HRNB_NO_PDL", "0") == "1":      # debug: launch the conv kernels without programmatic dependent launch
+            h.hrnb_debug_set(2, 1)
         _lib = h
     return _lib
 

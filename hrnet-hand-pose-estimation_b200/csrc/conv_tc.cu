@@ -713,7 +713,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_debug[2] ? 0 : 1;   // debug knob 2: disable programmatic dependent launch
+  cfg.numAttrs = (g_debug[2] || (p->flags & HRNB_CONV_NO_PDL)) ? 0 : 1;   // debug knob 2 / flag: no programmatic dependent launch
   void* kargs[1] = {(void*)&k};
   cudaError_t le = cudaLaunchKernelExC(&cfg, fn, kargs);
   count_launch();

@@ -54,10 +54,20 @@ __device__ __forceinline__ void grid_reduce_ordered(float (&v)[NV], float* __res
   __syncthreads();
   if (ticket_s == gridDim.x - 1) {      // last block of this plane: all partials are visible
     __threadfence();
+    // fixed-order two-level sum: 16 slices of blocks (slice j takes blocks j, j+16, ...) in parallel, then slices in order
+    __shared__ float red2[16][16];
+    const int i = threadIdx.x & 15, j = threadIdx.x >> 4;
+    float s = 0.f;
+    if (i < NV) {
+      for (unsigned b = j; b < gridDim.x; b += 16) s += __ldcg(partials + (size_t)b * 16 + i);
+    }
+    red2[j][i] = s;
+    __syncthreads();
     if (threadIdx.x < NV) {
-      float s = 0.f;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partials + (size_t)b * 16 + threadIdx.x);
-      dst[(size_t)plane * NV + threadIdx.x] = s;
+      float t = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) t += red2[jj][threadIdx.x];
+      dst[(size_t)plane * NV + threadIdx.x] = t;
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
@@ -498,7 +508,7 @@ __global__ void __launch_bounds__(256) grad_to_natural_kernel(const float* __res
 using namespace hrnb;
 
 static unsigned reduce_blocks(long long P) {
-  long long b = (P + 256 * 8 - 1) / (256 * 8);   // ~8 positions per thread
+  long long b = (P + 256 * 2 - 1) / (256 * 2);   // ~2 positions per thread (the kernels are latency bound on small maps)
   if (b < 1) b = 1;
   if (b > kMaxRedBlocks) b = kMaxRedBlocks;
   return (unsigned)b;

@@ -139,6 +139,7 @@ class ConvLayer:
         self.flags = (HRNB_CONV_RELU if relu else 0) | (HRNB_CONV_OUT_NCHW if out_nchw else 0) | \
                      (HRNB_CONV_GATHER if stride == 2 else 0)
         self.force_gather = False
+        self.no_pdl = False
 
     def pack(self, bn, kc):
         if (bn, kc) not in self.packs:

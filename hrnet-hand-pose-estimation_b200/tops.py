@@ -83,19 +83,21 @@ def wgrad_conv(dy, x, dw, k, stride):
 _WS = {}
 
 
-def reduce_ws(device):
-    """the per-device workspace of the deterministic reductions (zero-initialised once; self-resetting counters)"""
-    key = torch.device(device)
-    if key.index is None:
-        key = torch.device("cuda", torch.cuda.current_device())
+def reduce_ws(device, sid=0):
+    """workspace of the deterministic reductions, one per (device, stream slot): zero-initialised once, the counters
+    reset themselves; kernels sharing a workspace must be ordered on one stream"""
+    dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    key = (dev, sid)
     if key not in _WS:
-        _WS[key] = torch.zeros(int(_lib.lib().hrnb_reduce_ws_floats()), dtype=torch.float32, device=key)
+        _WS[key] = torch.zeros(int(_lib.lib().hrnb_reduce_ws_floats()), dtype=torch.float32, device=dev)
     return _WS[key]
 
 
-def bn_stats(c, sums):
-    _lib.check(_lib.lib().hrnb_bn_stats(c.ptr, c.ps, c.N, c.C, c.H, c.W, sums.data_ptr(), reduce_ws(sums.device).data_ptr(),
-                                        _lib.stream_ptr()))
+def bn_stats(c, sums, sid=0):
+    _lib.check(_lib.lib().hrnb_bn_stats(c.ptr, c.ps, c.N, c.C, c.H, c.W, sums.data_ptr(),
+                                        reduce_ws(sums.device, sid).data_ptr(), _lib.stream_ptr()))
 
 
 def bn_params(c, sums, gamma, beta, out, res=None, relu=True, running_mean=None, running_var=None):
@@ -114,12 +116,12 @@ def bn_apply(*a, **k):
     _lib.check(_lib.lib().hrnb_bn_apply(C.byref(p), _lib.stream_ptr()))
 
 
-def bn_bwd_params(dy, y, c, sums, gamma, dsums, dc, dgamma, dbeta, relu=True, dres=None, dres_mode=1):
+def bn_bwd_params(dy, y, c, sums, gamma, dsums, dc, dgamma, dbeta, relu=True, dres=None, dres_mode=1, sid=0):
     p = BnBwdParams()
     p.dy, p.dy_ps = dy.ptr, dy.ps
     p.y, p.y_ps = (y.ptr, y.ps) if (y is not None and relu) else (None, 0)
     p.c, p.c_ps, p.sums, p.gamma, p.dsums = c.ptr, c.ps, sums.data_ptr(), gamma.data_ptr(), dsums.data_ptr()
-    p.ws = reduce_ws(dsums.device).data_ptr()
+    p.ws = reduce_ws(dsums.device, sid).data_ptr()
     p.dc, p.dc_ps = dc.ptr, dc.ps
     p.dres, p.dres_ps, p.dres_mode = (dres.ptr, dres.ps, dres_mode) if dres is not None else (None, 0, 0)
     p.dgamma = dgamma.data_ptr() if dgamma is not None else None
@@ -154,6 +156,6 @@ def phase_merge(src, dst, mode=1):
                                             mode, _lib.stream_ptr()))
 
 
-def channel_sum(c, out, C_real):
-    _lib.check(_lib.lib().hrnb_channel_sum(c.ptr, c.ps, c.N, C_real, c.H, c.W, out.data_ptr(), reduce_ws(out.device).data_ptr(),
-                                           _lib.stream_ptr()))
+def channel_sum(c, out, C_real, sid=0):
+    _lib.check(_lib.lib().hrnb_channel_sum(c.ptr, c.ps, c.N, C_real, c.H, c.W, out.data_ptr(),
+                                           reduce_ws(out.device, sid).data_ptr(), _lib.stream_ptr()))

@@ -15,6 +15,7 @@ kernel writes (first contribution) or accumulates (later ones).  Each unit conv 
 conv output `c` and its output `y` (bf16 PF8) for the backward pass; gradients are bf16 PF8, parameter gradients fp32.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -25,10 +26,10 @@ from .ops import ConvLayer, PF8, PhasePF8, Repacker
 
 class T:
     """activation node: value + (lazily allocated) gradient buffer"""
-    __slots__ = ("v", "g", "ginit")
+    __slots__ = ("v", "g", "ginit", "g_sid")
 
     def __init__(self, v, g=None):
-        self.v, self.g, self.ginit = v, g, False
+        self.v, self.g, self.ginit, self.g_sid = v, g, False, None
 
 
 def _like(v, device):
@@ -46,8 +47,9 @@ class TrainPlan:
     def __init__(self, eng, B, H, W):
         self.eng, self.B, self.H, self.W = eng, B, H, W
         self.dev = eng.device
-        self.fwd, self.loss_steps, self.bwd = [], [], []
-        self.bwd_names, self.fwd_names, self._ctx = [], [], ""
+        self.fwd, self.loss_steps, self.bwd = [], [], []      # fwd / bwd: (kind, sid, fn | other stream, name)
+        self._ctx, self._sid = "", 0
+        self.multi_stream = eng.multi_stream
         self.all_bufs = []      # every activation / gradient buffer of the plan: the launch parameter structs hold raw
                                 # device pointers only, so the plan must own the tensors for as long as it can be replayed
         self.tape = []
@@ -74,16 +76,54 @@ class TrainPlan:
         return t.g
 
     def _f(self, fn, name=""):
-        self.fwd.append(fn)
-        self.fwd_names.append(name or self._ctx)
+        self.fwd.append(("op", self._sid, fn, name or self._ctx))
         self.n_launch["fwd"] += 1
 
     def _b(self, fn, name=""):
-        self.bwd.append(fn)
-        self.bwd_names.append(name or self._ctx)
+        self.bwd.append(("op", self._sid, fn, name or self._ctx))
         self.n_launch["bwd"] += 1
 
+    def _wait(self, steps, sid, other):
+        """stream `sid` waits for everything queued on stream `other` so far"""
+        if self.multi_stream and sid != other and other is not None:
+            steps.append(("wait", sid, other, ""))
+
+    def on(self, sid):
+        self._sid = sid if self.multi_stream else 0
+
+    def fwait(self, sid, other):
+        self._wait(self.fwd, sid, other)
+
+    def _gr(self, t):
+        """backward op on the current stream is about to READ t.g: order it after the stream that wrote it last"""
+        self._wait(self.bwd, self._sid, t.g_sid)
+
+    def _gw(self, t):
+        """backward op on the current stream is about to write / accumulate into t.g -> (buffer, mode)"""
+        g = self._grad(t)
+        self._wait(self.bwd, self._sid, t.g_sid)
+        mode = 2 if t.ginit else 1
+        t.ginit, t.g_sid = True, self._sid
+        return g, mode
+
+    @property
+    def fwd_fns(self):
+        return [st[2] for st in self.fwd if st[0] == "op"]
+
+    @property
+    def fwd_names(self):
+        return [st[3] for st in self.fwd if st[0] == "op"]
+
+    @property
+    def bwd_fns(self):
+        return [st[2] for st in self.bwd if st[0] == "op"]
+
+    @property
+    def bwd_names(self):
+        return [st[3] for st in self.bwd if st[0] == "op"]
+
     def _conv_fn(self, layer, x, out, res=None):
+        layer.no_pdl = not self.eng.pdl
         p = layer.params(x, out, res)
         self.keep.append(p)
         lib, ref = _lib.lib(), C.byref(p)
@@ -105,12 +145,14 @@ class TrainPlan:
         self._f(lambda: _lib.check(lib.hrnb_phase_split(s.ptr, s.ps, s.N, s.C, s.H, s.W, d.ptr, d.ps, d.phase_stride,
                                                         _lib.stream_ptr())), "phase_split")
 
+        sid = self._sid
+
         def back():
             assert ph.ginit
-            self._ctx = "phase_merge"
-            g, dst = ph.g, self._grad(x)
-            mode = 2 if x.ginit else 1
-            x.ginit = True
+            self._ctx, self._sid = "phase_merge", sid
+            self._gr(ph)
+            g = ph.g
+            dst, mode = self._gw(x)
             self._b(lambda: tops.phase_merge(g, dst, mode), "phase_merge")
         self.tape.append(back)
         return ph
@@ -128,7 +170,8 @@ class TrainPlan:
         self._f(self._conv_fn(L["fwd"], x.v, c), "conv:" + key)
         self.conv_out[key] = c
         sums, dsums = L["sums"], L["dsums"]
-        self._f(lambda: tops.bn_stats(c, sums), "bn_stats:" + key)
+        sid = self._sid
+        self._f(lambda: tops.bn_stats(c, sums, sid), "bn_stats:" + key)
         bp = tops.bn_params(c, sums, L["gamma"], L["beta"], y.v, res=res.v if res is not None else None, relu=relu,
                             running_mean=L["rm"], running_var=L["rv"])
         self.keep.append(bp)
@@ -137,15 +180,14 @@ class TrainPlan:
 
         def back():
             assert y.ginit, key
-            self._ctx = key
+            self._ctx, self._sid = key, sid
+            self._gr(y)
             dy = y.g
             dres, dmode = None, 0
             if res is not None:
-                dres = self._grad(res)
-                dmode = 2 if res.ginit else 1
-                res.ginit = True
+                dres, dmode = self._gw(res)
             bb = tops.bn_bwd_params(dy, y.v, c, sums, L["gamma"], dsums, dy, L["dgamma"], L["dbeta"], relu=relu,
-                                    dres=dres, dres_mode=dmode)
+                                    dres=dres, dres_mode=dmode, sid=sid)
             self.keep.append(bb)
             r = C.byref(bb)
             self._b(lambda: _lib.check(lib.hrnb_bn_bwd_reduce(r, _lib.stream_ptr())), "bn_bwd_reduce:" + key)
@@ -162,20 +204,17 @@ class TrainPlan:
         if sp.stride == 1:
             self._b(self._wgrad_fn(dc, x.v.ptr, x.v.ps, dw, cin_g, sp.cout, tops.fwd_taps_s1(sp.k, dc.Wp)), "wgrad:" + sp.key)
             if need_dx:
-                gx = self._grad(x)
-                fn = self._conv_fn(L["dgrad"], dc, gx, res=gx if x.ginit else None)
-                x.ginit = True
-                self._b(fn, "dgrad:" + sp.key)
+                gx, mode = self._gw(x)
+                self._b(self._conv_fn(L["dgrad"], dc, gx, res=gx if mode == 2 else None), "dgrad:" + sp.key)
         else:
             for ph, taps in tops.fwd_taps_s2(dc.Wp).items():
                 self._b(self._wgrad_fn(dc, x.v.ptr + ph * x.v.phase_stride * 2, x.v.ps, dw, cin_g, sp.cout, taps), "wgrad:" + sp.key)
             if need_dx:
-                gx = self._grad(x)
+                gx, mode = self._gw(x)
                 for ph in range(4):
                     out = _phase_view(gx, ph)
                     self.keep.append(out)
-                    self._b(self._conv_fn(L["dgrad"][ph], dc, out, res=out if x.ginit else None), "dgrad:" + sp.key)
-                x.ginit = True
+                    self._b(self._conv_fn(L["dgrad"][ph], dc, out, res=out if mode == 2 else None), "dgrad:" + sp.key)
 
     def fuse(self, srcs, shifts, out_v=None, out_g=None):
         ch, (H, W) = srcs[0].v.C, (srcs[0].v.H << shifts[0], srcs[0].v.W << shifts[0])
@@ -190,13 +229,14 @@ class TrainPlan:
         lib, ref = _lib.lib(), C.byref(p)
         self._f(lambda: _lib.check(lib.hrnb_fuse_sum(ref, _lib.stream_ptr())), "fuse")
 
+        sid = self._sid
+
         def back():
             assert out.ginit
-            self._ctx = "fuse"
+            self._ctx, self._sid = "fuse", sid
+            self._gr(out)
             for s, sh in zip(srcs, shifts):
-                g = self._grad(s)
-                mode = 2 if s.ginit else 1
-                s.ginit = True
+                g, mode = self._gw(s)
                 self._b(lambda g=g, sh=sh, mode=mode: tops.fuse_sum_bwd(out.g, out.v, g, sh, True, mode), "fuse_bwd")
         self.tape.append(back)
         return out
@@ -219,7 +259,7 @@ class TrainPlan:
         cols = T(self._buf(32, H2, W2))
         x = self.x
         self._f(lambda: _lib.check(lib.hrnb_stem_im2col(x.data_ptr(), cols.v.ptr, cols.v.ps, B, self.H, self.W,
-                                                        _lib.stream_ptr())))
+                                                        _lib.stream_ptr())), "stem_im2col")
         t = self.unit("conv1", cols, True, need_dx=False)
         cur = self.unit("conv2", self.split(t), True)
 
@@ -230,24 +270,40 @@ class TrainPlan:
             res = self.unit(pre + ".downsample.0", cur, False) if b == 0 else cur
             cur = self.unit(pre + ".conv3", c2, True, res=res)
 
-        xs = [self.unit("transition1.0.0", cur, True), self.unit("transition1.1.0.0", self.split(cur), True)]
+        # branch i of the multi-resolution stages lives on stream i (they only meet in the fuse layers)
+        xs = [self.unit("transition1.0.0", cur, True)]
+        ph = self.split(cur)
+        self.fwait(1, 0)
+        self.on(1)
+        xs.append(self.unit("transition1.1.0.0", ph, True))
         stage3_b0 = None
         cat = T(None)
         for s, nmod in zip((2, 3, 4), arch.modules):
             nb = s
             if s > 2:
-                xs.append(self.unit("transition%d.%d.0.0" % (s - 1, nb - 1), self.split(xs[-1]), True))
+                self.on(nb - 2)
+                ph = self.split(xs[-1])
+                self.fwait(nb - 1, nb - 2)
+                self.on(nb - 1)
+                xs.append(self.unit("transition%d.%d.0.0" % (s - 1, nb - 1), ph, True))
             for m in range(nmod):
                 pre = "stage%d.%d" % (s, m)
                 last_module = (s == 4 and m == nmod - 1)
+                splits = {}
                 for i in range(nb):
+                    self.on(i)
                     for b in range(arch.blocks):
                         bp = "%s.branches.%d.%d" % (pre, i, b)
                         y = self.unit(bp + ".conv1", xs[i], True)
                         xs[i] = self.unit(bp + ".conv2", y, True, res=xs[i])
-                splits = {}
+                    if i < nb - 1:
+                        splits[i] = self.split(xs[i])      # phase copy for the stride-2 chains that start at branch i
+                for i in range(nb):                        # every fuse output needs every branch
+                    for j in range(nb):
+                        self.fwait(i, j)
                 outs = []
                 for i in range(nb):
+                    self.on(i)
                     srcs, shifts = [], []
                     for j in range(nb):
                         if j == i:
@@ -256,8 +312,6 @@ class TrainPlan:
                             srcs.append(self.unit("%s.fuse_layers.%d.%d.0" % (pre, i, j), xs[j], False))
                             shifts.append(j - i)
                         else:
-                            if j not in splits:
-                                splits[j] = self.split(xs[j])
                             t = splits[j]
                             for k in range(i - j):
                                 last = k == i - j - 1
@@ -276,27 +330,32 @@ class TrainPlan:
             if s == 3:
                 stage3_b0 = xs[0]
 
-        # head: bilinear up-sampling of branches 1..3 into the concat buffer
+        # head: bilinear up-sampling of branches 1..3 into the concat buffer (each on its branch's stream)
         align = 1 if e.variant == "softmax" else 0
         plane0 = ch[0] // 8
         ups = []
         for i in range(1, 4):
+            self.on(i)
             dst = cat.v.view_planes(plane0, ch[i] // 8)
             gdst = cat.g.view_planes(plane0, ch[i] // 8)
             plane0 += ch[i] // 8
             src = xs[i]
             self.keep += [dst, gdst]
             self._f(lambda src=src, dst=dst: _lib.check(lib.hrnb_bilinear_up(
-                src.v.ptr, src.v.ps, src.v.N, src.v.C, src.v.H, src.v.W, dst.ptr, dst.ps, dst.H, dst.W, align, _lib.stream_ptr())))
-            ups.append((src, gdst))
+                src.v.ptr, src.v.ps, src.v.N, src.v.C, src.v.H, src.v.W, dst.ptr, dst.ps, dst.H, dst.W, align, _lib.stream_ptr())),
+                "bilinear")
+            ups.append((i, src, gdst))
+        for i in range(1, 4):
+            self.fwait(0, i)
+        self.on(0)
 
         def back_head():
             assert cat.ginit
-            cat_b0.ginit = True
-            for src, gdst in ups:
-                g = self._grad(src)
-                mode = 2 if src.ginit else 1
-                src.ginit = True
+            cat_b0.ginit, cat_b0.g_sid = True, cat.g_sid
+            for i, src, gdst in ups:
+                self.on(i)
+                self._gr(cat)
+                g, mode = self._gw(src)
                 self._b(lambda g=g, gdst=gdst, mode=mode: tops.bilinear_up_bwd(gdst, g, align, mode), "bilinear_bwd")
         self.tape.append(back_head)
 
@@ -310,15 +369,16 @@ class TrainPlan:
         dlog = self._buf(32 if J <= 32 else (J + 15) // 16 * 16, H4, W4)
 
         def back_final():
+            self.on(0)
+            self._ctx = "last_layer.3"
             self._b(lambda: _lib.check(lib.hrnb_nchw_f32_to_pf8(d_logits.data_ptr(), B, J, H4, W4, dlog.ptr, dlog.ps,
-                                                                _lib.stream_ptr())))
+                                                                _lib.stream_ptr())), "nchw_to_pf8")
             if F3["dbias"] is not None:
-                self._b(lambda: tops.channel_sum(dlog, F3["dbias"], J))
+                self._b(lambda: tops.channel_sum(dlog, F3["dbias"], J, 0), "channel_sum")
             k = F3["spec"].k
             self._b(self._wgrad_fn(dlog, hid.v.ptr, hid.v.ps, F3["dw"], arch.head_channels, J, tops.fwd_taps_s1(k, dlog.Wp)), "wgrad:last_layer.3")
-            gx = self._grad(hid)
+            gx, _ = self._gw(hid)
             self._b(self._conv_fn(F3["dgrad"], dlog, gx), "dgrad:last_layer.3")
-            hid.ginit = True
         self.tape.append(back_final)
         self.out = {"logits": logits}
         self.d_logits = d_logits
@@ -340,7 +400,8 @@ class TrainPlan:
             self.d_coords = torch.zeros_like(coords)
             temp = e.temp_param
             self._f(lambda: _lib.check(lib.hrnb_softmax_softargmax(logits.data_ptr(), temp.data_ptr(), BJ, H4, W4,
-                                                                   heat.data_ptr(), coords.data_ptr(), _lib.stream_ptr())))
+                                                                   heat.data_ptr(), coords.data_ptr(), _lib.stream_ptr())),
+                    "softmax_softargmax")
             self.out["heatmap"], self.out["coords"] = heat, coords
 
             def loss_fused():
@@ -380,16 +441,34 @@ class TrainPlan:
                                                                    _lib.stream_ptr()))
 
         # backward launch list from the tape
+        self.on(0)
         if self.softmax_back is not None:
-            self._b(self.softmax_back)
+            self._b(self.softmax_back, "softmax_bwd")
         for back in reversed(self.tape):
             back()
         self.tape = None
 
     # ---- execution ------------------------------------------------------------------------------------------
+    def _run(self, steps):
+        main = torch.cuda.current_stream()
+        side = self.eng.side_streams if self.multi_stream else []
+        streams = [main] + side
+        for sd in side:
+            sd.wait_stream(main)
+        for kind, sid, a, _ in steps:
+            if kind == "op":
+                if sid == 0:
+                    a()
+                else:
+                    with torch.cuda.stream(streams[sid]):
+                        a()
+            else:
+                streams[sid].wait_stream(streams[a])
+        for sd in side:
+            main.wait_stream(sd)
+
     def run_forward(self, want_features=False):
-        for fn in self.fwd:
-            fn()
+        self._run(self.fwd)
         if want_features:
             self.feat_fn()
 
@@ -398,8 +477,7 @@ class TrainPlan:
             fn()
 
     def run_backward(self):
-        for fn in self.bwd:
-            fn()
+        self._run(self.bwd)
 
     def _graphed(self, name, body):
         if not self.eng.use_graph:
@@ -421,7 +499,7 @@ class TrainEngine:
     per-shape TrainPlans of one network on one device."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, loss_factors=(1.0, 0.1),
-                 use_graph=True):
+                 use_graph=True, multi_stream=None):
         self.model = model
         self.arch, self.variant = model.arch, model.variant
         self.device = next(model.parameters()).device
@@ -429,8 +507,11 @@ class TrainEngine:
             raise RuntimeError("the B200 HRNet trains on CUDA only (no CPU fallback): call .cuda() first")
         self.loss_factors = tuple(float(f) for f in loss_factors)
         self.use_graph = use_graph
+        self.multi_stream = os.environ.get("HRNB_SINGLE_STREAM", "0") != "1" if multi_stream is None else bool(multi_stream)
+        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "0") == "1"     # programmatic dependent launch of the conv kernels
         self.plans = {}
         with torch.cuda.device(self.device):
+            self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
             self._setup(lr, betas, eps, weight_decay)
 
     def _setup(self, lr, betas, eps, weight_decay):

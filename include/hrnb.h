@@ -42,7 +42,8 @@ enum {
   HRNB_CONV_OUT_NCHW = 2,   /* write fp32 NCHW [N, cout_real, H, W] instead of PF8 bf16       */
   HRNB_CONV_GATHER = 4,     /* per-tap gathered A operand (any stride); otherwise flat-shift      */
   HRNB_CONV_IN_PHASES = 8,  /* 3x3 stride-2 conv whose input is given as 4 phase tensors (see below) */
-  HRNB_CONV_OUT_PHASES = 16 /* write the PF8 output as 4 phase tensors for a following stride-2 conv */
+  HRNB_CONV_OUT_PHASES = 16, /* write the PF8 output as 4 phase tensors for a following stride-2 conv */
+  HRNB_CONV_NO_PDL = 32     /* launch without programmatic dependent launch (plain stream order)      */
 };
 
 /* One conv + folded-BN bias (+ residual) (+ ReLU) launch.

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from hrnet_b200.parallel import gather_joints, max_over_ranks, shard_range
+from hrnet_b200.parallel import GradAllReduce, gather_joints, max_over_ranks, shard_range
 
 
 def test_shard_range_is_a_partition():
@@ -41,6 +41,14 @@ def _worker(rank, world, port, n_total):
         # weak-scaling aggregate the bench reports: units of all ranks / slowest rank's time
         value = n_total / (ms / 1e3)
         assert abs(value - n_total / 0.015) < 1e-6
+        # training exchange step: bucketed sum-all-reduce of the flat gradient buffer; mean via the optimizer's scale
+        for nb in (1, 3):
+            grads = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+            ar = GradAllReduce(grads.numel(), n_buckets=nb)
+            assert ar.bounds[0][0] == 0 and ar.bounds[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(ar.bounds, ar.bounds[1:]))
+            ar(grads)
+            assert torch.equal(grads, torch.arange(1000, dtype=torch.float32) * sum(range(1, world + 1)))
+            assert ar.mean_scale == 1.0 / world
     finally:
         dist.destroy_process_group()
 

@@ -15,14 +15,14 @@ del junk
 eng = TrainEngine(m, use_graph=False)
 p = eng.plan(B, H, W)
 p.x.copy_(xs); p.gt_heat.copy_(gts); p.gt_xy.copy_(xys); p.vis.copy_(viss)
-for i, fn in enumerate(p.fwd):
+for i, fn in enumerate(p.fwd_fns):
     fn(); torch.cuda.synchronize()
     if not bool(torch.isfinite(eng.stats).all()):
         print("first non-finite BN statistics after fwd step", i, p.fwd_names[i])
         break
 print("logits finite", bool(torch.isfinite(p.out["logits"]).all()))
 p.run_loss(); torch.cuda.synchronize(); print("losses", p.losses.tolist())
-for i, fn in enumerate(p.bwd):
+for i, fn in enumerate(p.bwd_fns):
     fn(); torch.cuda.synchronize()
     if not bool(torch.isfinite(eng.flat.grads).all()) or not bool(torch.isfinite(eng.stats).all()):
         print("first non-finite gradient after bwd step", i, p.bwd_names[i]); break

@@ -23,12 +23,12 @@ def trial(tag, no_pdl, sync_each, reps=4):
     names = [n for n, _ in m.named_parameters()]
     for r in range(reps):
         p.x.copy_(x); p.gt_heat.copy_(gt); p.gt_xy.copy_(xy); p.vis.copy_(vis)
-        for fn in p.fwd:
+        for fn in p.fwd_fns:
             fn()
             if sync_each: torch.cuda.synchronize()
         p.run_loss()
         first = None
-        for i, fn in enumerate(p.bwd):
+        for i, fn in enumerate(p.bwd_fns):
             fn()
             if sync_each: torch.cuda.synchronize()
         torch.cuda.synchronize()
