@@ -56,8 +56,8 @@ def test_no_cpu_fallback():
     m = pose_hrnet_softmax.get_pose_net(make_cfg(32), is_train=False).eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 3, 256, 256))
-    m.train()
-    with pytest.raises(NotImplementedError):
+    m.train()                                   # training runs on the CUDA engine too: CPU tensors / modules are refused
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 3, 256, 256))
     from hrnet_b200.core.loss import HeatmapLoss
     from hrnet_b200.utils.heatmap_decoding import get_final_preds
