@@ -506,7 +506,7 @@ class TrainEngine:
         if self.device.type != "cuda":
             raise RuntimeError("the B200 HRNet trains on CUDA only (no CPU fallback): call .cuda() first")
         self.loss_factors = tuple(float(f) for f in loss_factors)
-        self.use_graph = use_graph
+        self.use_graph = use_graph and os.environ.get("HRNB_NO_GRAPH", "0") != "1"
         # Branch-parallel streams are opt-in (HRNB_TRAIN_STREAMS=1 or multi_stream=True): measured 29.1 vs 33.0 ms/step at
         # batch 64, but one of ~15 multi-stream bench runs ended in a device-side mbarrier time-out that has not been
         # reproduced or explained yet, so the default is the single-stream plan that never showed it.
