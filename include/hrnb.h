@@ -272,6 +272,10 @@ typedef struct hrnb_bn_params {
   float eps, momentum;
 } hrnb_bn_params;
 int hrnb_bn_apply(const hrnb_bn_params* p, void* stream);
+/* hrnb_bn_stats + hrnb_bn_apply in ONE cooperative launch (second pass over c served from L2): writes sums_out[C][2]
+ * (p->sums is ignored), then out.  All blocks synchronise through `ws`, so the launch is cooperative and its grid is
+ * sized to the device occupancy. */
+int hrnb_bn_forward(const hrnb_bn_params* p, float* sums_out, float* ws, void* stream);
 
 typedef struct hrnb_bn_bwd_params {
   const void* dy;         /* gradient of the unit output, PF8                                         */
@@ -297,6 +301,8 @@ typedef struct hrnb_bn_bwd_params {
 } hrnb_bn_bwd_params;
 int hrnb_bn_bwd_reduce(const hrnb_bn_bwd_params* p, void* stream);
 int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream);
+/* hrnb_bn_bwd_reduce + hrnb_bn_bwd_apply in ONE cooperative launch. */
+int hrnb_bn_backward(const hrnb_bn_bwd_params* p, void* stream);
 
 /* ---- backward of hrnb_fuse_sum / hrnb_bilinear_up / hrnb_phase_split ---------------------------- */
 /* dsrc[q] (=|+=) sum over the 2^shift x 2^shift block of dy * (y > 0) (mode 1 write, 2 accumulate); dy, y on the
