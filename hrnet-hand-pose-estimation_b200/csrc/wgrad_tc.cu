@@ -247,7 +247,11 @@ static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid) 
   if (NT < 16 || NT > 256 || NT % 16 || p->cin % NT) return fail(HRNB_EINVAL, "wgrad: NT must be a multiple of 16 (<= 256) dividing cin");
   k->NT = NT;
   k->n_cit = p->cin / NT;
-  int TG = p->TG > 0 ? p->TG : 512 / NT;
+  // taps per CTA: three (one kernel row) for 3x3 convs - balanced groups, and fewer K splits (= fewer fp32 reductions
+  // into dW) than with all nine taps per CTA [measured on B200, tools/wgrad_bench.py: 43 -> 37 us (32 ch @ 64x64),
+  // 29.5 -> 20.5 us (64 ch @ 32x32), 68.6 -> 47 us (64 ch @ 64x64) at batch 64]
+  int TG = p->TG > 0 ? p->TG : (p->ntap == 9 ? 3 : 512 / NT);
+  if (TG * NT > 512) TG = 512 / NT;
   if (TG > p->ntap) TG = p->ntap;
   if (TG < 1 || TG * NT > 512) return fail(HRNB_EINVAL, "wgrad: TG*NT exceeds 512 TMEM columns");
   k->TG = TG;
@@ -288,7 +292,7 @@ static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid) 
   const int base_items = k->n_cot * k->n_cit * k->n_tg;
   int ksplit = p->ksplit;
   if (ksplit <= 0) {
-    ksplit = (148 + base_items / 2) / base_items;
+    ksplit = 148 / base_items;       // one wave of CTAs: rounding up to 152 items costs a whole second wave
     if (ksplit < 1) ksplit = 1;
   }
   if (ksplit > k->nchunks) ksplit = k->nchunks;
