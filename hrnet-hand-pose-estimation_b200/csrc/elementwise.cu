@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 __global__ void __launch_bounds__(256) phase_split_kernel(const __nv_bfloat16* __restrict__ src, long long src_ps, Geo g,
                                                          __nv_bfloat16* __restrict__ dst, long long dst_ps,
                                                          long long phase_stride) {
+  pdl_enter();
   const int plane = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.P) return;
@@ -176,6 +177,7 @@ __device__ __forceinline__ void acc8(float (&a)[8], const uint4 r) {
 }
 
 __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseK k) {
+  pdl_enter();
   const int plane = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= k.g.P) return;
@@ -334,8 +336,8 @@ extern "C" int hrnb_phase_split(const void* src, int64_t src_ps, int32_t N, int3
   if (!src || !dst || C % 8 || (H & 1) || (W & 1) || phase_stride <= 0) return fail(HRNB_EINVAL, "phase_split: bad params");
   const Geo g = make_geo(N, H, W);
   dim3 grid((unsigned)((g.P + 255) / 256), C / 8);
-  phase_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ps, g, (__nv_bfloat16*)dst,
-                                                              dst_ps, phase_stride);
+  launch_pdl(phase_split_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, (long long)src_ps, g,
+             (__nv_bfloat16*)dst, (long long)dst_ps, (long long)phase_stride);
   count_launch();
   return check_launch("phase_split_kernel");
 }
@@ -360,7 +362,7 @@ extern "C" int hrnb_fuse_sum(const hrnb_fuse_params* p, void* stream) {
   k.g = make_geo(p->N, p->H, p->W);
   k.relu = p->relu;
   dim3 grid((unsigned)((k.g.P + 255) / 256), p->C / 8);
-  fuse_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  launch_pdl(fuse_sum_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("fuse_sum_kernel");
 }

@@ -32,6 +32,14 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: let the next kernel of the stream be scheduled now (its blocks become resident and
+// wait), then wait until the previous kernel has completed and its writes are visible.  Both are no-ops for a kernel
+// that was launched without the programmatic attribute / has no such dependent.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

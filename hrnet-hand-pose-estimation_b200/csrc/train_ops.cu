@@ -150,6 +150,7 @@ __device__ __forceinline__ void plane_reduce_broadcast(float (&v)[NV], float* __
 // sums[c][0] = sum_p x, sums[c][1] = sum_p x^2 (padding positions are zero and add nothing)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ c, long long c_ps, long long P,
                                                       float* __restrict__ sums, float* __restrict__ ws) {
+  pdl_enter();
   const int plane = blockIdx.y;
   const __nv_bfloat16* base = c + (long long)plane * c_ps * 8;
   float v[16];
@@ -210,6 +211,7 @@ struct BnK {
 
 // y = [relu]( gamma*(c-mean)*invstd + beta [+ res] ), zeros at padding; block (0, plane) also updates the running stats
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnK k) {
+  pdl_enter();
   __shared__ float sa[8], sb[8];
   const int plane = blockIdx.y;
   if (threadIdx.x < 8) {
@@ -350,6 +352,7 @@ __device__ __forceinline__ void relu_mask8(float (&g)[8], const uint4 yv) {
 
 // dsums[c][0] = sum g, dsums[c][1] = sum g*xhat with g = dy * relu mask
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
+  pdl_enter();
   __shared__ float sm[8], si[8];
   const int plane = blockIdx.y;
   if (threadIdx.x < 8) bn_channel_stats(k.sums, plane * 8 + threadIdx.x, k.count, k.eps, sm[threadIdx.x], si[threadIdx.x]);
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
 
 // dc = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dres (+)= g; block (0, plane) writes dgamma / dbeta
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdK k) {
+  pdl_enter();
   __shared__ float sm[8], si[8], sa[8], s0[8], s1[8];
   const int plane = blockIdx.y;
   if (threadIdx.x < 8) {
@@ -526,6 +530,7 @@ struct FuseBwdK {
 };
 
 __global__ void __launch_bounds__(256) fuse_sum_bwd_kernel(const FuseBwdK k) {
+  pdl_enter();
   const int plane = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= k.sg.P) return;
@@ -616,6 +621,7 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) phase_merge_kernel(const __nv_bfloat16* __restrict__ src, long long src_ps,
                                                          long long phase_stride, __nv_bfloat16* __restrict__ dst,
                                                          long long dst_ps, Geo g, int mode) {
+  pdl_enter();
   const int plane = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.P) return;
@@ -796,7 +802,7 @@ extern "C" int hrnb_bn_stats(const void* c, int64_t c_ps, int32_t N, int32_t C, 
   if (!c || !sums || !ws || C % 8 || C <= 0 || C / 8 > kMaxPlanes) return fail(HRNB_EINVAL, "bn_stats: bad params");
   const Geo g = make_geo(N, H, W);
   dim3 grid(reduce_blocks(g.P), C / 8);
-  bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)c, c_ps, g.P, sums, ws);
+  launch_pdl(bn_stats_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)c, (long long)c_ps, (long long)g.P, sums, ws);
   count_launch();
   return check_launch("bn_stats_kernel");
 }
@@ -832,7 +838,7 @@ extern "C" int hrnb_bn_apply(const hrnb_bn_params* p, void* stream) {
   k.relu = p->relu; k.eps = p->eps; k.momentum = p->momentum;
   k.count = (float)((long long)p->N * p->H * p->W);
   dim3 grid((unsigned)((k.g.P + 255) / 256), p->C / 8);
-  bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  launch_pdl(bn_apply_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("bn_apply_kernel");
 }
@@ -880,7 +886,7 @@ extern "C" int hrnb_bn_bwd_reduce(const hrnb_bn_bwd_params* p, void* stream) {
   const int rc = make_bwd(p, &k);
   if (rc) return rc;
   dim3 grid(reduce_blocks(k.g.P), p->C / 8);
-  bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  launch_pdl(bn_bwd_reduce_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("bn_bwd_reduce_kernel");
 }
@@ -891,7 +897,7 @@ extern "C" int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream) {
   if (rc) return rc;
   if (!p->dc) return fail(HRNB_EINVAL, "bn_bwd_apply: dc missing");
   dim3 grid((unsigned)((k.g.P + 255) / 256), p->C / 8);
-  bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  launch_pdl(bn_bwd_apply_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("bn_bwd_apply_kernel");
 }
@@ -923,7 +929,7 @@ extern "C" int hrnb_fuse_sum_bwd(const void* dy, int64_t dy_ps, const void* y, i
   k.sg = make_geo(N, H >> shift, W >> shift);
   k.shift = shift; k.mode = mode; k.relu = relu;
   dim3 grid((unsigned)((k.sg.P + 255) / 256), C / 8);
-  fuse_sum_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k);
+  launch_pdl(fuse_sum_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("fuse_sum_bwd_kernel");
 }
@@ -946,8 +952,8 @@ extern "C" int hrnb_phase_merge(const void* src, int64_t src_ps, int64_t phase_s
     return fail(HRNB_EINVAL, "phase_merge: bad params");
   const Geo g = make_geo(N, H, W);
   dim3 grid((unsigned)((g.P + 255) / 256), C / 8);
-  phase_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ps, phase_stride,
-                                                              (__nv_bfloat16*)dst, dst_ps, g, mode);
+  launch_pdl(phase_merge_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, (long long)src_ps,
+             (long long)phase_stride, (__nv_bfloat16*)dst, (long long)dst_ps, g, (int)mode);
   count_launch();
   return check_launch("phase_merge_kernel");
 }

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradK k)
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_enter();     // everything above (barriers, TMEM) overlaps the previous kernel's tail; global memory only from here on
 
   // work item -> (cout tile, cin tile, tap group, K split)
   int r = blockIdx.x;
@@ -332,7 +333,7 @@ extern "C" int hrnb_wgrad(const hrnb_wgrad_params* p, void* stream) {
     if (e != cudaSuccess) return fail_cuda(e, "wgrad: cudaFuncSetAttribute");
     attr_set[dev] = true;
   }
-  wgrad_tc_kernel<<<(unsigned)grid, kWgThreads, (size_t)smem, (cudaStream_t)stream>>>(k);
+  launch_pdl(wgrad_tc_kernel, dim3((unsigned)grid), dim3(kWgThreads), (size_t)smem, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("wgrad_tc_kernel");
 }

@@ -520,7 +520,10 @@ class TrainEngine:
         # batch 64, but one of ~15 multi-stream bench runs ended in a device-side mbarrier time-out that has not been
         # reproduced or explained yet, so the default is the single-stream plan that never showed it.
         self.multi_stream = os.environ.get("HRNB_TRAIN_STREAMS", "0") == "1" if multi_stream is None else bool(multi_stream)
-        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "0") == "1"     # programmatic dependent launch of the conv kernels
+        # programmatic dependent launch for ALL kernels of the step (each kernel's blocks are scheduled while the previous
+        # kernel drains): on for the single-stream plan, off with branch-parallel streams; HRNB_TRAIN_PDL=0/1 overrides
+        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "0" if self.multi_stream else "1") == "1"
+        _lib.lib().hrnb_debug_set(4, 1 if self.pdl else 0)
         # BatchNorm statistics+apply / reduce+apply as single cooperative launches: opt-in (HRNB_BN_FUSED=1) - measured
         # 32.5 vs 33.2 ms/step; the default keeps the plain two-launch kernels (no grid-wide spin barrier in the product path)
         self.bn_fused = os.environ.get("HRNB_BN_FUSED", "0") == "1" if bn_fused is None else bool(bn_fused)
