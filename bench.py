@@ -404,6 +404,14 @@ def timed_kinds(fns, names, torch, reps=2):
     return best_tot, kinds, list(zip(names, best))
 
 
+def _mark(msg):
+    """progress marker on stderr (stdout carries exactly one JSON line)"""
+    print("[bench] %s t=%.1fs" % (msg, time.time() - _T0), file=sys.stderr, flush=True)
+
+
+_T0 = time.time()
+
+
 def run_b200_train(args):
     import torch
     import torch.distributed as dist
@@ -445,9 +453,11 @@ def run_b200_train(args):
         x, gt, xy, vis = pool[i % 4]
         eng.train_step(x, gt, xy, vis, allreduce=allreduce)
 
+    _mark("engine + plan built")
     for i in range(max(args.warmup, 3)):
         step(i)
     torch.cuda.synchronize()
+    _mark("warm-up done")
     loss0 = float(plan.losses[0])
     if world > 1:
         dist.barrier()
@@ -468,6 +478,7 @@ def run_b200_train(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
     loss1 = float(plan.losses[0])
+    _mark("timed region done (%.2f ms/step)" % (ms / args.steps))
 
     # ---- e2e: TrainEngine.train_step fed from pinned host memory, losses read back to the host every step ----
     host = []
@@ -494,6 +505,7 @@ def run_b200_train(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(g0.elapsed_time(g1), device=dev)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    _mark("e2e done")
 
     if rank != 0:
         if world > 1:
@@ -505,6 +517,7 @@ def run_b200_train(args):
     fns = plan.fwd_fns + plan.loss_steps + plan.bwd_fns
     names = plan.fwd_names + ["loss"] * len(plan.loss_steps) + plan.bwd_names
     serial_ms, kinds, detail = timed_kinds(fns, names, torch)
+    _mark("per-kernel timing done")
     tshare = sum(kinds.get(k, [0.0, 0])[0] for k in ("conv", "dgrad", "wgrad"))
     n_tensor = sum(kinds.get(k, [0.0, 0])[1] for k in ("conv", "dgrad", "wgrad"))
     roof = None

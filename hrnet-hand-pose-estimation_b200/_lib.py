@@ -127,6 +127,8 @@ _SIGS = {
     "hrnb_bn_apply": (C.c_int, [C.POINTER(BnParams), _vp]),
     "hrnb_bn_forward": (C.c_int, [C.POINTER(BnParams), _vp, _vp, _vp]),
     "hrnb_bn_backward": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
+    "hrnb_bn_forward_batch": (C.c_int, [C.POINTER(BnParams), _i32, _vp, _vp]),
+    "hrnb_bn_backward_batch": (C.c_int, [C.POINTER(BnBwdParams), _i32, _vp]),
     "hrnb_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
     "hrnb_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
     "hrnb_fuse_sum_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

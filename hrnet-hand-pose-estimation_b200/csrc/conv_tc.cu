@@ -125,6 +125,11 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     fence_mbar_init();
   }
   if (warp == 1) {
+    // TMEM must NOT be held while waiting for the previous kernel: a programmatically launched dependent that
+    // allocates first and then waits can starve a co-resident CTA of the kernel it depends on (CTA A holds 256
+    // columns, CTA B of the next kernel blocks on 512, CTA C of the kernel after that gets the free 256 and waits for B
+    // -> B never gets 512) [observed as rare mbarrier time-outs with three co-resident conv CTAs / several streams].
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     tmem_alloc(tmem_ptr_smem, (uint32_t)k.tmem_cols);
     tmem_relinquish();
   }

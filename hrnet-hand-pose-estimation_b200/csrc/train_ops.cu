@@ -25,10 +25,10 @@ constexpr int kMaxPlanes = 1024;
 constexpr int kMaxRedBlocks = 296;
 
 template <int NV>
-__device__ __forceinline__ void grid_reduce_ordered(float (&v)[NV], float* __restrict__ dst, float* __restrict__ ws) {
+__device__ __forceinline__ void grid_reduce_ordered_nb(float (&v)[NV], float* __restrict__ dst_plane, float* __restrict__ ws,
+                                                       int plane, unsigned nb, unsigned bx) {
   __shared__ float red[8][NV];
   __shared__ unsigned ticket_s;
-  const int plane = blockIdx.y;
   unsigned* counter = reinterpret_cast<unsigned*>(ws) + plane;
   float* partials = ws + kMaxPlanes + (size_t)plane * kMaxRedBlocks * 16;
 #pragma unroll
@@ -46,20 +46,20 @@ __device__ __forceinline__ void grid_reduce_ordered(float (&v)[NV], float* __res
     float s = 0.f;
     const int nw = (blockDim.x + 31) >> 5;
     for (int w = 0; w < nw; ++w) s += red[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * 16 + threadIdx.x] = s;
+    partials[(size_t)bx * 16 + threadIdx.x] = s;
     __threadfence();
   }
   __syncthreads();
   if (threadIdx.x == 0) ticket_s = atomicAdd(counter, 1u);
   __syncthreads();
-  if (ticket_s == gridDim.x - 1) {      // last block of this plane: all partials are visible
+  if (ticket_s == nb - 1) {      // last block of this plane: all partials are visible
     __threadfence();
     // fixed-order two-level sum: 16 slices of blocks (slice j takes blocks j, j+16, ...) in parallel, then slices in order
     __shared__ float red2[16][16];
     const int i = threadIdx.x & 15, j = threadIdx.x >> 4;
     float s = 0.f;
     if (i < NV) {
-      for (unsigned b = j; b < gridDim.x; b += 16) s += __ldcg(partials + (size_t)b * 16 + i);
+      for (unsigned b = j; b < nb; b += 16) s += __ldcg(partials + (size_t)b * 16 + i);
     }
     red2[j][i] = s;
     __syncthreads();
@@ -67,10 +67,15 @@ __device__ __forceinline__ void grid_reduce_ordered(float (&v)[NV], float* __res
       float t = 0.f;
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) t += red2[jj][threadIdx.x];
-      dst[(size_t)plane * NV + threadIdx.x] = t;
+      dst_plane[threadIdx.x] = t;
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
+}
+
+template <int NV>
+__device__ __forceinline__ void grid_reduce_ordered(float (&v)[NV], float* __restrict__ dst, float* __restrict__ ws) {
+  grid_reduce_ordered_nb<NV>(v, dst + (size_t)blockIdx.y * NV, ws, (int)blockIdx.y, gridDim.x, blockIdx.x);
 }
 
 // Same ordered reduction, followed by a hand-shake so that EVERY block of the plane may read dst afterwards: the
@@ -148,17 +153,17 @@ __device__ __forceinline__ void plane_reduce_broadcast(float (&v)[NV], float* __
 // BN forward, batch statistics
 // ------------------------------------------------------------------------------------------------
 // sums[c][0] = sum_p x, sums[c][1] = sum_p x^2 (padding positions are zero and add nothing)
-__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ c, long long c_ps, long long P,
-                                                      float* __restrict__ sums, float* __restrict__ ws) {
-  pdl_enter();
-  const int plane = blockIdx.y;
+// `plane` = channel plane of this tensor, `gplane` = its slot in the reduction workspace, nb / bx = blocks of this plane
+__device__ __forceinline__ void bn_stats_body(const __nv_bfloat16* __restrict__ c, long long c_ps, long long P,
+                                              float* __restrict__ sums, float* __restrict__ ws, int plane, int gplane,
+                                              unsigned nb, unsigned bx) {
   const __nv_bfloat16* base = c + (long long)plane * c_ps * 8;
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
   // four independent 16-byte loads in flight per thread (the kernel is latency bound, not bandwidth bound)
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += 4 * stride) {
+  const long long stride = (long long)nb * blockDim.x;
+  for (long long p = (long long)bx * blockDim.x + threadIdx.x; p < P; p += 4 * stride) {
     uint4 r[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) r[u] = (p + u * stride < P) ? ldg_nc_v4(base + (p + u * stride) * 8) : make_uint4(0u, 0u, 0u, 0u);
@@ -173,7 +178,13 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
       }
     }
   }
-  grid_reduce_ordered<16>(v, sums, ws);   // [channel][2] interleaved
+  grid_reduce_ordered_nb<16>(v, sums + (size_t)plane * 16, ws, gplane, nb, bx);   // [channel][2] interleaved
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ c, long long c_ps, long long P,
+                                                      float* __restrict__ sums, float* __restrict__ ws) {
+  pdl_enter();
+  bn_stats_body(c, c_ps, P, sums, ws, (int)blockIdx.y, (int)blockIdx.y, gridDim.x, blockIdx.x);
 }
 
 // per-channel sum only (bias gradient of the BN-less final conv): out[c] = sum_p x  (out padded to 8 * planes floats)
@@ -210,10 +221,8 @@ struct BnK {
 };
 
 // y = [relu]( gamma*(c-mean)*invstd + beta [+ res] ), zeros at padding; block (0, plane) also updates the running stats
-__global__ void __launch_bounds__(256) bn_apply_kernel(const BnK k) {
-  pdl_enter();
+__device__ __forceinline__ void bn_apply_body(const BnK& k, int plane, unsigned bx) {
   __shared__ float sa[8], sb[8];
-  const int plane = blockIdx.y;
   if (threadIdx.x < 8) {
     const int ch = plane * 8 + threadIdx.x;
     const float mean = k.sums[2 * ch] / k.count;
@@ -222,14 +231,14 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnK k) {
     const float a = k.gamma[ch] * rsqrtf(var + k.eps);
     sa[threadIdx.x] = a;
     sb[threadIdx.x] = k.beta[ch] - mean * a;
-    if (blockIdx.x == 0 && k.running_mean != nullptr) {
+    if (bx == 0 && k.running_mean != nullptr) {
       const float unbiased = k.count > 1.f ? var * k.count / (k.count - 1.f) : var;
       k.running_mean[ch] = (1.f - k.momentum) * k.running_mean[ch] + k.momentum * mean;
       k.running_var[ch] = (1.f - k.momentum) * k.running_var[ch] + k.momentum * unbiased;
     }
   }
   __syncthreads();
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p = (long long)bx * blockDim.x + threadIdx.x;
   if (p >= k.g.P) return;
   const Pos q = decode_pos(k.g, p);
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
@@ -251,6 +260,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnK k) {
     o = pack8(x);
   }
   *reinterpret_cast<uint4*>(k.out + ((long long)plane * k.out_ps + p) * 8) = o;
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnK k) {
+  pdl_enter();
+  bn_apply_body(k, (int)blockIdx.y, blockIdx.x);
 }
 
 // statistics + normalisation in ONE cooperative launch (see plane_reduce_broadcast)
@@ -351,18 +365,16 @@ __device__ __forceinline__ void relu_mask8(float (&g)[8], const uint4 yv) {
 }
 
 // dsums[c][0] = sum g, dsums[c][1] = sum g*xhat with g = dy * relu mask
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
-  pdl_enter();
+__device__ __forceinline__ void bn_bwd_reduce_body(const BnBwdK& k, int plane, int gplane, unsigned nb, unsigned bx) {
   __shared__ float sm[8], si[8];
-  const int plane = blockIdx.y;
   if (threadIdx.x < 8) bn_channel_stats(k.sums, plane * 8 + threadIdx.x, k.count, k.eps, sm[threadIdx.x], si[threadIdx.x]);
   __syncthreads();
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long stride = (long long)nb * blockDim.x;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < k.g.P; p += 2 * stride) {
+  for (long long p = (long long)bx * blockDim.x + threadIdx.x; p < k.g.P; p += 2 * stride) {
     uint4 rg[2], ry[2], rc[2];     // two positions = up to six independent 16-byte loads in flight
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -385,14 +397,17 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
       }
     }
   }
-  grid_reduce_ordered<16>(v, k.dsums, k.ws);
+  grid_reduce_ordered_nb<16>(v, k.dsums + (size_t)plane * 16, k.ws, gplane, nb, bx);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
+  pdl_enter();
+  bn_bwd_reduce_body(k, (int)blockIdx.y, (int)blockIdx.y, gridDim.x, blockIdx.x);
 }
 
 // dc = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dres (+)= g; block (0, plane) writes dgamma / dbeta
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdK k) {
-  pdl_enter();
+__device__ __forceinline__ void bn_bwd_apply_body(const BnBwdK& k, int plane, unsigned bx) {
   __shared__ float sm[8], si[8], sa[8], s0[8], s1[8];
-  const int plane = blockIdx.y;
   if (threadIdx.x < 8) {
     const int ch = plane * 8 + threadIdx.x;
     float mean, invstd;
@@ -403,13 +418,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdK k) {
     const float d0 = k.dsums[2 * ch], d1 = k.dsums[2 * ch + 1];
     s0[threadIdx.x] = d0 / k.count;
     s1[threadIdx.x] = d1 / k.count;
-    if (blockIdx.x == 0) {
+    if (bx == 0) {
       if (k.dgamma) k.dgamma[ch] = d1;
       if (k.dbeta) k.dbeta[ch] = d0;
     }
   }
   __syncthreads();
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p = (long long)bx * blockDim.x + threadIdx.x;
   if (p >= k.g.P) return;
   const Pos q = decode_pos(k.g, p);
   const bool real = q.px > 0 && q.py > 0;
@@ -436,6 +451,77 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdK k) {
   }
   *reinterpret_cast<uint4*>(k.dc + ((long long)plane * k.dc_ps + p) * 8) = o;
   if (k.dres_mode != 0) *reinterpret_cast<uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8) = gres;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdK k) {
+  pdl_enter();
+  bn_bwd_apply_body(k, (int)blockIdx.y, blockIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Horizontally batched BatchNorm kernels: the same four kernels over up to kMaxBatch independent tensors (the branches
+// of a HighResolutionModule at the same depth) in ONE launch each.  blockIdx.y runs over the concatenated channel
+// planes; a block finds its tensor from the plane offsets and leaves if blockIdx.x exceeds that tensor's block count.
+// Rationale [measured]: at batch 64 most BatchNorm launches are latency bound (~8-10 us each for 1-4 MB tensors).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxBatch = 4;
+struct BnBatchK {
+  BnK k[kMaxBatch];
+  float* sums_out[kMaxBatch];
+  int plane0[kMaxBatch + 1];
+  unsigned nb_red[kMaxBatch], nb_app[kMaxBatch];
+  unsigned blk0_red[kMaxBatch + 1], blk0_app[kMaxBatch + 1];   // first block of tensor j in the 1-D grids
+  float* ws;
+  int n;
+};
+struct BnBwdBatchK {
+  BnBwdK k[kMaxBatch];
+  int plane0[kMaxBatch + 1];
+  unsigned nb_red[kMaxBatch], nb_app[kMaxBatch];
+  unsigned blk0_red[kMaxBatch + 1], blk0_app[kMaxBatch + 1];
+  int n;
+};
+
+// 1-D grid -> (tensor j, plane of that tensor, block index within the plane); blocks of a plane are consecutive
+__device__ __forceinline__ void batch_locate(const unsigned* blk0, const unsigned* nb, int n, int& j, int& plane, unsigned& bx) {
+  j = 0;
+  while (j + 1 < n && blockIdx.x >= blk0[j + 1]) ++j;
+  const unsigned r = blockIdx.x - blk0[j];
+  plane = (int)(r / nb[j]);
+  bx = r - (unsigned)plane * nb[j];
+}
+
+__global__ void __launch_bounds__(256) bn_stats_batch_kernel(const BnBatchK b) {
+  pdl_enter();
+  int j, plane;
+  unsigned bx;
+  batch_locate(b.blk0_red, b.nb_red, b.n, j, plane, bx);
+  const BnK& k = b.k[j];
+  bn_stats_body(k.c, k.c_ps, k.g.P, b.sums_out[j], b.ws, plane, b.plane0[j] + plane, b.nb_red[j], bx);
+}
+
+__global__ void __launch_bounds__(256) bn_apply_batch_kernel(const BnBatchK b) {
+  pdl_enter();
+  int j, plane;
+  unsigned bx;
+  batch_locate(b.blk0_app, b.nb_app, b.n, j, plane, bx);
+  bn_apply_body(b.k[j], plane, bx);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_batch_kernel(const BnBwdBatchK b) {
+  pdl_enter();
+  int j, plane;
+  unsigned bx;
+  batch_locate(b.blk0_red, b.nb_red, b.n, j, plane, bx);
+  bn_bwd_reduce_body(b.k[j], plane, b.plane0[j] + plane, b.nb_red[j], bx);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_batch_kernel(const BnBwdBatchK b) {
+  pdl_enter();
+  int j, plane;
+  unsigned bx;
+  batch_locate(b.blk0_app, b.nb_app, b.n, j, plane, bx);
+  bn_bwd_apply_body(b.k[j], plane, bx);
 }
 
 // both backward passes in ONE cooperative launch: reduce (sum g, sum g*xhat) -> broadcast -> dc, dres
@@ -902,6 +988,47 @@ extern "C" int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream) {
   return check_launch("bn_bwd_apply_kernel");
 }
 
+static int fill_bnk(const hrnb_bn_params* p, BnK* k) {
+  if (!p->c || !p->sums || !p->gamma || !p->beta || !p->out || p->C % 8 || p->C <= 0) return fail(HRNB_EINVAL, "bn batch: bad params");
+  k->c = (const __nv_bfloat16*)p->c; k->c_ps = p->c_ps;
+  k->sums = p->sums; k->gamma = p->gamma; k->beta = p->beta;
+  k->res = (const __nv_bfloat16*)p->res; k->res_ps = p->res_ps;
+  k->out = (__nv_bfloat16*)p->out; k->out_ps = p->out_ps;
+  k->running_mean = p->running_mean; k->running_var = p->running_var;
+  if ((k->running_mean == nullptr) != (k->running_var == nullptr)) return fail(HRNB_EINVAL, "bn batch: running stats must come in pairs");
+  k->g = make_geo(p->N, p->H, p->W);
+  k->relu = p->relu; k->eps = p->eps; k->momentum = p->momentum;
+  k->count = (float)((long long)p->N * p->H * p->W);
+  return HRNB_OK;
+}
+
+extern "C" int hrnb_bn_forward_batch(const hrnb_bn_params* p, int32_t n, float* ws, void* stream) {
+  if (!p || !ws || n < 1 || n > kMaxBatch) return fail(HRNB_EINVAL, "bn_forward_batch: 1..4 tensors");
+  BnBatchK b;
+  b.n = n;
+  b.ws = ws;
+  b.plane0[0] = 0;
+  b.blk0_red[0] = b.blk0_app[0] = 0;
+  for (int j = 0; j < n; ++j) {
+    const int rc = fill_bnk(&p[j], &b.k[j]);
+    if (rc) return rc;
+    b.sums_out[j] = const_cast<float*>(p[j].sums);
+    b.plane0[j + 1] = b.plane0[j] + p[j].C / 8;
+    b.nb_red[j] = reduce_blocks(b.k[j].g.P);
+    b.nb_app[j] = (unsigned)((b.k[j].g.P + 255) / 256);
+    b.blk0_red[j + 1] = b.blk0_red[j] + b.nb_red[j] * (unsigned)(p[j].C / 8);
+    b.blk0_app[j + 1] = b.blk0_app[j] + b.nb_app[j] * (unsigned)(p[j].C / 8);
+  }
+  if (b.plane0[n] > kMaxPlanes) return fail(HRNB_EINVAL, "bn_forward_batch: too many channel planes");
+  launch_pdl(bn_stats_batch_kernel, dim3(b.blk0_red[n]), dim3(256), 0, (cudaStream_t)stream, b);
+  count_launch();
+  int rc = check_launch("bn_stats_batch_kernel");
+  if (rc) return rc;
+  launch_pdl(bn_apply_batch_kernel, dim3(b.blk0_app[n]), dim3(256), 0, (cudaStream_t)stream, b);
+  count_launch();
+  return check_launch("bn_apply_batch_kernel");
+}
+
 extern "C" int hrnb_bn_backward(const hrnb_bn_bwd_params* p, void* stream) {
   BnBwdK k;
   const int rc = make_bwd(p, &k);
@@ -913,6 +1040,33 @@ extern "C" int hrnb_bn_backward(const hrnb_bn_bwd_params* p, void* stream) {
   void* args[1] = {(void*)&k};
   return launch_coop((const void*)bn_bwd_fused_kernel, dim3((unsigned)bx, (unsigned)planes), args, (cudaStream_t)stream,
                      "bn_bwd_fused_kernel");
+}
+
+extern "C" int hrnb_bn_backward_batch(const hrnb_bn_bwd_params* p, int32_t n, void* stream) {
+  if (!p || n < 1 || n > kMaxBatch) return fail(HRNB_EINVAL, "bn_backward_batch: 1..4 tensors");
+  BnBwdBatchK b;
+  b.n = n;
+  b.plane0[0] = 0;
+  b.blk0_red[0] = b.blk0_app[0] = 0;
+  for (int j = 0; j < n; ++j) {
+    const int rc = make_bwd(&p[j], &b.k[j]);
+    if (rc) return rc;
+    if (!p[j].dc) return fail(HRNB_EINVAL, "bn_backward_batch: dc missing");
+    if (p[j].ws != p[0].ws) return fail(HRNB_EINVAL, "bn_backward_batch: one reduction workspace per launch");
+    b.plane0[j + 1] = b.plane0[j] + p[j].C / 8;
+    b.nb_red[j] = reduce_blocks(b.k[j].g.P);
+    b.nb_app[j] = (unsigned)((b.k[j].g.P + 255) / 256);
+    b.blk0_red[j + 1] = b.blk0_red[j] + b.nb_red[j] * (unsigned)(p[j].C / 8);
+    b.blk0_app[j + 1] = b.blk0_app[j] + b.nb_app[j] * (unsigned)(p[j].C / 8);
+  }
+  if (b.plane0[n] > kMaxPlanes) return fail(HRNB_EINVAL, "bn_backward_batch: too many channel planes");
+  launch_pdl(bn_bwd_reduce_batch_kernel, dim3(b.blk0_red[n]), dim3(256), 0, (cudaStream_t)stream, b);
+  count_launch();
+  int rc = check_launch("bn_bwd_reduce_batch_kernel");
+  if (rc) return rc;
+  launch_pdl(bn_bwd_apply_batch_kernel, dim3(b.blk0_app[n]), dim3(256), 0, (cudaStream_t)stream, b);
+  count_launch();
+  return check_launch("bn_bwd_apply_batch_kernel");
 }
 
 extern "C" int hrnb_fuse_sum_bwd(const void* dy, int64_t dy_ps, const void* y, int64_t y_ps, void* dsrc, int64_t dsrc_ps,

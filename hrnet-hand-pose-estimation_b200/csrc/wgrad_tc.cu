@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradK k)
     mbar_init(tmem_full, 1u);
     fence_mbar_init();
   }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 1) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");    // never hold TMEM while waiting for the previous kernel (see conv_tc.cu)
     tmem_alloc(tmem_ptr_smem, (uint32_t)k.tmem_cols);
     tmem_relinquish();
   }

@@ -205,6 +205,49 @@ class TrainPlan:
         self.tape.append(back)
         return y
 
+    def units(self, keys, xs, relu, ress=None):
+        """n <= 4 independent units (the branches of a module at the same depth): convs launched one by one, their
+        BatchNorm statistics / normalisation and the BatchNorm backward horizontally batched into two launches each"""
+        e, lib, n = self.eng, _lib.lib(), len(keys)
+        ress = ress or [None] * n
+        Ls, cs, ys, bps = [], [], [], []
+        for key, x, res in zip(keys, xs, ress):
+            L = e.units[key]
+            sp = L["spec"]
+            assert sp.stride == 1
+            self._ctx = key
+            c = self._buf(sp.cout, x.v.H, x.v.W)
+            y = T(self._buf(sp.cout, x.v.H, x.v.W))
+            self._f(self._conv_fn(L["fwd"], x.v, c), "conv:" + key)
+            self.conv_out[key] = c
+            bps.append(tops.bn_params(c, L["sums"], L["gamma"], L["beta"], y.v, res=res.v if res is not None else None,
+                                      relu=relu, running_mean=L["rm"], running_var=L["rv"]))
+            Ls.append(L); cs.append(c); ys.append(y)
+        arr = (_lib.BnParams * n)(*bps)
+        ws = tops.reduce_ws(self.dev, 0)
+        self.keep += [arr, bps]
+        self._f(lambda: _lib.check(lib.hrnb_bn_forward_batch(arr, n, ws.data_ptr(), _lib.stream_ptr())), "bn_fwd_batch:" + keys[0])
+        self.n_launch["fwd"] += 1           # two launches per call
+
+        def back():
+            self._ctx, self._sid = keys[0], 0
+            bbs = []
+            for L, c, y, res in zip(Ls, cs, ys, ress):
+                assert y.ginit
+                self._gr(y)
+                dres, dmode = (None, 0) if res is None else self._gw(res)
+                bbs.append(tops.bn_bwd_params(y.g, y.v, c, L["sums"], L["gamma"], L["dsums"], y.g, L["dgamma"], L["dbeta"],
+                                              relu=relu, dres=dres, dres_mode=dmode, sid=0))
+            barr = (_lib.BnBwdParams * n)(*bbs)
+            self.keep += [barr, bbs]
+            self._b(lambda: _lib.check(lib.hrnb_bn_backward_batch(barr, n, _lib.stream_ptr())), "bn_bwd_batch:" + keys[0])
+            self.n_launch["bwd"] += 1
+            for L, x, y in zip(Ls, xs, ys):
+                self._ctx = L["spec"].key
+                self._conv_backward(L, x, y.g, True)
+        self.tape.append(back)
+        return ys
+
     def _conv_backward(self, L, x, dc, need_dx):
         """weight gradient of conv L from (dc, x) and, if asked, the data gradient into x.g"""
         sp = L["spec"]
@@ -299,14 +342,23 @@ class TrainPlan:
                 pre = "stage%d.%d" % (s, m)
                 last_module = (s == 4 and m == nmod - 1)
                 splits = {}
-                for i in range(nb):
-                    self.on(i)
+                if e.bn_batch and not self.multi_stream:
+                    # single-stream plan: walk the branches in lock-step so that their BatchNorm kernels batch horizontally
                     for b in range(arch.blocks):
-                        bp = "%s.branches.%d.%d" % (pre, i, b)
-                        y = self.unit(bp + ".conv1", xs[i], True)
-                        xs[i] = self.unit(bp + ".conv2", y, True, res=xs[i])
-                    if i < nb - 1:
-                        splits[i] = self.split(xs[i])      # phase copy for the stride-2 chains that start at branch i
+                        bps_ = ["%s.branches.%d.%d" % (pre, i, b) for i in range(nb)]
+                        ys_ = self.units([p_ + ".conv1" for p_ in bps_], xs, True)
+                        xs = self.units([p_ + ".conv2" for p_ in bps_], ys_, True, ress=xs)
+                    for i in range(nb - 1):
+                        splits[i] = self.split(xs[i])
+                else:
+                    for i in range(nb):
+                        self.on(i)
+                        for b in range(arch.blocks):
+                            bp = "%s.branches.%d.%d" % (pre, i, b)
+                            y = self.unit(bp + ".conv1", xs[i], True)
+                            xs[i] = self.unit(bp + ".conv2", y, True, res=xs[i])
+                        if i < nb - 1:
+                            splits[i] = self.split(xs[i])      # phase copy for the stride-2 chains that start at branch i
                 for i in range(nb):                        # every fuse output needs every branch
                     for j in range(nb):
                         self.fwait(i, j)
@@ -508,7 +560,7 @@ class TrainEngine:
     per-shape TrainPlans of one network on one device."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, loss_factors=(1.0, 0.1),
-                 use_graph=True, multi_stream=None, bn_fused=None):
+                 use_graph=True, multi_stream=None, bn_fused=None, bn_batch=None):
         self.model = model
         self.arch, self.variant = model.arch, model.variant
         self.device = next(model.parameters()).device
@@ -527,6 +579,8 @@ class TrainEngine:
         # BatchNorm statistics+apply / reduce+apply as single cooperative launches: opt-in (HRNB_BN_FUSED=1) - measured
         # 32.5 vs 33.2 ms/step; the default keeps the plain two-launch kernels (no grid-wide spin barrier in the product path)
         self.bn_fused = os.environ.get("HRNB_BN_FUSED", "0") == "1" if bn_fused is None else bool(bn_fused)
+        # single-stream plan: BatchNorm kernels of the branches of a module batched horizontally (HRNB_BN_BATCH=0: off)
+        self.bn_batch = os.environ.get("HRNB_BN_BATCH", "1") != "0" if bn_batch is None else bool(bn_batch)
         self.plans = {}
         with torch.cuda.device(self.device):
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]

@@ -276,6 +276,9 @@ int hrnb_bn_apply(const hrnb_bn_params* p, void* stream);
  * (p->sums is ignored), then out.  All blocks synchronise through `ws`, so the launch is cooperative and its grid is
  * sized to the device occupancy. */
 int hrnb_bn_forward(const hrnb_bn_params* p, float* sums_out, float* ws, void* stream);
+/* Horizontally batched form: statistics (written to p[j].sums) + normalisation of n <= 4 independent tensors (the
+ * branches of a HighResolutionModule at the same depth) in two launches instead of 2n. */
+int hrnb_bn_forward_batch(const hrnb_bn_params* p, int32_t n, float* ws, void* stream);
 
 typedef struct hrnb_bn_bwd_params {
   const void* dy;         /* gradient of the unit output, PF8                                         */
@@ -303,6 +306,9 @@ int hrnb_bn_bwd_reduce(const hrnb_bn_bwd_params* p, void* stream);
 int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream);
 /* hrnb_bn_bwd_reduce + hrnb_bn_bwd_apply in ONE cooperative launch. */
 int hrnb_bn_backward(const hrnb_bn_bwd_params* p, void* stream);
+/* Horizontally batched hrnb_bn_bwd_reduce + hrnb_bn_bwd_apply over n <= 4 independent units (two launches); all
+ * p[j].ws must be the same workspace. */
+int hrnb_bn_backward_batch(const hrnb_bn_bwd_params* p, int32_t n, void* stream);
 
 /* ---- backward of hrnb_fuse_sum / hrnb_bilinear_up / hrnb_phase_split ---------------------------- */
 /* dsrc[q] (=|+=) sum over the 2^shift x 2^shift block of dy * (y > 0) (mode 1 write, 2 accumulate); dy, y on the

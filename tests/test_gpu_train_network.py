@@ -234,6 +234,30 @@ def test_fused_bn_plan_against_linearised_oracle():
             assert l2 < LIN_L2_TOL and cos > LIN_COS_TOL, (k, l2, cos)
 
 
+def test_batched_bn_plan_equals_per_unit_plan():
+    """horizontally batched BatchNorm launches (default single-stream plan) reproduce the per-unit launches bit for bit:
+    same per-tensor block counts, hence the same ordered sums"""
+    from hrnet_b200.train import TrainEngine
+    B, H, W = 2, 128, 128
+    res = []
+    for batch in (False, True):
+        m, cfg, sd, x, gt, xy, vis = _setup("softmax", True, B, H, W)
+        eng = TrainEngine(m, use_graph=batch, bn_batch=batch, multi_stream=False)
+        for _ in range(2):
+            p = eng.train_step(x.cuda(), gt.cuda(), xy.cuda(), vis.cuda(), optimizer_step=False)
+        torch.cuda.synchronize()
+        names = [n for n, _ in m.named_parameters()]
+        res.append((p.out["logits"].clone(), p.losses.clone(), dict(zip(names, [g.clone() for g in eng.flat.natural_grads()])),
+                    {k: v.clone() for k, v in m.named_buffers()}))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for k in ("bn1.weight", "stage3.1.branches.2.3.bn2.weight", "stage4.2.branches.3.1.bn1.bias", "last_layer.1.bias"):
+        assert torch.equal(res[0][2][k], res[1][2][k]), k
+    for k in ("stage4.0.branches.1.2.bn2.running_mean", "stage2.0.branches.0.0.bn1.running_var"):
+        assert torch.equal(res[0][3][k], res[1][3][k]), k
+    a, b = res[0][2]["stage2.0.branches.0.0.conv1.weight"], res[1][2]["stage2.0.branches.0.0.conv1.weight"]
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(a.abs().max()))
+
+
 def test_multi_stream_plan_equals_single_stream():
     """Branches on separate CUDA streams (hazard-ordered gradient accumulation) must reproduce the single-stream plan:
     forward bit-exactly (ordered reductions), parameter gradients up to the fp32 reduction order of the split-K wgrad."""
