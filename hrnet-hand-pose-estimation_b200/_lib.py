@@ -125,8 +125,6 @@ _SIGS = {
     "hrnb_channel_sum": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hrnb_reduce_ws_floats": (_i64, []),
     "hrnb_bn_apply": (C.c_int, [C.POINTER(BnParams), _vp]),
-    "hrnb_bn_forward": (C.c_int, [C.POINTER(BnParams), _vp, _vp, _vp]),
-    "hrnb_bn_backward": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
     "hrnb_bn_forward_batch": (C.c_int, [C.POINTER(BnParams), _i32, _vp, _vp]),
     "hrnb_bn_backward_batch": (C.c_int, [C.POINTER(BnBwdParams), _i32, _vp]),
     "hrnb_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwdParams), _vp]),

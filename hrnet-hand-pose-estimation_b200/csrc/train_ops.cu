@@ -78,77 +78,6 @@ __device__ __forceinline__ void grid_reduce_ordered(float (&v)[NV], float* __res
   grid_reduce_ordered_nb<NV>(v, dst + (size_t)blockIdx.y * NV, ws, (int)blockIdx.y, gridDim.x, blockIdx.x);
 }
 
-// Same ordered reduction, followed by a hand-shake so that EVERY block of the plane may read dst afterwards: the
-// fused BatchNorm kernels below run "reduce over the tensor -> use the result on the same tensor" in one launch (the
-// second pass hits L2, and one launch of ~8 us fixed cost disappears per BatchNorm per direction).  Needs all blocks
-// of the grid to be co-resident: the host launches these kernels cooperatively with a grid sized to the occupancy.
-// Counters (uint, zero once, self-resetting): arrive = ws[plane], depart = ws[kDepartOff + plane].
-constexpr size_t kDepartOff = (size_t)kMaxPlanes + (size_t)kMaxPlanes * kMaxRedBlocks * 16 + (size_t)kMaxPlanes * 8;
-
-template <int NV>
-__device__ __forceinline__ void plane_reduce_broadcast(float (&v)[NV], float* __restrict__ dst, float* __restrict__ ws) {
-  __shared__ float red[8][NV];
-  __shared__ float red2[16][16];
-  __shared__ unsigned ticket_s;
-  const int plane = blockIdx.y;
-  unsigned* arrive = reinterpret_cast<unsigned*>(ws) + plane;
-  unsigned* depart = reinterpret_cast<unsigned*>(ws) + kDepartOff + plane;
-  float* partials = ws + kMaxPlanes + (size_t)plane * kMaxRedBlocks * 16;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) red[warp][i] = v[i];
-  }
-  __syncthreads();
-  if (threadIdx.x < NV) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * 16 + threadIdx.x] = s;
-    __threadfence();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) ticket_s = atomicAdd(arrive, 1u);
-  __syncthreads();
-  if (ticket_s == gridDim.x - 1) {      // last block to arrive: ordered two-level sum of all partials, then publish
-    __threadfence();
-    const int i = threadIdx.x & 15, j = threadIdx.x >> 4;
-    float s = 0.f;
-    if (i < NV) {
-      for (unsigned b = j; b < gridDim.x; b += 16) s += __ldcg(partials + (size_t)b * 16 + i);
-    }
-    red2[j][i] = s;
-    __syncthreads();
-    if (threadIdx.x < NV) {
-      float t = 0.f;
-#pragma unroll
-      for (int jj = 0; jj < 16; ++jj) t += red2[jj][threadIdx.x];
-      dst[(size_t)plane * NV + threadIdx.x] = t;
-      __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(arrive, 1u);          // arrive == gridDim.x + 1  <=>  dst is published
-  }
-  if (threadIdx.x == 0) {
-    volatile unsigned* a = arrive;
-    unsigned spins = 0;
-    while (*a < gridDim.x + 1) {
-      if (++spins > (1u << 28)) __trap();                 // co-residency violated: fail loudly instead of hanging
-    }
-    __threadfence();
-    const unsigned d = atomicAdd(depart, 1u);
-    if (d == gridDim.x - 1) {                             // everybody has seen the result: reset for the next launch
-      *depart = 0u;
-      *arrive = 0u;
-    }
-  }
-  __syncthreads();
-}
-
 // ------------------------------------------------------------------------------------------------
 // BN forward, batch statistics
 // ------------------------------------------------------------------------------------------------
@@ -265,70 +194,6 @@ __device__ __forceinline__ void bn_apply_body(const BnK& k, int plane, unsigned 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnK k) {
   pdl_enter();
   bn_apply_body(k, (int)blockIdx.y, blockIdx.x);
-}
-
-// statistics + normalisation in ONE cooperative launch (see plane_reduce_broadcast)
-__global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const BnK k, float* __restrict__ sums, float* __restrict__ ws) {
-  __shared__ float sa[8], sb[8];
-  const int plane = blockIdx.y;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const __nv_bfloat16* base = k.c + (long long)plane * k.c_ps * 8;
-  float v[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = 0.f;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < k.g.P; p += 4 * stride) {
-    uint4 r[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = (p + u * stride < k.g.P) ? ldg_nc_v4(base + (p + u * stride) * 8) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float a[8];
-      unpack8(r[u], a);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[2 * i] += a[i];
-        v[2 * i + 1] = fmaf(a[i], a[i], v[2 * i + 1]);
-      }
-    }
-  }
-  plane_reduce_broadcast<16>(v, sums, ws);
-  if (threadIdx.x < 8) {
-    const int ch = plane * 8 + threadIdx.x;
-    const float mean = __ldcg(sums + 2 * ch) / k.count;
-    float var = __ldcg(sums + 2 * ch + 1) / k.count - mean * mean;
-    var = fmaxf(var, 0.f);
-    const float a = k.gamma[ch] * rsqrtf(var + k.eps);
-    sa[threadIdx.x] = a;
-    sb[threadIdx.x] = k.beta[ch] - mean * a;
-    if (blockIdx.x == 0 && k.running_mean != nullptr) {
-      const float unbiased = k.count > 1.f ? var * k.count / (k.count - 1.f) : var;
-      k.running_mean[ch] = (1.f - k.momentum) * k.running_mean[ch] + k.momentum * mean;
-      k.running_var[ch] = (1.f - k.momentum) * k.running_var[ch] + k.momentum * unbiased;
-    }
-  }
-  __syncthreads();
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < k.g.P; p += stride) {
-    const Pos q = decode_pos(k.g, p);
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (q.px > 0 && q.py > 0) {
-      float x[8];
-      unpack8(ldg_nc_v4(base + p * 8), x);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], sa[i], sb[i]);
-      if (k.res != nullptr) {
-        float r[8];
-        unpack8(ldg_nc_v4(k.res + ((long long)plane * k.res_ps + p) * 8), r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] += r[i];
-      }
-      if (k.relu) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
-      }
-      o = pack8(x);
-    }
-    *reinterpret_cast<uint4*>(k.out + ((long long)plane * k.out_ps + p) * 8) = o;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -522,86 +387,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_batch_kernel(const BnBwdBatc
   unsigned bx;
   batch_locate(b.blk0_app, b.nb_app, b.n, j, plane, bx);
   bn_bwd_apply_body(b.k[j], plane, bx);
-}
-
-// both backward passes in ONE cooperative launch: reduce (sum g, sum g*xhat) -> broadcast -> dc, dres
-__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const BnBwdK k) {
-  __shared__ float sm[8], si[8], sa[8], s0[8], s1[8];
-  const int plane = blockIdx.y;
-  if (threadIdx.x < 8) {
-    const int ch = plane * 8 + threadIdx.x;
-    float mean, invstd;
-    bn_channel_stats(k.sums, ch, k.count, k.eps, mean, invstd);
-    sm[threadIdx.x] = mean;
-    si[threadIdx.x] = invstd;
-    sa[threadIdx.x] = k.gamma[ch] * invstd;
-  }
-  __syncthreads();
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  float v[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = 0.f;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < k.g.P; p += 2 * stride) {
-    uint4 rg[2], ry[2], rc[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const long long q = p + u * stride;
-      const bool ok = q < k.g.P;
-      rg[u] = ok ? *reinterpret_cast<const uint4*>(k.dy + ((long long)plane * k.dy_ps + q) * 8) : z;
-      rc[u] = ok ? ldg_nc_v4(k.c + ((long long)plane * k.c_ps + q) * 8) : z;
-      ry[u] = (ok && k.relu) ? ldg_nc_v4(k.y + ((long long)plane * k.y_ps + q) * 8) : z;
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float g[8], x[8];
-      unpack8(rg[u], g);
-      unpack8(rc[u], x);
-      if (k.relu) relu_mask8(g, ry[u]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[2 * i] += g[i];
-        v[2 * i + 1] = fmaf(g[i], (x[i] - sm[i]) * si[i], v[2 * i + 1]);
-      }
-    }
-  }
-  plane_reduce_broadcast<16>(v, k.dsums, k.ws);
-  if (threadIdx.x < 8) {
-    const int ch = plane * 8 + threadIdx.x;
-    const float d0 = __ldcg(k.dsums + 2 * ch), d1 = __ldcg(k.dsums + 2 * ch + 1);
-    s0[threadIdx.x] = d0 / k.count;
-    s1[threadIdx.x] = d1 / k.count;
-    if (blockIdx.x == 0) {
-      if (k.dgamma) k.dgamma[ch] = d1;
-      if (k.dbeta) k.dbeta[ch] = d0;
-    }
-  }
-  __syncthreads();
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < k.g.P; p += stride) {
-    const Pos q = decode_pos(k.g, p);
-    uint4 o = z, gres = z;
-    if (q.px > 0 && q.py > 0) {
-      float g[8], x[8];
-      unpack8(*reinterpret_cast<const uint4*>(k.dy + ((long long)plane * k.dy_ps + p) * 8), g);
-      unpack8(ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8), x);
-      if (k.relu) relu_mask8(g, ldg_nc_v4(k.y + ((long long)plane * k.y_ps + p) * 8));
-      if (k.dres_mode == 2) {
-        float r[8];
-        unpack8(*reinterpret_cast<const uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8), r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] += g[i];
-        gres = pack8(r);
-      } else if (k.dres_mode == 1) {
-        gres = pack8(g);
-      }
-      float d[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = sa[i] * (g[i] - s0[i] - (x[i] - sm[i]) * si[i] * s1[i]);
-      o = pack8(d);
-    }
-    *reinterpret_cast<uint4*>(k.dc + ((long long)plane * k.dc_ps + p) * 8) = o;
-    if (k.dres_mode != 0) *reinterpret_cast<uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8) = gres;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -842,45 +627,7 @@ static unsigned reduce_blocks(long long P) {
 }
 
 extern "C" int64_t hrnb_reduce_ws_floats(void) {
-  return (int64_t)kDepartOff + kMaxPlanes;
-}
-
-// grid of a fused (cooperative) BatchNorm kernel: all blocks must be co-resident
-static int coop_blocks_x(const void* fn, long long P, int planes) {
-  static int cap[64][2] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
-  const int which = fn == (const void*)bn_fwd_fused_kernel ? 0 : 1;
-  if (cap[dev][which] == 0) {
-    int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) != cudaSuccess || per_sm <= 0) per_sm = 1;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    cap[dev][which] = per_sm * sms;
-  }
-  long long b = (P + 256 * 4 - 1) / (256 * 4);
-  const long long lim = cap[dev][which] / planes;
-  if (b > lim) b = lim;
-  if (b > kMaxRedBlocks) b = kMaxRedBlocks;
-  if (b < 1) b = lim >= 1 ? 1 : 0;
-  return (int)b;
-}
-
-static int launch_coop(const void* fn, dim3 grid, void** args, cudaStream_t st, const char* name) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
-  count_launch();
-  if (e != cudaSuccess) return fail_cuda(e, name);
-  return check_launch(name);
+  return (int64_t)kMaxPlanes + (int64_t)kMaxPlanes * kMaxRedBlocks * 16 + (int64_t)kMaxPlanes * 8;
 }
 
 extern "C" int hrnb_bn_stats(const void* c, int64_t c_ps, int32_t N, int32_t C, int32_t H, int32_t W, float* sums,
@@ -927,27 +674,6 @@ extern "C" int hrnb_bn_apply(const hrnb_bn_params* p, void* stream) {
   launch_pdl(bn_apply_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("bn_apply_kernel");
-}
-
-extern "C" int hrnb_bn_forward(const hrnb_bn_params* p, float* sums_out, float* ws, void* stream) {
-  if (!p || !p->c || !sums_out || !ws || !p->gamma || !p->beta || !p->out || p->C % 8 || p->C <= 0 || p->C / 8 > kMaxPlanes)
-    return fail(HRNB_EINVAL, "bn_forward: bad params");
-  BnK k;
-  k.c = (const __nv_bfloat16*)p->c; k.c_ps = p->c_ps;
-  k.sums = sums_out; k.gamma = p->gamma; k.beta = p->beta;
-  k.res = (const __nv_bfloat16*)p->res; k.res_ps = p->res_ps;
-  k.out = (__nv_bfloat16*)p->out; k.out_ps = p->out_ps;
-  k.running_mean = p->running_mean; k.running_var = p->running_var;
-  if ((k.running_mean == nullptr) != (k.running_var == nullptr)) return fail(HRNB_EINVAL, "bn_forward: running stats must come in pairs");
-  k.g = make_geo(p->N, p->H, p->W);
-  k.relu = p->relu; k.eps = p->eps; k.momentum = p->momentum;
-  k.count = (float)((long long)p->N * p->H * p->W);
-  const int planes = p->C / 8;
-  const int bx = coop_blocks_x((const void*)bn_fwd_fused_kernel, k.g.P, planes);
-  if (bx < 1) return fail(HRNB_EINVAL, "bn_forward: too many channel planes for a cooperative grid");
-  void* args[3] = {(void*)&k, (void*)&sums_out, (void*)&ws};
-  return launch_coop((const void*)bn_fwd_fused_kernel, dim3((unsigned)bx, (unsigned)planes), args, (cudaStream_t)stream,
-                     "bn_fwd_fused_kernel");
 }
 
 static int make_bwd(const hrnb_bn_bwd_params* p, BnBwdK* k) {
@@ -1027,19 +753,6 @@ extern "C" int hrnb_bn_forward_batch(const hrnb_bn_params* p, int32_t n, float* 
   launch_pdl(bn_apply_batch_kernel, dim3(b.blk0_app[n]), dim3(256), 0, (cudaStream_t)stream, b);
   count_launch();
   return check_launch("bn_apply_batch_kernel");
-}
-
-extern "C" int hrnb_bn_backward(const hrnb_bn_bwd_params* p, void* stream) {
-  BnBwdK k;
-  const int rc = make_bwd(p, &k);
-  if (rc) return rc;
-  if (!p->dc) return fail(HRNB_EINVAL, "bn_backward: dc missing");
-  const int planes = p->C / 8;
-  const int bx = coop_blocks_x((const void*)bn_bwd_fused_kernel, k.g.P, planes);
-  if (bx < 1) return fail(HRNB_EINVAL, "bn_backward: too many channel planes for a cooperative grid");
-  void* args[1] = {(void*)&k};
-  return launch_coop((const void*)bn_bwd_fused_kernel, dim3((unsigned)bx, (unsigned)planes), args, (cudaStream_t)stream,
-                     "bn_bwd_fused_kernel");
 }
 
 extern "C" int hrnb_bn_backward_batch(const hrnb_bn_bwd_params* p, int32_t n, void* stream) {

@@ -130,19 +130,10 @@ def bn_bwd_params(dy, y, c, sums, gamma, dsums, dc, dgamma, dbeta, relu=True, dr
     return p
 
 
-def bn_bwd(*a, fused=False, **k):
+def bn_bwd(*a, **k):
     p = bn_bwd_params(*a, **k)
-    if fused:
-        _lib.check(_lib.lib().hrnb_bn_backward(C.byref(p), _lib.stream_ptr()))
-        return
     _lib.check(_lib.lib().hrnb_bn_bwd_reduce(C.byref(p), _lib.stream_ptr()))
     _lib.check(_lib.lib().hrnb_bn_bwd_apply(C.byref(p), _lib.stream_ptr()))
-
-
-def bn_forward(c, sums, gamma, beta, out, sid=0, **k):
-    """batch statistics + normalisation (+ residual, ReLU) in one cooperative launch; writes `sums` too"""
-    p = bn_params(c, sums, gamma, beta, out, **k)
-    _lib.check(_lib.lib().hrnb_bn_forward(C.byref(p), sums.data_ptr(), reduce_ws(sums.device, sid).data_ptr(), _lib.stream_ptr()))
 
 
 # ---- elementwise backward ---------------------------------------------------------------------------------

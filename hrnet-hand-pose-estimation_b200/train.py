@@ -175,14 +175,8 @@ class TrainPlan:
                             running_mean=L["rm"], running_var=L["rv"])
         self.keep.append(bp)
         lib, bref = _lib.lib(), C.byref(bp)
-        fused = e.bn_fused
-        if fused:        # statistics + normalisation in one cooperative launch
-            ws = tops.reduce_ws(self.dev, sid)
-            self._f(lambda: _lib.check(lib.hrnb_bn_forward(bref, sums.data_ptr(), ws.data_ptr(), _lib.stream_ptr())),
-                    "bn_fwd:" + key)
-        else:
-            self._f(lambda: tops.bn_stats(c, sums, sid), "bn_stats:" + key)
-            self._f(lambda: _lib.check(lib.hrnb_bn_apply(bref, _lib.stream_ptr())), "bn_apply:" + key)
+        self._f(lambda: tops.bn_stats(c, sums, sid), "bn_stats:" + key)
+        self._f(lambda: _lib.check(lib.hrnb_bn_apply(bref, _lib.stream_ptr())), "bn_apply:" + key)
 
         def back():
             assert y.ginit, key
@@ -196,11 +190,8 @@ class TrainPlan:
                                     dres=dres, dres_mode=dmode, sid=sid)
             self.keep.append(bb)
             r = C.byref(bb)
-            if fused:
-                self._b(lambda: _lib.check(lib.hrnb_bn_backward(r, _lib.stream_ptr())), "bn_bwd:" + key)
-            else:
-                self._b(lambda: _lib.check(lib.hrnb_bn_bwd_reduce(r, _lib.stream_ptr())), "bn_bwd_reduce:" + key)
-                self._b(lambda: _lib.check(lib.hrnb_bn_bwd_apply(r, _lib.stream_ptr())), "bn_bwd_apply:" + key)
+            self._b(lambda: _lib.check(lib.hrnb_bn_bwd_reduce(r, _lib.stream_ptr())), "bn_bwd_reduce:" + key)
+            self._b(lambda: _lib.check(lib.hrnb_bn_bwd_apply(r, _lib.stream_ptr())), "bn_bwd_apply:" + key)
             self._conv_backward(L, x, dy, need_dx)
         self.tape.append(back)
         return y
@@ -560,7 +551,7 @@ class TrainEngine:
     per-shape TrainPlans of one network on one device."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, loss_factors=(1.0, 0.1),
-                 use_graph=True, multi_stream=None, bn_fused=None, bn_batch=None):
+                 use_graph=True, multi_stream=None, bn_batch=None):
         self.model = model
         self.arch, self.variant = model.arch, model.variant
         self.device = next(model.parameters()).device
@@ -568,17 +559,15 @@ class TrainEngine:
             raise RuntimeError("the B200 HRNet trains on CUDA only (no CPU fallback): call .cuda() first")
         self.loss_factors = tuple(float(f) for f in loss_factors)
         self.use_graph = use_graph and os.environ.get("HRNB_NO_GRAPH", "0") != "1"
-        # Branch-parallel streams are opt-in (HRNB_TRAIN_STREAMS=1 or multi_stream=True): measured 29.1 vs 33.0 ms/step at
-        # batch 64, but one of ~15 multi-stream bench runs ended in a device-side mbarrier time-out that has not been
-        # reproduced or explained yet, so the default is the single-stream plan that never showed it.
+        # Default: single-stream plan, every kernel launched with programmatic dependent launch (HRNB_TRAIN_PDL=0: off),
+        # BatchNorm kernels of a module's branches batched horizontally.  Opt-in (HRNB_TRAIN_STREAMS=1): branches of a
+        # HighResolutionModule on parallel streams.  Measured at batch 64: 26.9 ms/step (streams + PDL), 29.6 (default),
+        # 31.4 (single stream, no PDL, per-unit BN).  The streams plan is not the default because about one bench run in
+        # eight still ends in a device-side mbarrier time-out (a tcgen05 kernel waiting forever); the TMEM-held-across-
+        # griddepcontrol.wait deadlock found in round 1 (conv_tc.cu prologue) is fixed, this second one is not understood.
         self.multi_stream = os.environ.get("HRNB_TRAIN_STREAMS", "0") == "1" if multi_stream is None else bool(multi_stream)
-        # programmatic dependent launch for ALL kernels of the step (each kernel's blocks are scheduled while the previous
-        # kernel drains): on for the single-stream plan, off with branch-parallel streams; HRNB_TRAIN_PDL=0/1 overrides
-        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "0" if self.multi_stream else "1") == "1"
+        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "1") == "1"
         _lib.lib().hrnb_debug_set(4, 1 if self.pdl else 0)
-        # BatchNorm statistics+apply / reduce+apply as single cooperative launches: opt-in (HRNB_BN_FUSED=1) - measured
-        # 32.5 vs 33.2 ms/step; the default keeps the plain two-launch kernels (no grid-wide spin barrier in the product path)
-        self.bn_fused = os.environ.get("HRNB_BN_FUSED", "0") == "1" if bn_fused is None else bool(bn_fused)
         # single-stream plan: BatchNorm kernels of the branches of a module batched horizontally (HRNB_BN_BATCH=0: off)
         self.bn_batch = os.environ.get("HRNB_BN_BATCH", "1") != "0" if bn_batch is None else bool(bn_batch)
         self.plans = {}

@@ -272,10 +272,6 @@ typedef struct hrnb_bn_params {
   float eps, momentum;
 } hrnb_bn_params;
 int hrnb_bn_apply(const hrnb_bn_params* p, void* stream);
-/* hrnb_bn_stats + hrnb_bn_apply in ONE cooperative launch (second pass over c served from L2): writes sums_out[C][2]
- * (p->sums is ignored), then out.  All blocks synchronise through `ws`, so the launch is cooperative and its grid is
- * sized to the device occupancy. */
-int hrnb_bn_forward(const hrnb_bn_params* p, float* sums_out, float* ws, void* stream);
 /* Horizontally batched form: statistics (written to p[j].sums) + normalisation of n <= 4 independent tensors (the
  * branches of a HighResolutionModule at the same depth) in two launches instead of 2n. */
 int hrnb_bn_forward_batch(const hrnb_bn_params* p, int32_t n, float* ws, void* stream);
@@ -304,8 +300,6 @@ typedef struct hrnb_bn_bwd_params {
 } hrnb_bn_bwd_params;
 int hrnb_bn_bwd_reduce(const hrnb_bn_bwd_params* p, void* stream);
 int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream);
-/* hrnb_bn_bwd_reduce + hrnb_bn_bwd_apply in ONE cooperative launch. */
-int hrnb_bn_backward(const hrnb_bn_bwd_params* p, void* stream);
 /* Horizontally batched hrnb_bn_bwd_reduce + hrnb_bn_bwd_apply over n <= 4 independent units (two launches); all
  * p[j].ws must be the same workspace. */
 int hrnb_bn_backward_batch(const hrnb_bn_bwd_params* p, int32_t n, void* stream);
