@@ -562,6 +562,8 @@ def run_b200_train(args):
 
 
 def main():
+    if "HRNB_KEEP_NCCL_DEBUG" not in os.environ:
+        os.environ["NCCL_DEBUG"] = "WARN"       # NCCL's version banner goes to stdout, which must carry exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

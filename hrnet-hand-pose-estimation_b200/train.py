@@ -502,6 +502,14 @@ class TrainPlan:
 
     # ---- execution ------------------------------------------------------------------------------------------
     def _run(self, steps):
+        lib = _lib.lib()
+        lib.hrnb_debug_set(4, 1 if self.eng.pdl else 0)     # PDL attribute for the elementwise / wgrad launches of THIS plan only
+        try:
+            self._run_steps(steps)
+        finally:
+            lib.hrnb_debug_set(4, 0)
+
+    def _run_steps(self, steps):
         main = torch.cuda.current_stream()
         side = self.eng.side_streams if self.multi_stream else []
         streams = [main] + side
@@ -567,7 +575,6 @@ class TrainEngine:
         # griddepcontrol.wait deadlock found in round 1 (conv_tc.cu prologue) is fixed, this second one is not understood.
         self.multi_stream = os.environ.get("HRNB_TRAIN_STREAMS", "0") == "1" if multi_stream is None else bool(multi_stream)
         self.pdl = os.environ.get("HRNB_TRAIN_PDL", "1") == "1"
-        _lib.lib().hrnb_debug_set(4, 1 if self.pdl else 0)
         # single-stream plan: BatchNorm kernels of the branches of a module batched horizontally (HRNB_BN_BATCH=0: off)
         self.bn_batch = os.environ.get("HRNB_BN_BATCH", "1") != "0" if bn_batch is None else bool(bn_batch)
         self.plans = {}
