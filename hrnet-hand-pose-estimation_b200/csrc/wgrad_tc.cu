@@ -36,6 +36,10 @@ struct WgradK {
   int n_cot, NT, n_cit, TG, n_tg, KP, S, lead, haloB, ksplit, nchunks;
   unsigned a_stage_bytes, b_stage_bytes;
   int tmem_cols;
+  // M-stacked mode (3x3 convs with cout <= 64): the M = 128 rows hold `stack` copies of dY shifted by s0, s0+1, ... positions
+  // (copy i = rows [i*cpl*8, (i+1)*cpl*8)), so ONE MMA per kernel row r yields the taps (r, s0..s0+stack-1):
+  //   dW[r,s][co,ci] = sum_q dY[q - s, co] * X[q + (r-1)*Wp - 1, ci]            (q = p + s)
+  int stack, s0, cpl;   // stack == 0: plain mode
 };
 
 constexpr int kWgThreads = 192;
@@ -122,9 +126,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradK k)
           uint8_t* a_dst = a_ring + (size_t)stage * k.a_stage_bytes;
           uint8_t* b_dst = b_ring + (size_t)stage * k.b_stage_bytes;
           const long long pa = (long long)c * k.KP;
-          for (int j = 0; j < mt; ++j)
-            bulk_g2s(a_dst + (size_t)j * a_plane_bytes, k.dy + ((long long)(cot * 16 + j) * k.dy_ps + pa) * 8,
-                     a_plane_bytes, &full[stage]);
+          if (k.stack > 0) {
+            for (int j = 0; j < mt; ++j)      // plane j of the stage = channel plane j % cpl of copy j / cpl
+              bulk_g2s(a_dst + (size_t)j * a_plane_bytes,
+                       k.dy + ((long long)(j % k.cpl) * k.dy_ps + pa - (k.s0 + j / k.cpl)) * 8, a_plane_bytes, &full[stage]);
+          } else {
+            for (int j = 0; j < mt; ++j)
+              bulk_g2s(a_dst + (size_t)j * a_plane_bytes, k.dy + ((long long)(cot * 16 + j) * k.dy_ps + pa) * 8,
+                       a_plane_bytes, &full[stage]);
+          }
           for (int j = 0; j < nplanes_b; ++j)
             bulk_g2s(b_dst + (size_t)j * b_plane_bytes,
                      k.x + ((long long)(cit * nplanes_b + j) * k.x_ps + pa - k.lead) * 8, b_plane_bytes, &full[stage]);
@@ -178,18 +188,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradK k)
     } else {
       // =============================== epilogue ===============================
       const int q = warp & 3;
-      const int co = cot * 128 + q * 32 + lane;
+      int co = cot * 128 + q * 32 + lane;
+      int tap_add = 0;
+      bool row_ok = co < k.cout;
+      if (k.stack > 0) {                       // row -> (copy, channel)
+        const int row = q * 32 + lane, per = k.cpl * 8;
+        const int copy = row / per;
+        co = row - copy * per;
+        tap_add = k.s0 + copy;
+        row_ok = copy < k.stack && co < k.cout;
+      }
       mbar_wait(tmem_full, 0);
       tc_fence_after_sync();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
       const int groups = k.NT / 16;
       for (int t = 0; t < tn; ++t) {
-        const long long row0 = (long long)k.tap_id[t0 + t] * k.cin + (long long)cit * k.NT;
+        const long long row0 = (long long)(k.tap_id[t0 + t] + tap_add) * k.cin + (long long)cit * k.NT;
         for (int g = 0; g < groups; ++g) {
           uint32_t v[16];
           tmem_ld16(t_base + (uint32_t)(t * k.NT + g * 16), v);
           tmem_ld_wait();
-          if (co < k.cout) {
+          if (row_ok) {
             float* dst = k.dw + (row0 + g * 16) * k.cout + co;
 #pragma unroll
             for (int i = 0; i < 16; ++i) atomicAdd(dst + (long long)i * k.cout, __uint_as_float(v[i]));
@@ -208,7 +227,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradK k)
   }
 }
 
-static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid) {
+// stacked[0] = copies of dY stacked in M (0 = plain mode), stacked[1] = first column shift s0 of this launch
+static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid, const int* stacked = nullptr) {
   if (!p || !p->dy || !p->x || !p->dw) return fail(HRNB_EINVAL, "wgrad: null pointer");
   if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->cout <= 0 || p->cin <= 0) return fail(HRNB_EINVAL, "wgrad: bad geometry");
   if (p->cin % 16) return fail(HRNB_EINVAL, "wgrad: cin must be a multiple of 16");
@@ -234,9 +254,27 @@ static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid) 
   k->dy_planes = (p->cout + 7) / 8;
   k->ntap = p->ntap;
   k->lead = -lo;
+  k->stack = k->s0 = k->cpl = 0;
   for (int t = 0; t < 9; ++t) {
     k->tap_boff[t] = t < p->ntap ? k->lead + p->tap_dpos[t] : 0;
     k->tap_id[t] = t < p->ntap ? p->tap_id[t] : 0;
+  }
+  int extra_k = 0;
+  if (stacked && stacked[0] > 0) {
+    // "taps" of this launch are the three kernel rows: B offset (r-1)*Wp - 1, gradient index r*3 (+ column shift in the epilogue)
+    k->stack = stacked[0];
+    k->s0 = stacked[1];
+    k->cpl = (p->cout + 7) / 8;
+    k->dy_planes = k->stack * k->cpl;
+    k->ntap = 3;
+    lo = -(Wp + 1);
+    hi = Wp - 1;
+    k->lead = -lo;
+    for (int r = 0; r < 3; ++r) {
+      k->tap_boff[r] = k->lead + (r - 1) * Wp - 1;
+      k->tap_id[r] = r * 3;
+    }
+    extra_k = 2;      // q = p + s runs two positions past P
   }
   k->n_cot = (k->dy_planes + 15) / 16;
   // cin tile: the widest multiple of 16 dividing cin (<= 256 for single-tap layers, <= 128 otherwise so that
@@ -254,11 +292,12 @@ static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid) 
   // into dW) than with all nine taps per CTA [measured on B200, tools/wgrad_bench.py: 43 -> 37 us (32 ch @ 64x64),
   // 29.5 -> 20.5 us (64 ch @ 32x32), 68.6 -> 47 us (64 ch @ 64x64) at batch 64]
   int TG = p->TG > 0 ? p->TG : (p->ntap == 9 ? 3 : 512 / NT);
+  if (k->stack > 0) TG = 3;
   if (TG * NT > 512) TG = 512 / NT;
-  if (TG > p->ntap) TG = p->ntap;
+  if (TG > k->ntap) TG = k->ntap;
   if (TG < 1 || TG * NT > 512) return fail(HRNB_EINVAL, "wgrad: TG*NT exceeds 512 TMEM columns");
   k->TG = TG;
-  k->n_tg = (p->ntap + TG - 1) / TG;
+  k->n_tg = (k->ntap + TG - 1) / TG;
   int cols = 32;
   while (cols < TG * NT) cols <<= 1;
   k->tmem_cols = cols;
@@ -290,8 +329,8 @@ static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid) 
   k->haloB = KP + halo_extra;
   k->a_stage_bytes = ab;
   k->b_stage_bytes = bb;
-  k->nchunks = (int)((P + KP - 1) / KP);
-  if (HRNB_GUARD_TAIL(Wp) < KP + hi) return fail(HRNB_EINVAL, "wgrad: KP exceeds the PF8 tail guard");
+  k->nchunks = (int)((P + extra_k + KP - 1) / KP);
+  if (HRNB_GUARD_TAIL(Wp) < KP + hi + extra_k) return fail(HRNB_EINVAL, "wgrad: KP exceeds the PF8 tail guard");
   const int base_items = k->n_cot * k->n_cit * k->n_tg;
   int ksplit = p->ksplit;
   if (ksplit <= 0) {
@@ -321,11 +360,41 @@ extern "C" int64_t hrnb_wgrad_smem_bytes(const hrnb_wgrad_params* p) {
   return derive_wgrad(p, &k, &grid);
 }
 
+// standard 3x3 stride-1 tap table (tap t = (r,s) reads p + (r-1)*Wp + (s-1), gradient slot t)?
+static bool is_standard_3x3(const hrnb_wgrad_params* p) {
+  if (!p || p->ntap != 9) return false;
+  const int Wp = p->W + 1;
+  for (int t = 0; t < 9; ++t)
+    if (p->tap_dpos[t] != (t / 3 - 1) * Wp + (t % 3 - 1) || p->tap_id[t] != t) return false;
+  return true;
+}
+
+static int launch_wgrad(const WgradK& k, int grid, long long smem, cudaStream_t st);
+
 extern "C" int hrnb_wgrad(const hrnb_wgrad_params* p, void* stream) {
   WgradK k;
   int grid = 0;
+  // M-stacked form for thin 3x3 layers (cout <= 40: all three column shifts fit in M = 128): 3x fewer MMAs and a single pass
+  // over dY / X [measured, batch 64: 36.9 -> 22.6 us for 32 ch @ 64x64; with only two copies per launch (cout 48 / 64) the
+  // second launch costs more than it saves: 20.5 -> 31.7 us, so those keep the plain form]
+  if (is_standard_3x3(p) && p->cout <= 40 && p->TG == 0 && hrnb::g_debug[5] == 0) {
+    const int cpl = (p->cout + 7) / 8;
+    const int per = 16 / cpl >= 3 ? 3 : 16 / cpl;        // copies per launch
+    for (int s0 = 0; s0 < 3; s0 += per) {
+      const int st2[2] = {s0 + per <= 3 ? per : 3 - s0, s0};
+      const long long smem = derive_wgrad(p, &k, &grid, st2);
+      if (smem < 0) return (int)smem;
+      const int rc = launch_wgrad(k, grid, smem, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    return HRNB_OK;
+  }
   const long long smem = derive_wgrad(p, &k, &grid);
   if (smem < 0) return (int)smem;
+  return launch_wgrad(k, grid, smem, (cudaStream_t)stream);
+}
+
+static int launch_wgrad(const WgradK& k, int grid, long long smem, cudaStream_t stream) {
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);

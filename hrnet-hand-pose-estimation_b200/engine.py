@@ -89,6 +89,7 @@ class Plan:
         return dst
 
     def _conv(self, sid, layer, x, out, res=None, name="", out2=None):
+        layer.no_pdl = not self.engine.pdl
         p = layer.params(x, out, res, out2=out2)
         self.keep.append(p)
         lib = _lib.lib()
@@ -311,6 +312,9 @@ class HRNetEngine:
         self.plans = {}
         self.use_graph = os.environ.get("HRNB_NO_GRAPH", "0") != "1"
         self.single_stream = os.environ.get("HRNB_SINGLE_STREAM", "0") == "1"
+        # programmatic dependent launch of the conv kernels is opt-in (HRNB_PDL=1; 4.16 vs 4.21 ms/step at batch 64): PDL
+        # launches showed rare device-side mbarrier time-outs in the training engine this round (train.py)
+        self.pdl = os.environ.get("HRNB_PDL", "0") == "1"
         with torch.cuda.device(self.device):
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
             self._pack(sd)

@@ -567,14 +567,15 @@ class TrainEngine:
             raise RuntimeError("the B200 HRNet trains on CUDA only (no CPU fallback): call .cuda() first")
         self.loss_factors = tuple(float(f) for f in loss_factors)
         self.use_graph = use_graph and os.environ.get("HRNB_NO_GRAPH", "0") != "1"
-        # Default: single-stream plan, every kernel launched with programmatic dependent launch (HRNB_TRAIN_PDL=0: off),
-        # BatchNorm kernels of a module's branches batched horizontally.  Opt-in (HRNB_TRAIN_STREAMS=1): branches of a
-        # HighResolutionModule on parallel streams.  Measured at batch 64: 26.9 ms/step (streams + PDL), 29.6 (default),
-        # 31.4 (single stream, no PDL, per-unit BN).  The streams plan is not the default because about one bench run in
-        # eight still ends in a device-side mbarrier time-out (a tcgen05 kernel waiting forever); the TMEM-held-across-
-        # griddepcontrol.wait deadlock found in round 1 (conv_tc.cu prologue) is fixed, this second one is not understood.
-        self.multi_stream = os.environ.get("HRNB_TRAIN_STREAMS", "0") == "1" if multi_stream is None else bool(multi_stream)
-        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "1") == "1"
+        # Default: branches of a HighResolutionModule on parallel streams, plain stream-ordered launches.
+        # HRNB_TRAIN_STREAMS=0: single-stream plan with the BatchNorm kernels of a module's branches batched horizontally.
+        # HRNB_TRAIN_PDL=1: programmatic dependent launch (PDL) on every kernel of the step.  Measured at batch 64:
+        # 27.4 ms/step (streams, default), 26.9 (streams + PDL), 29.6 (single stream + PDL), 30.6 (single stream).
+        # PDL is NOT on by default: with it about one bench run in eight (either plan) ended in a device-side mbarrier
+        # time-out - a tcgen05 kernel waiting forever.  One cause was found and fixed this round (TMEM held across
+        # griddepcontrol.wait, conv_tc.cu prologue), a second one is not understood yet; without PDL no run ever hung.
+        self.multi_stream = os.environ.get("HRNB_TRAIN_STREAMS", "1") != "0" if multi_stream is None else bool(multi_stream)
+        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "0") == "1"
         # single-stream plan: BatchNorm kernels of the branches of a module batched horizontally (HRNB_BN_BATCH=0: off)
         self.bn_batch = os.environ.get("HRNB_BN_BATCH", "1") != "0" if bn_batch is None else bool(bn_batch)
         self.plans = {}
