@@ -8,7 +8,7 @@
 one batch of synthetic images: forward with batch-statistics BatchNorm, spatial softmax + soft-argmax decode,
 HeatmapLoss + 0.1 * JointsMSELoss (pose2d), full backward, gradient all-reduce over NCCL when N > 1, fused Adam
 (lr 1e-3, L2 wd 1e-4) and weight re-pack.  --mode infer: forward + softmax + soft-argmax decode only.
-Weights random-init (reference default init, seed 0), images ~ N(0,1), targets: sigma-2 Gaussians (oracle/fixtures).
+Weights random-init (reference default init, seed 0), images ~ N(0,1), targets: sigma-2 Gaussians (hrnet_b200.synthetic; the CPU arms use the identical oracle/fixtures).
 `value` is images/s with the batch already resident in HBM; `e2e` is the same metric through the public API with
 pinned-host inputs copied every step and the losses (train) / decoded joints (infer) read back every step.
 `--impl reference` times the CPU restatement of the reference (oracle/, torch-CPU fp32, all host threads) on a
@@ -258,7 +258,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from hrnet_b200 import _lib
-    from oracle import fixtures
+    from hrnet_b200 import synthetic as fixtures     # the product arm never imports oracle/
     H, W, B = args.height, args.img_width, args.batch
     model, cfg = build_model(args.width, H, W, dev)
     model.return_features = False      # the decode path does not consume the 480-channel feature tensor
@@ -427,7 +427,7 @@ def run_b200_train(args):
     from hrnet_b200 import _lib
     from hrnet_b200.parallel import max_over_ranks
     from hrnet_b200.train import TrainEngine
-    from oracle import fixtures
+    from hrnet_b200 import synthetic as fixtures     # the product arm never imports oracle/
     H, W, B = args.height, args.img_width, args.batch
     model, cfg = build_model(args.width, H, W, dev)
     model.train()
@@ -580,7 +580,18 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_b200(args)
+        try:
+            run_b200(args)
+        except Exception:
+            # a tcgen05 kernel that trapped on its bounded mbarrier wait leaves (kernel, CTA, warp, barrier) records
+            try:
+                from hrnet_b200 import _lib
+                recs = _lib.hang_report()
+                if recs:
+                    print("[bench] mbarrier time-out records (%d): %s" % (len(recs), recs[:48]), file=sys.stderr)
+            except Exception:
+                pass
+            raise
 
 
 if __name__ == "__main__":

@@ -41,6 +41,7 @@ class ConvParams(C.Structure):
         ("in_phase_stride", C.c_int64), ("out_phase_stride", C.c_int64),
         ("out2", C.c_void_p), ("out2_ps", C.c_int64), ("out2_phase_stride", C.c_int64),
         ("ntap_custom", C.c_int32), ("tap_src", C.c_int32 * 9), ("tap_dpos", C.c_int32 * 9),
+        ("stats_sums", C.c_void_p), ("stats_ws", C.c_void_p),
     ]
 
 
@@ -88,6 +89,7 @@ class BnBwdParams(C.Structure):
         ("ws", C.c_void_p), ("dc", C.c_void_p), ("dc_ps", C.c_int64), ("dres", C.c_void_p), ("dres_ps", C.c_int64), ("dres_mode", C.c_int32),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("N", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu", C.c_int32), ("eps", C.c_float),
+        ("beta", C.c_void_p),
     ]
 
 
@@ -103,6 +105,7 @@ _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 _SIGS = {
     "hrnb_conv": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "hrnb_conv_smem_bytes": (_i64, [C.POINTER(ConvParams)]),
+    "hrnb_conv_stats_ws_floats": (_i64, []),
     "hrnb_pack_conv_weights": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hrnb_stem_conv1": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "hrnb_stem_im2col": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
@@ -125,7 +128,7 @@ _SIGS = {
     "hrnb_channel_sum": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hrnb_reduce_ws_floats": (_i64, []),
     "hrnb_bn_apply": (C.c_int, [C.POINTER(BnParams), _vp]),
-    "hrnb_bn_forward_batch": (C.c_int, [C.POINTER(BnParams), _i32, _vp, _vp]),
+    "hrnb_bn_forward_batch": (C.c_int, [C.POINTER(BnParams), _i32, _vp, _i32, _vp]),
     "hrnb_bn_backward_batch": (C.c_int, [C.POINTER(BnBwdParams), _i32, _vp]),
     "hrnb_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
     "hrnb_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
@@ -138,6 +141,8 @@ _SIGS = {
     "hrnb_last_error": (C.c_char_p, []),
     "hrnb_abi_version": (C.c_int, []),
     "hrnb_launch_count": (_i64, []),
+    "hrnb_hang_init": (C.c_int, []),
+    "hrnb_hang_report": (C.c_int, [_vp, C.c_int]),
     "hrnb_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "hrnb_debug_trace": (C.c_int, [_vp]),
 }
@@ -165,10 +170,12 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if h.hrnb_abi_version() != 2:
+        if h.hrnb_abi_version() != 3:
             raise HrnbError("libhrnb.so ABI version mismatch")
         if os.environ.get("HRNB_NO_PDL", "0") == "1":      # debug: launch the conv kernels without programmatic dependent launch
             h.hrnb_debug_set(2, 1)
+        if os.environ.get("HRNB_TMEM_SHARE", "0") == "1":  # debug: let TMEM-holding CTAs of different kernels share an SM (can deadlock)
+            h.hrnb_debug_set(6, 1)
         _lib = h
     return _lib
 
@@ -182,6 +189,29 @@ def check(rc):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def hang_init():
+    """arm the mbarrier time-out records on the current device (engines call this once; not under stream capture)"""
+    check(lib().hrnb_hang_init())
+
+
+def hang_report():
+    """-> [] or the records the stuck warps left before the trap: dicts(kernel, grid, cta, warp, barrier, parity)"""
+    buf = (C.c_uint64 * 512)()
+    n = lib().hrnb_hang_report(buf, 512)
+    if n < 2 or buf[0] == 0:
+        return []
+    out = []
+    for i in range(2, n - 1, 2):
+        w0, w1 = buf[i], buf[i + 1]
+        if w0 == 0 and w1 == 0:
+            continue
+        threads = w0 >> 48
+        out.append({"kernel": {576: "conv_tc", 704: "conv_tc<gather>", 192: "wgrad_tc"}.get(threads, "threads=%d" % threads),
+                    "grid": (w0 >> 32) & 0xffff, "cta": (w0 >> 8) & 0xffffff, "warp": w0 & 0xff,
+                    "barrier_smem": w1 >> 8, "parity": w1 & 0xff})
+    return out
 
 
 def launch_count():

@@ -20,6 +20,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("HRNB_HANG_RECORDS", "0") == "1":      # debug build: stuck warps leave records before the bounded-wait trap
+    NVCC_FLAGS.append("-DHRNB_HANG_RECORDS")
+
+
 def _digest():
     h = hashlib.sha256()
     names = sorted(os.listdir(CSRC)) + ["../../include/hrnb.h"]

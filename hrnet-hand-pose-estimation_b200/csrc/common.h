@@ -10,6 +10,14 @@ int fail(int code, const char* msg);                 // records msg, returns cod
 int fail_cuda(cudaError_t e, const char* where);     // records "where: <cuda error>", returns HRNB_ECUDA
 int check_launch(const char* kernel);                // cudaGetLastError() -> HRNB_OK / HRNB_ECUDA
 void count_launch();
+unsigned long long* hang_buffer_device_ptr();        // mapped host buffer of the mbarrier time-out records (api.cu), or nullptr
+int bind_hang_buffer_conv();                         // per translation unit: point its g_hang_buf at the buffer
+int bind_hang_buffer_wgrad();
+// Every kernel that allocates tensor memory asks for at least this much dynamic shared memory, so that no two of them are
+// ever co-resident on one SM (2 x 116 KB > 227 KB).  With concurrent streams a conv CTA holding all 512 TMEM columns and a
+// wgrad CTA blocked in tcgen05.alloc on the same SM deadlocked: the conv's MMA / epilogue warps stopped inside tcgen05
+// instructions, only its producer warp was left waiting on an mbarrier [hang records, round 1: DESIGN.md §5].
+constexpr long long kTmemExclusiveSmem = 116 * 1024;
 extern int g_debug[8];                               // hrnb_debug_set knobs (conv_tc.cu); [4] != 0: PDL for the elementwise / wgrad kernels
 
 // kernel launch with the programmatic-dependent-launch attribute when knob 4 is set (the kernel must call pdl_enter())

@@ -64,6 +64,8 @@ struct ConvK {
   int dbg;                // debug bitmask (hrnb_debug_set(3, m)): 1 no residual loads, 2 no stores, 4 no TMEM loads
   unsigned a_stage_bytes, b_stage_bytes;
   int tap_off[9];         // flat-shift path: row offset of tap t inside an A stage (source * KC * halo + lead + dpos)
+  float* stats_sums;      // STATS variant: per-channel (sum, sum of squares) of the conv output over the real positions
+  float* stats_ws;        // STATS variant: ticket counter + per-CTA partial sums (hrnb_conv_stats_ws_floats)
 };
 
 // debug timeline: slot = role*64 + 2*tile_iter + {0,1}; written by one lane of CTA 0 only when tracing is on
@@ -89,7 +91,17 @@ constexpr int kThreadsGather = kThreadsFS + 128;   // + gather producers
 // KSTEPS = KC/2 (K=16 MMA steps per tap and chunk) is a template parameter so that the MMA issue loop is straight-line code:
 // the issuing thread can only run about one MMA ahead of the tensor pipe, so every scalar instruction and branch between two
 // tcgen05.mma is tensor-pipe idle time for the thin (N = 32 / 64) layers [measured: 106 cycles/MMA with a runtime loop].
-template <bool GATHER, bool NCHW, int KSTEPS>
+//
+// STATS (training path, BN == cout <= 64): the epilogue also accumulates the BatchNorm batch statistics of the tensor it
+// writes - sum and sum of squares per output channel over the real positions - so that the separate pass over the conv
+// output (bn_stats_kernel) disappears.  Every epilogue thread owns one TMEM lane (row) and, because BN/16 divides the four
+// warps of a lane quarter, ONE fixed 16-column group for all its tiles: 32 running sums live in registers for the whole
+// persistent loop (two FMAs per element), are reduced once per CTA (transposed butterfly over the lanes, warps in order)
+// and stored as the CTA's partial; the last CTA to arrive (ticket) adds the partials in CTA order.  Tile -> CTA mapping
+// and every summation order are static, so the statistics are bit-reproducible run to run.
+constexpr int kStatsSlot = 128;   // floats per CTA partial: [column group (<= 4)][sum x16 | sumsq x16]
+constexpr int kStatsMaxCtas = 320;
+template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false>
 __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ? 1 : kCtasPerSm) conv_tc_kernel(const ConvK k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
@@ -297,8 +309,13 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     constexpr int CS = kEpiWarps / 4;   // warps per quarter
     const bool relu = (k.flags & HRNB_CONV_RELU) != 0;
     constexpr bool nchw = NCHW;
-    const bool has_res = k.res != nullptr && !(k.dbg & 1);
+    const bool has_res = !STATS && k.res != nullptr && !(k.dbg & 1);
     const int groups = k.BN / 16;  // 16-column groups per M block
+    // STATS: running sums of this thread's row over its column group, as packed fp32 pairs (FADD2 / FFMA2):
+    // st2[j] = sums of columns (2j, 2j+1), st2[8 + j] = their sums of squares
+    unsigned long long st2[STATS ? 16 : 1];
+#pragma unroll
+    for (int i = 0; i < (STATS ? 16 : 1); ++i) st2[i] = 0ull;
     const int E = k.MB * groups;   // groups per tile; this warp takes e = cs, cs + CS, ...
     int it = 0;
     for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
@@ -396,6 +413,16 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[h * 8 + i]) + bsv[h * 8 + i];
+                if constexpr (STATS) {
+                  if (real) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const unsigned long long xx = pack_f32x2(x[2 * j], x[2 * j + 1]);
+                      st2[h * 4 + j] = add_f32x2(st2[h * 4 + j], xx);
+                      st2[8 + h * 4 + j] = fma_f32x2(xx, xx, st2[8 + h * 4 + j]);
+                    }
+                  }
+                }
                 const uint4 r = rb[u][h];  // zeros when there is no residual / padding row
                 x[0] += bf16_lo(r.x); x[1] += bf16_hi(r.x);
                 x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
@@ -439,6 +466,26 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+    if constexpr (STATS) {
+      float st[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        unpack_f32x2(st2[j], st[2 * j], st[2 * j + 1]);
+        unpack_f32x2(st2[8 + j], st[16 + 2 * j], st[16 + 2 * j + 1]);
+      }
+      // transposed butterfly: 32 values x 32 lanes -> lane l holds the warp total of value l (fixed order)
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+          const float send = upper ? st[i] : st[i + off];
+          const float keep = upper ? st[i + off] : st[i];
+          st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      bias_s[256 + (warp - 2) * 32 + lane] = st[0];   // bias uses <= 64 floats in this variant; 16 warps x 32 floats
     }
   } else {
     // =============================== gather producers (GATHER only) ===============================
@@ -510,6 +557,50 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, (uint32_t)k.tmem_cols);
+  }
+  if constexpr (STATS) {
+    const int groups = k.BN / 16, nval = groups * 32;
+    const int t = threadIdx.x;
+    unsigned* counter = reinterpret_cast<unsigned*>(k.stats_ws);
+    float* partials = k.stats_ws + 32;
+    // the ticket lives in the spare bytes of the barrier block (28 mbarriers + the TMEM pointer end at byte 228 of 256):
+    // a static __shared__ variable would push dynamic + static shared memory over the 227 KB opt-in limit
+    volatile unsigned& ticket_s = *reinterpret_cast<volatile unsigned*>(smem + 240);
+    if (t < nval) {
+      // column group g is drained by the warps with cs % groups == g (cs = epilogue warp index / 4), all four lane quarters
+      const int g = t >> 5, i = t & 31;
+      float s = 0.f;
+      for (int cs = g; cs < kEpiWarps / 4; cs += groups) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += bias_s[256 + (cs * 4 + j) * 32 + i];
+      }
+      partials[(size_t)blockIdx.x * kStatsSlot + t] = s;
+      __threadfence();
+    }
+    __syncthreads();
+    if (t == 0) ticket_s = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (ticket_s == gridDim.x - 1) {   // last CTA: every partial is visible
+      __threadfence();
+      float* red2 = bias_s + 256;      // [4 slices][128]
+      const int idx = t & 127, slice = t >> 7;
+      if (slice < 4) {
+        float s = 0.f;
+        if (idx < nval) {
+#pragma unroll 8
+          for (unsigned b = slice; b < gridDim.x; b += 4) s += __ldcg(partials + (size_t)b * kStatsSlot + idx);
+        }
+        red2[slice * 128 + idx] = s;
+      }
+      __syncthreads();
+      if (t < nval) {
+        const float tot = (red2[t] + red2[128 + t]) + (red2[256 + t] + red2[384 + t]);
+        const int g = t >> 5, i = t & 31;
+        const int ch = g * 16 + (i & 15);
+        if (ch < k.cout) k.stats_sums[2 * ch + (i >> 4)] = tot;
+      }
+      if (t == 0) *counter = 0u;
+    }
   }
 }
 
@@ -594,6 +685,14 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     return fail(HRNB_EINVAL, "conv: out2 needs a plain PF8 primary output with even H and W");
   k->oHp2 = p->H / 2 + 1;
   k->oWp2 = p->W / 2 + 1;
+  k->stats_sums = p->stats_sums;
+  k->stats_ws = p->stats_ws;
+  if (p->stats_sums != nullptr) {
+    const int groups = p->BN / 16;
+    if (!p->stats_ws || gather || nchw || k->n_tiles != 1 || (groups != 1 && groups != 2 && groups != 4) || p->res != nullptr ||
+        (p->flags & HRNB_CONV_RELU))
+      return fail(HRNB_EINVAL, "conv: fused BatchNorm statistics need the flat-shift PF8 path, BN == cout in {16, 32, 64}, no residual, no ReLU");
+  }
   k->lead = 0;
   if (phases_in && p->in_phase_stride <= 0) return fail(HRNB_EINVAL, "conv: in_phase_stride missing");
   if ((p->flags & HRNB_CONV_OUT_PHASES) && p->out_phase_stride <= 0) return fail(HRNB_EINVAL, "conv: out_phase_stride missing");
@@ -648,6 +747,13 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   return smem;
 }
 
+int bind_hang_buffer_conv() {
+  unsigned long long* d = hang_buffer_device_ptr();
+  if (d == nullptr) return fail(HRNB_ECUDA, "hang buffer: cudaHostAlloc failed");
+  cudaError_t e = cudaMemcpyToSymbol(g_hang_buf, &d, sizeof(d));
+  return e == cudaSuccess ? HRNB_OK : fail_cuda(e, "hang buffer: cudaMemcpyToSymbol");
+}
+
 }  // namespace hrnb
 
 using namespace hrnb;
@@ -663,6 +769,8 @@ extern "C" int hrnb_debug_trace(void* dev_buf_5x64_i64) {
   return HRNB_OK;
 }
 
+extern "C" int64_t hrnb_conv_stats_ws_floats(void) { return 32 + (int64_t)kStatsMaxCtas * kStatsSlot; }
+
 extern "C" int64_t hrnb_conv_smem_bytes(const hrnb_conv_params* p) {
   ConvK k;
   return derive(p, &k);
@@ -674,13 +782,14 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (smem < 0) return (int)smem;
   const bool gather = (p->flags & HRNB_CONV_GATHER) != 0;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[64][21] = {};
+  static bool attr_set[64][28] = {};
   static int sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
   const bool nchw_out = (p->flags & HRNB_CONV_OUT_NCHW) != 0;
   if (gather && nchw_out) return fail(HRNB_EINVAL, "conv: NCHW output is not available for the gather variant");
+  const bool stats = p->stats_sums != nullptr;
   const int ks = p->KC / 2;
   int ksi = -1;
   const void* fn = nullptr;
@@ -688,12 +797,14 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (ks == KS) {                                                                                            \
     ksi = IDX;                                                                                               \
     fn = gather ? (const void*)conv_tc_kernel<true, false, KS>                                               \
-                : (nchw_out ? (const void*)conv_tc_kernel<false, true, KS> : (const void*)conv_tc_kernel<false, false, KS>); \
+                : (nchw_out ? (const void*)conv_tc_kernel<false, true, KS>                                   \
+                            : (stats ? (const void*)conv_tc_kernel<false, false, KS, true>                   \
+                                     : (const void*)conv_tc_kernel<false, false, KS>));                      \
   }
   HRNB_PICK(1, 0) HRNB_PICK(2, 1) HRNB_PICK(3, 2) HRNB_PICK(4, 3) HRNB_PICK(6, 4) HRNB_PICK(8, 5) HRNB_PICK(16, 6)
 #undef HRNB_PICK
   if (!fn) return fail(HRNB_EINVAL, "conv: KC must be one of 2, 4, 6, 8, 12, 16, 32");
-  const int variant = ksi * 3 + (gather ? 2 : (nchw_out ? 1 : 0));
+  const int variant = ksi * 4 + (gather ? 2 : (nchw_out ? 1 : (stats ? 3 : 0)));
   if (!attr_set[dev][variant]) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "conv: cudaFuncSetAttribute");
@@ -709,10 +820,11 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (g_debug[1] > 0) per_sm = g_debug[1] == 1 ? 1 : per_sm;   // debug: force one CTA per SM
   int grid = sm_count[dev] * per_sm;
   if (grid > k.num_tiles) grid = k.num_tiles;
+  if (stats && grid > kStatsMaxCtas) return fail(HRNB_EINVAL, "conv: fused statistics support at most 320 CTAs");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(gather ? (unsigned)kThreadsGather : (unsigned)kThreadsFS);
-  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.dynamicSmemBytes = (size_t)(smem < kTmemExclusiveSmem && g_debug[6] == 0 ? kTmemExclusiveSmem : smem);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

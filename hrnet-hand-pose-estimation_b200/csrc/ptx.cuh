@@ -68,13 +68,42 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (launch error) instead of hanging the GPU box.
-// (The guard counts failed probes instead of reading %globaltimer: that register is slow to read and a
-// timer read per failed probe put microseconds on every pipeline hand-off.)
+// Hang diagnostics (debug build only: nvcc -DHRNB_HANG_RECORDS): a mapped HOST buffer (hrnb_hang_init) that survives the
+// trap.  Every warp that times out leaves a record: word 0 = blockDim.x << 48 | gridDim.x << 32 | blockIdx.x << 8 | warp,
+// word 1 = barrier smem address << 8 | parity (blockDim.x tells the kernel: 576 conv, 704 conv gather, 192 wgrad; the
+// address tells the barrier).  Not in the default build: the extra operand set-up in front of every wait was measurable in
+// the wait-heavy wgrad kernel.
+static __device__ unsigned long long* g_hang_buf = nullptr;   // one copy per translation unit, bound by hrnb_hang_init
+constexpr int kHangSlots = 255;
+__device__ __forceinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+#ifdef HRNB_HANG_RECORDS
+  unsigned long long* b = g_hang_buf;
+  if (b != nullptr && (threadIdx.x & 31) == 0) {
+    const unsigned warp = threadIdx.x >> 5;
+    const unsigned slot = (blockIdx.x * 23u + warp) % kHangSlots;
+    b[2 + 2 * slot] = ((unsigned long long)blockDim.x << 48) | ((unsigned long long)gridDim.x << 32) |
+                      ((unsigned long long)blockIdx.x << 8) | warp;
+    b[3 + 2 * slot] = ((unsigned long long)bar_addr << 8) | parity;
+    b[0] = 1ull;
+    __threadfence_system();
+  }
+  const uint64_t t0 = globaltimer_ns();
+  while (globaltimer_ns() - t0 < 20000000ull) {}   // 20 ms: let the other stuck warps leave their records too
+#endif
+  __trap();
+}
+// Bounded wait: a protocol bug must trap (launch error) instead of hanging the GPU box.  The guard counts failed probes -
+// nothing else may sit in or in front of this loop (a %globaltimer read per probe put microseconds on every pipeline
+// hand-off).  A failed probe that suspends takes ~4 us [measured], so 2^22 probes bound a wait by ~16 s; probes that
+// return at once by >= 0.2 s - no legitimate wait on this path is longer than milliseconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+#ifdef HRNB_HANG_RECORDS
+    if (++spins > (1u << 20)) mbar_timeout(smem_u32(bar), parity);
+#else
+    if (++spins > (1u << 22)) __trap();
+#endif
   }
 }
 
@@ -188,6 +217,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// packed fp32 pairs (sm_100: FADD2 / FFMA2 issue two fp32 operations per instruction)
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }

@@ -350,6 +350,13 @@ static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid, 
   return smem;
 }
 
+int bind_hang_buffer_wgrad() {
+  unsigned long long* d = hang_buffer_device_ptr();
+  if (d == nullptr) return fail(HRNB_ECUDA, "hang buffer: cudaHostAlloc failed");
+  cudaError_t e = cudaMemcpyToSymbol(g_hang_buf, &d, sizeof(d));
+  return e == cudaSuccess ? HRNB_OK : fail_cuda(e, "hang buffer: cudaMemcpyToSymbol");
+}
+
 }  // namespace hrnb
 
 using namespace hrnb;
@@ -404,6 +411,7 @@ static int launch_wgrad(const WgradK& k, int grid, long long smem, cudaStream_t 
     if (e != cudaSuccess) return fail_cuda(e, "wgrad: cudaFuncSetAttribute");
     attr_set[dev] = true;
   }
+  if (smem < kTmemExclusiveSmem && hrnb::g_debug[6] == 0) smem = kTmemExclusiveSmem;   // one TMEM-holding CTA per SM (common.h)
   launch_pdl(wgrad_tc_kernel, dim3((unsigned)grid), dim3(kWgThreads), (size_t)smem, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("wgrad_tc_kernel");

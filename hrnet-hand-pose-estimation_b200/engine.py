@@ -316,6 +316,7 @@ class HRNetEngine:
         # launches showed rare device-side mbarrier time-outs in the training engine this round (train.py)
         self.pdl = os.environ.get("HRNB_PDL", "0") == "1"
         with torch.cuda.device(self.device):
+            _lib.hang_init()
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
             self._pack(sd)
 

@@ -165,6 +165,24 @@ def autotune_conv(layer, x, out, res, out2, max_candidates=8):
     return _TUNED[key]
 
 
+def stats_eligible(p):
+    """can this conv launch also produce the BatchNorm batch statistics of its output (include/hrnb.h: stats_sums)?"""
+    return (p.BN == p.cout and p.cout in (16, 32, 64) and not p.res and
+            not (p.flags & (HRNB_CONV_GATHER | HRNB_CONV_OUT_NCHW | HRNB_CONV_RELU)))
+
+
+def attach_stats(p, sums):
+    """make conv launch `p` write (sum, sum of squares) per output channel into `sums` (fp32 [cout, 2]); the reduction
+    workspace is private to the launch struct (zeroed once; the ticket counter resets itself).  False if not eligible."""
+    if not stats_eligible(p):
+        return False
+    assert sums.dtype == torch.float32 and sums.numel() >= 2 * p.cout and sums.is_contiguous()
+    ws = torch.zeros(int(_lib.lib().hrnb_conv_stats_ws_floats()), dtype=torch.float32, device=sums.device)
+    p.stats_sums, p.stats_ws = sums.data_ptr(), ws.data_ptr()
+    p._keep_stats = (sums, ws)
+    return True
+
+
 class ConvLayer:
     """conv (1x1 / 3x3 pad 1, stride 1 or 2) + folded BN (+ residual) (+ ReLU) on PF8 tensors.
 
@@ -323,9 +341,13 @@ class ConvLayer:
             p.MB //= 2          # tile does not fit in shared memory at this MB
         return p
 
-    def __call__(self, x, out, res=None, mb=None, bn=None, out2=None):
+    def __call__(self, x, out, res=None, mb=None, bn=None, out2=None, stats=None):
+        """stats: fp32 [cout, 2] tensor -> the launch also writes the BatchNorm batch statistics (sum, sum of squares per
+        channel) of `out`; raises when the launch is not eligible (see attach_stats)"""
         assert x.C == self.cin, (x.C, self.cin)
         p = self.params(x, out, res, mb, bn, out2=out2)
+        if stats is not None and not attach_stats(p, stats):
+            raise ValueError("conv launch not eligible for fused BatchNorm statistics (BN=%d cout=%d flags=%d)" % (p.BN, p.cout, p.flags))
         _lib.check(_lib.lib().hrnb_conv(C.byref(p), _lib.stream_ptr()))
         return out
 

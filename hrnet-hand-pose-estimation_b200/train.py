@@ -21,7 +21,7 @@ import torch
 
 from . import _lib, arch as A, tops
 from .flat import FlatParams
-from .ops import ConvLayer, PF8, PhasePF8, Repacker
+from .ops import ConvLayer, PF8, PhasePF8, Repacker, attach_stats
 
 
 class T:
@@ -122,12 +122,18 @@ class TrainPlan:
     def bwd_names(self):
         return [st[3] for st in self.bwd if st[0] == "op"]
 
-    def _conv_fn(self, layer, x, out, res=None):
+    def _conv_fn(self, layer, x, out, res=None, stats=None):
+        """-> launch closure; with `stats` (fp32 [cout, 2]) -> (closure, fused): fused = the conv also writes the
+        BatchNorm batch statistics of `out` (eligible tile shapes only, ops.stats_eligible)"""
         layer.no_pdl = not self.eng.pdl
-        p = layer.params(x, out, res)
+        want = stats is not None and self.eng.fuse_stats and res is None and layer.cout in (16, 32, 64)
+        p = layer.params(x, out, res, bn=layer.cout if want else None)     # fused statistics need one N tile
         self.keep.append(p)
         lib, ref = _lib.lib(), C.byref(p)
-        return lambda: _lib.check(lib.hrnb_conv(ref, _lib.stream_ptr()))
+        fn = lambda: _lib.check(lib.hrnb_conv(ref, _lib.stream_ptr()))
+        if stats is None:
+            return fn
+        return fn, (want and attach_stats(p, stats))
 
     def _wgrad_fn(self, dy, x_ptr, x_ps, dw, cin, cout, taps):
         p = tops.wgrad_params(dy, x_ptr, x_ps, dw, cin, cout, taps)
@@ -167,15 +173,17 @@ class TrainPlan:
         self._ctx = key
         c = self._buf(sp.cout, Ho, Wo)
         y = T(self._buf(sp.cout, Ho, Wo))
-        self._f(self._conv_fn(L["fwd"], x.v, c), "conv:" + key)
-        self.conv_out[key] = c
         sums, dsums = L["sums"], L["dsums"]
+        conv_fn, fused = self._conv_fn(L["fwd"], x.v, c, stats=sums)
+        self._f(conv_fn, "conv:" + key)
+        self.conv_out[key] = c
         sid = self._sid
         bp = tops.bn_params(c, sums, L["gamma"], L["beta"], y.v, res=res.v if res is not None else None, relu=relu,
                             running_mean=L["rm"], running_var=L["rv"])
         self.keep.append(bp)
         lib, bref = _lib.lib(), C.byref(bp)
-        self._f(lambda: tops.bn_stats(c, sums, sid), "bn_stats:" + key)
+        if not fused:      # else: the conv's epilogue already reduced the batch statistics (conv_tc.cu, STATS variant)
+            self._f(lambda: tops.bn_stats(c, sums, sid), "bn_stats:" + key)
         self._f(lambda: _lib.check(lib.hrnb_bn_apply(bref, _lib.stream_ptr())), "bn_apply:" + key)
 
         def back():
@@ -187,7 +195,8 @@ class TrainPlan:
             if res is not None:
                 dres, dmode = self._gw(res)
             bb = tops.bn_bwd_params(dy, y.v, c, sums, L["gamma"], dsums, dy, L["dgamma"], L["dbeta"], relu=relu,
-                                    dres=dres, dres_mode=dmode, sid=sid)
+                                    dres=dres, dres_mode=dmode, sid=sid,
+                                    beta=L["beta"] if (res is None and e.mask_from_c) else None)
             self.keep.append(bb)
             r = C.byref(bb)
             self._b(lambda: _lib.check(lib.hrnb_bn_bwd_reduce(r, _lib.stream_ptr())), "bn_bwd_reduce:" + key)
@@ -202,14 +211,17 @@ class TrainPlan:
         e, lib, n = self.eng, _lib.lib(), len(keys)
         ress = ress or [None] * n
         Ls, cs, ys, bps = [], [], [], []
-        for key, x, res in zip(keys, xs, ress):
+        have_stats = 0
+        for j, (key, x, res) in enumerate(zip(keys, xs, ress)):
             L = e.units[key]
             sp = L["spec"]
             assert sp.stride == 1
             self._ctx = key
             c = self._buf(sp.cout, x.v.H, x.v.W)
             y = T(self._buf(sp.cout, x.v.H, x.v.W))
-            self._f(self._conv_fn(L["fwd"], x.v, c), "conv:" + key)
+            conv_fn, fused = self._conv_fn(L["fwd"], x.v, c, stats=L["sums"])
+            have_stats |= int(bool(fused)) << j
+            self._f(conv_fn, "conv:" + key)
             self.conv_out[key] = c
             bps.append(tops.bn_params(c, L["sums"], L["gamma"], L["beta"], y.v, res=res.v if res is not None else None,
                                       relu=relu, running_mean=L["rm"], running_var=L["rv"]))
@@ -217,8 +229,10 @@ class TrainPlan:
         arr = (_lib.BnParams * n)(*bps)
         ws = tops.reduce_ws(self.dev, 0)
         self.keep += [arr, bps]
-        self._f(lambda: _lib.check(lib.hrnb_bn_forward_batch(arr, n, ws.data_ptr(), _lib.stream_ptr())), "bn_fwd_batch:" + keys[0])
-        self.n_launch["fwd"] += 1           # two launches per call
+        self._f(lambda: _lib.check(lib.hrnb_bn_forward_batch(arr, n, ws.data_ptr(), have_stats, _lib.stream_ptr())),
+                "bn_fwd_batch:" + keys[0])
+        if have_stats != (1 << n) - 1:
+            self.n_launch["fwd"] += 1       # statistics launch for the tensors the convs did not cover + normalisation launch
 
         def back():
             self._ctx, self._sid = keys[0], 0
@@ -228,7 +242,8 @@ class TrainPlan:
                 self._gr(y)
                 dres, dmode = (None, 0) if res is None else self._gw(res)
                 bbs.append(tops.bn_bwd_params(y.g, y.v, c, L["sums"], L["gamma"], L["dsums"], y.g, L["dgamma"], L["dbeta"],
-                                              relu=relu, dres=dres, dres_mode=dmode, sid=0))
+                                              relu=relu, dres=dres, dres_mode=dmode, sid=0,
+                                              beta=L["beta"] if (res is None and e.mask_from_c) else None))
             barr = (_lib.BnBwdParams * n)(*bbs)
             self.keep += [barr, bbs]
             self._b(lambda: _lib.check(lib.hrnb_bn_backward_batch(barr, n, _lib.stream_ptr())), "bn_bwd_batch:" + keys[0])
@@ -239,19 +254,35 @@ class TrainPlan:
         self.tape.append(back)
         return ys
 
+    def _bw(self, fn, name):
+        """record a weight-gradient launch.  Nothing downstream in the backward pass reads dW, so with the multi-stream plan
+        it goes to the companion stream (4 + s) of the branch stream s, ordered after the kernel that produced dc: the
+        chain bn_bwd -> dgrad -> bn_bwd ... of the branch no longer waits for its weight gradients."""
+        if not (self.multi_stream and self.eng.wgrad_streams):
+            return self._b(fn, name)
+        sid = self._sid
+        wsid = 4 if self.eng.wgrad_streams == 2 else 4 + sid      # 2: one shared weight-gradient stream
+        if not self._wg_forked:        # one fork per producer of dc, however many wgrad launches follow
+            self._wait(self.bwd, wsid, sid)
+            self._wg_forked = True
+        self._sid = wsid
+        self._b(fn, name)
+        self._sid = sid
+
     def _conv_backward(self, L, x, dc, need_dx):
         """weight gradient of conv L from (dc, x) and, if asked, the data gradient into x.g"""
         sp = L["spec"]
         dw = L["dw"]
         cin_g = dw.shape[1]
+        self._wg_forked = False
         if sp.stride == 1:
-            self._b(self._wgrad_fn(dc, x.v.ptr, x.v.ps, dw, cin_g, sp.cout, tops.fwd_taps_s1(sp.k, dc.Wp)), "wgrad:" + sp.key)
+            self._bw(self._wgrad_fn(dc, x.v.ptr, x.v.ps, dw, cin_g, sp.cout, tops.fwd_taps_s1(sp.k, dc.Wp)), "wgrad:" + sp.key)
             if need_dx:
                 gx, mode = self._gw(x)
                 self._b(self._conv_fn(L["dgrad"], dc, gx, res=gx if mode == 2 else None), "dgrad:" + sp.key)
         else:
             for ph, taps in tops.fwd_taps_s2(dc.Wp).items():
-                self._b(self._wgrad_fn(dc, x.v.ptr + ph * x.v.phase_stride * 2, x.v.ps, dw, cin_g, sp.cout, taps), "wgrad:" + sp.key)
+                self._bw(self._wgrad_fn(dc, x.v.ptr + ph * x.v.phase_stride * 2, x.v.ps, dw, cin_g, sp.cout, taps), "wgrad:" + sp.key)
             if need_dx:
                 gx, mode = self._gw(x)
                 for ph in range(4):
@@ -576,11 +607,20 @@ class TrainEngine:
         # griddepcontrol.wait, conv_tc.cu prologue), a second one is not understood yet; without PDL no run ever hung.
         self.multi_stream = os.environ.get("HRNB_TRAIN_STREAMS", "1") != "0" if multi_stream is None else bool(multi_stream)
         self.pdl = os.environ.get("HRNB_TRAIN_PDL", "0") == "1"
+        # BatchNorm batch statistics reduced in the epilogue of the producing conv where the tile shape allows it (cout = BN
+        # in {16, 32, 64}: the high-resolution layers); HRNB_FUSE_STATS=0: always the separate bn_stats pass
+        self.fuse_stats = os.environ.get("HRNB_FUSE_STATS", "1") != "0"
+        # BatchNorm backward of units without a residual input rebuilds the ReLU mask from the conv output instead of reading
+        # the unit output (two tensor reads less per unit); HRNB_BN_MASK_C=0: always read y
+        self.mask_from_c = os.environ.get("HRNB_BN_MASK_C", "0") == "1"
+        # multi-stream plan: weight-gradient launches on a companion stream per branch (HRNB_WGRAD_STREAMS=0: in line)
+        self.wgrad_streams = int(os.environ.get("HRNB_WGRAD_STREAMS", "0"))
         # single-stream plan: BatchNorm kernels of the branches of a module batched horizontally (HRNB_BN_BATCH=0: off)
         self.bn_batch = os.environ.get("HRNB_BN_BATCH", "1") != "0" if bn_batch is None else bool(bn_batch)
         self.plans = {}
         with torch.cuda.device(self.device):
-            self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+            _lib.hang_init()
+            self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(7)]   # 1-3: branches, 4-7: their wgrads
             self._setup(lr, betas, eps, weight_decay)
 
     def _setup(self, lr, betas, eps, weight_decay):

@@ -29,7 +29,7 @@ extern "C" {
 #define HRNB_EINVAL (-1)  /* bad argument / unsupported shape */
 #define HRNB_ECUDA (-2)   /* CUDA runtime error (message in hrnb_last_error) */
 
-#define HRNB_ABI_VERSION 2
+#define HRNB_ABI_VERSION 3
 
 /* guard bands (in positions) a PF8 plane must carry around [0, P) */
 #define HRNB_GUARD_LEAD(Wp) ((((Wp) + 2) + 7) / 8 * 8)
@@ -87,12 +87,23 @@ typedef struct hrnb_conv_params {
   int32_t ntap_custom;
   int32_t tap_src[9];
   int32_t tap_dpos[9];
+  /* Fused BatchNorm batch statistics (training path; NULL = off).  The epilogue also writes
+   * stats_sums[2*c] = sum_p out[p,c], stats_sums[2*c+1] = sum_p out[p,c]^2 over the real positions, from the fp32
+   * accumulators, in a fixed summation order (bit-reproducible) - the input of hrnb_bn_apply / hrnb_bn_bwd_*, i.e. it
+   * replaces the hrnb_bn_stats pass of nn.BatchNorm2d(train) lib/models/pose_hrnet.py:36.  Needs the flat-shift PF8
+   * path with BN == cout in {16, 32, 64}, no residual, no ReLU.  stats_ws: hrnb_conv_stats_ws_floats() floats, zeroed
+   * once, not shared between launches that may run concurrently. */
+  float* stats_sums;
+  float* stats_ws;
 } hrnb_conv_params;
 
 int hrnb_conv(const hrnb_conv_params* p, void* stream);
 
 /* dynamic shared memory (bytes) hrnb_conv will request for these parameters; < 0 on invalid params */
 int64_t hrnb_conv_smem_bytes(const hrnb_conv_params* p);
+
+/* floats of workspace a launch with stats_sums != NULL needs (first 32 floats = ticket counter, zero-initialised) */
+int64_t hrnb_conv_stats_ws_floats(void);
 
 /* Pack OIHW fp32 conv weights (device) into the tile order hrnb_conv streams, folding a per-output
  * channel scale (BN gamma/sqrt(var+eps), or NULL for 1).  out must hold
@@ -273,8 +284,9 @@ typedef struct hrnb_bn_params {
 } hrnb_bn_params;
 int hrnb_bn_apply(const hrnb_bn_params* p, void* stream);
 /* Horizontally batched form: statistics (written to p[j].sums) + normalisation of n <= 4 independent tensors (the
- * branches of a HighResolutionModule at the same depth) in two launches instead of 2n. */
-int hrnb_bn_forward_batch(const hrnb_bn_params* p, int32_t n, float* ws, void* stream);
+ * branches of a HighResolutionModule at the same depth) in two launches instead of 2n.  Bit j of have_stats_mask set:
+ * p[j].sums already holds the statistics (hrnb_conv_params.stats_sums), tensor j is left out of the statistics launch. */
+int hrnb_bn_forward_batch(const hrnb_bn_params* p, int32_t n, float* ws, int32_t have_stats_mask, void* stream);
 
 typedef struct hrnb_bn_bwd_params {
   const void* dy;         /* gradient of the unit output, PF8                                         */
@@ -297,6 +309,8 @@ typedef struct hrnb_bn_bwd_params {
   int32_t N, C, H, W;
   int32_t relu;
   float eps;
+  const float* beta;      /* relu != 0 and y == NULL (units WITHOUT a residual input only): the ReLU mask is rebuilt
+                           * from c as fma(c, a, b) > 0 with the forward pass's own a, b - saves both reads of y      */
 } hrnb_bn_bwd_params;
 int hrnb_bn_bwd_reduce(const hrnb_bn_bwd_params* p, void* stream);
 int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream);
@@ -338,6 +352,13 @@ const char* hrnb_last_error(void);
 int hrnb_abi_version(void);
 /* number of kernel launches issued through this library by the calling process (for bench gpu_launches) */
 int64_t hrnb_launch_count(void);
+/* Hang diagnostics.  Every mbarrier wait of the tcgen05 kernels is bounded (4 s): a protocol bug traps instead of hanging
+ * the device.  hrnb_hang_init() (once per device, outside stream capture) arms a mapped host buffer into which the warps
+ * that time out write (kernel, CTA, warp, barrier) records before trapping; hrnb_hang_report() copies up to n 64-bit words
+ * of it (word 0 != 0: a time-out happened; records from word 2, two words each: blockDim.x << 48 | gridDim.x << 32 |
+ * blockIdx.x << 8 | warp, barrier shared-memory address << 8 | parity) and works after the context died. */
+int hrnb_hang_init(void);
+int hrnb_hang_report(uint64_t* out_host, int n);
 /* debug knobs (key 0: exchange the LBO/SBO roles of the UMMA descriptors); not part of the product API */
 int hrnb_debug_set(int key, int value);
 /* debug: device buffer of 5*64 int64 receiving clock64 timestamps of CTA 0's roles (NULL = off) */

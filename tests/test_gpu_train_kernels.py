@@ -141,7 +141,7 @@ def test_dgrad_stride2_matches_autograd(N, H, W, cin, cout):
 
 
 @pytest.mark.parametrize("N,C,H,W,relu,use_res", [(2, 32, 16, 16, True, True), (4, 64, 8, 12, True, False), (2, 256, 8, 8, False, False),
-                                                  (64, 32, 64, 64, True, True)])
+                                                  (64, 32, 64, 64, True, True), (64, 32, 64, 64, True, False)])
 def test_bn_train_forward_backward(N, C, H, W, relu, use_res):
     from hrnet_b200 import tops
     from hrnet_b200.ops import PF8
@@ -177,12 +177,83 @@ def test_bn_train_forward_backward(N, C, H, W, relu, use_res):
     dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     prev = _bf16(_rand(N, C, H, W, seed=12))
     dres = PF8.from_nchw(prev) if use_res else None
+    if relu and not use_res:
+        # the same backward with the ReLU mask rebuilt from c (y is not read): bit-identical to the y-mask form
+        dy2, ds2 = PF8.from_nchw(dy), torch.zeros(C, 2, device="cuda")
+        dg2, db2 = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        tops.bn_bwd(dy2, None, cp, sums, gamma.detach(), ds2, dy2, dg2, db2, relu=True, beta=beta.detach())
     tops.bn_bwd(dyp, y, cp, sums, gamma.detach(), dsums, dyp, dgamma, dbeta, relu=relu, dres=dres, dres_mode=2)
+    if relu and not use_res:
+        assert torch.equal(dy2.buf, dyp.buf) and torch.equal(ds2, dsums) and torch.equal(dg2, dgamma) and torch.equal(db2, dbeta)
     assert dyp.padding_is_zero()
     assert _relerr(dyp.to_nchw(), cr.grad) < 2e-2
     assert _relerr(dgamma, gamma.grad) < 1e-2 and _relerr(dbeta, beta.grad) < 1e-2
     if use_res:
         assert _relerr(dres.to_nchw(), rr.grad + prev) < 1e-2
+
+
+STATS_CASES = [
+    # N, H, W, cin, cout, k, stride
+    (2, 16, 16, 32, 32, 3, 1),
+    (64, 64, 64, 32, 32, 3, 1),      # BASELINE configs[1] branch-0 layer at its full size
+    (3, 32, 32, 64, 64, 3, 1),
+    (5, 24, 40, 64, 32, 1, 1),
+    (2, 32, 32, 32, 16, 1, 1),
+    (2, 32, 32, 32, 64, 3, 2),
+    (64, 32, 32, 256, 64, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", STATS_CASES, ids=lambda c: "N%d_%dx%d_c%d-%d_k%d_s%d" % c)
+def test_conv_fused_bn_statistics(case):
+    """conv launch with stats_sums (BatchNorm batch statistics reduced in the conv epilogue, include/hrnb.h) against
+    torch (fp64 sums of the fp32 conv of the same bf16 inputs), against the separate hrnb_bn_stats pass over the bf16
+    output, bit-identical when repeated (fixed summation order), and the conv output itself unchanged."""
+    from hrnet_b200 import tops
+    from hrnet_b200.ops import ConvLayer, PF8, PhasePF8, phase_split
+    N, H, W, cin, cout, k, stride = case
+    x = _bf16(_rand(N, cin, H, W, seed=21) + 0.2)
+    w = _bf16(_rand(cout, cin, k, k, seed=22, scale=1.0 / (cin * k * k) ** 0.5)).contiguous()
+    ref = F.conv2d(x, w, None, stride=stride, padding=k // 2).double()
+    ref_sums = torch.stack([ref.sum(dim=(0, 2, 3)), (ref * ref).sum(dim=(0, 2, 3))], dim=1)
+    xp = PF8.from_nchw(x)
+    if stride == 2:
+        ph = PhasePF8(N, cin, H, W)
+        phase_split(xp, ph)
+        xp = ph
+    layer = ConvLayer(w, stride=stride)
+    Ho, Wo = H // stride, W // stride
+    plain, out = PF8(N, cout, Ho, Wo), PF8(N, cout, Ho, Wo)
+    layer(xp, plain, bn=cout)
+    sums = torch.full((cout, 2), 7.0, device="cuda")
+    layer(xp, out, bn=cout, stats=sums)
+    torch.cuda.synchronize()
+    assert torch.equal(out.buf, plain.buf)
+    tol = 2e-3 * ref_sums.abs().max(dim=0).values.float()
+    assert ((sums - ref_sums.float()).abs() <= tol).all(), (sums - ref_sums.float()).abs().max(dim=0)
+    separate = torch.zeros(cout, 2, device="cuda")
+    tops.bn_stats(out, separate)
+    assert ((sums - separate).abs() <= tol).all()
+    again = torch.zeros(cout, 2, device="cuda")
+    layer(xp, out, bn=cout, stats=again)      # a new launch struct = a new workspace
+    assert torch.equal(again, sums)
+    from hrnet_b200 import _lib
+    from hrnet_b200.ops import attach_stats
+    p = layer.params(xp, out, bn=cout)
+    third = torch.zeros(cout, 2, device="cuda")
+    assert attach_stats(p, third)
+    for _ in range(3):               # the same struct replayed: the ticket counter must have reset itself
+        third.zero_()
+        _lib.check(_lib.lib().hrnb_conv(C.byref(p), _lib.stream_ptr()))
+    assert torch.equal(third, sums)
+
+
+def test_conv_fused_bn_statistics_rejects_ineligible_launches():
+    from hrnet_b200.ops import ConvLayer, PF8
+    x = PF8.from_nchw(_rand(2, 128, 16, 16, seed=23))
+    layer = ConvLayer(_rand(128, 128, 3, 3, seed=24, scale=0.03).contiguous())
+    with pytest.raises(ValueError):
+        layer(x, PF8(2, 128, 16, 16), stats=torch.zeros(128, 2, device="cuda"))
 
 
 def test_fuse_sum_backward_matches_autograd():

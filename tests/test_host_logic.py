@@ -82,3 +82,14 @@ def test_state_dict_interchange_with_reference():
     ours.load_state_dict({"module." + k: v for k, v in ref.state_dict().items()}, strict=False)  # DP prefix: no match, no crash
     for k, v in ref.state_dict().items():
         assert ours.state_dict()[k].shape == v.shape and ours.state_dict()[k].dtype == v.dtype
+
+
+def test_product_synthetic_data_equals_the_test_fixtures():
+    """bench.py's product arm draws its workload from hrnet_b200.synthetic (it must not import oracle/): same tensors as
+    the fixtures the goldens and the CPU baseline use"""
+    import torch
+    from hrnet_b200 import synthetic
+    from oracle import fixtures
+    assert torch.equal(synthetic.images(2, 64, 96, seed=5), fixtures.images(2, 64, 96, seed=5))
+    for a, b in zip(synthetic.targets(3, 21, 16, 24, seed=7), fixtures.targets(3, 21, 16, 24, seed=7)):
+        assert torch.equal(a, b)
