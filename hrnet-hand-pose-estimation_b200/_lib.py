@@ -89,7 +89,6 @@ class BnBwdParams(C.Structure):
         ("ws", C.c_void_p), ("dc", C.c_void_p), ("dc_ps", C.c_int64), ("dres", C.c_void_p), ("dres_ps", C.c_int64), ("dres_mode", C.c_int32),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("N", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu", C.c_int32), ("eps", C.c_float),
-        ("beta", C.c_void_p),
     ]
 
 

@@ -202,14 +202,24 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
             if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
           }
           // one weight stage per K chunk: all taps of the chunk in a single bulk copy (one hand-off per chunk)
-          mbar_wait(&empty_b[b_stage], b_phase ^ 1);
           if (b_prefetched) {
-            b_prefetched = false;   // stage 0 of the first tile is already in flight
-          } else if (k.dbg & 16) {
-            if (elect_one_sync()) mbar_arrive(&full_b[b_stage]);
-          } else if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
-            bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, k.b_stage_bytes, &full_b[b_stage]);
+            // Stage 0 of the first tile is already in flight - and there is NOTHING to wait for: waiting here for the
+            // "previous" phase of empty_b[0] (parity 1) is only a no-op while that barrier is still in phase 0.  The MMA
+            // warp can consume the prefetched stage and commit empty_b[0] before this warp gets here (it only needs the
+            // A stage issued a few instructions above; an instruction-cache miss of this warp under multi-kernel
+            // co-residency is enough), the barrier flips to phase 1 and the wait then blocks until the stage is released
+            // a SECOND time - never, in a CTA with one tile and <= SB chunks.  That was the device-side mbarrier
+            // time-out of round 1 (programmatic dependent launch / extra streams; profiles/r1_hang_records_*.txt: only
+            // producer warps of 1-tile conv CTAs stuck on empty_b[0], parity 1).
+            b_prefetched = false;
+          } else {
+            mbar_wait(&empty_b[b_stage], b_phase ^ 1);
+            if (k.dbg & 16) {
+              if (elect_one_sync()) mbar_arrive(&full_b[b_stage]);
+            } else if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
+              bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, k.b_stage_bytes, &full_b[b_stage]);
+            }
           }
           __syncwarp();
           wsrc += b_elems;

@@ -149,26 +149,17 @@ struct BnK {
   float eps, momentum, count;
 };
 
-// The normalisation as one FMA per element, y = fma(c, a, b).  Shared by the forward kernel and by the backward kernels that
-// rebuild the ReLU mask from c instead of reading y (same instructions -> bit-identical pre-activation values).
-__device__ __forceinline__ void bn_affine(const float* sums, const float* gamma, const float* beta, int ch, float count, float eps,
-                                          float& mean, float& var, float& a, float& b) {
-  mean = sums[2 * ch] / count;
-  var = sums[2 * ch + 1] / count - mean * mean;
-  var = fmaxf(var, 0.f);
-  a = gamma[ch] * rsqrtf(var + eps);
-  b = __fmaf_rn(-mean, a, beta[ch]);
-}
-
 // y = [relu]( gamma*(c-mean)*invstd + beta [+ res] ), zeros at padding; block (0, plane) also updates the running stats
 __device__ __forceinline__ void bn_apply_body(const BnK& k, int plane, unsigned bx) {
   __shared__ float sa[8], sb[8];
   if (threadIdx.x < 8) {
     const int ch = plane * 8 + threadIdx.x;
-    float mean, var, a, b;
-    bn_affine(k.sums, k.gamma, k.beta, ch, k.count, k.eps, mean, var, a, b);
+    const float mean = k.sums[2 * ch] / k.count;
+    float var = k.sums[2 * ch + 1] / k.count - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float a = k.gamma[ch] * rsqrtf(var + k.eps);
     sa[threadIdx.x] = a;
-    sb[threadIdx.x] = b;
+    sb[threadIdx.x] = k.beta[ch] - mean * a;
     if (bx == 0 && k.running_mean != nullptr) {
       const float unbiased = k.count > 1.f ? var * k.count / (k.count - 1.f) : var;
       k.running_mean[ch] = (1.f - k.momentum) * k.running_mean[ch] + k.momentum * mean;
@@ -184,7 +175,7 @@ __device__ __forceinline__ void bn_apply_body(const BnK& k, int plane, unsigned 
     float x[8];
     unpack8(ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8), x);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = __fmaf_rn(x[i], sa[i], sb[i]);
+    for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], sa[i], sb[i]);
     if (k.res != nullptr) {
       float r[8];
       unpack8(ldg_nc_v4(k.res + ((long long)plane * k.res_ps + p) * 8), r);
@@ -213,7 +204,6 @@ struct BnBwdK {
   const __nv_bfloat16* y; long long y_ps;
   const __nv_bfloat16* c; long long c_ps;
   const float* sums; const float* gamma;
-  const float* beta;      // relu && y == nullptr: ReLU mask rebuilt from c (units without a residual input)
   float* dsums;
   float* ws;
   __nv_bfloat16* dc; long long dc_ps;
@@ -238,23 +228,12 @@ __device__ __forceinline__ void relu_mask8(float (&g)[8], const uint4 yv) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) g[i] = yy[i] > 0.f ? g[i] : 0.f;
 }
-// ... or from the conv output when the unit has no residual input: y > 0  <=>  fma(c, a, b) > 0 (bf16 rounding keeps the sign)
-__device__ __forceinline__ void relu_mask8_from_c(float (&g)[8], const float (&x)[8], const float* sa, const float* sb) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) g[i] = __fmaf_rn(x[i], sa[i], sb[i]) > 0.f ? g[i] : 0.f;
-}
+
 
 // dsums[c][0] = sum g, dsums[c][1] = sum g*xhat with g = dy * relu mask
 __device__ __forceinline__ void bn_bwd_reduce_body(const BnBwdK& k, int plane, int gplane, unsigned nb, unsigned bx) {
-  __shared__ float sm[8], si[8], ma[8], mb[8];
-  const bool mask_y = k.relu && k.y != nullptr, mask_c = k.relu && k.y == nullptr;
-  if (threadIdx.x < 8) {
-    bn_channel_stats(k.sums, plane * 8 + threadIdx.x, k.count, k.eps, sm[threadIdx.x], si[threadIdx.x]);
-    if (mask_c) {
-      float mean, var;
-      bn_affine(k.sums, k.gamma, k.beta, plane * 8 + threadIdx.x, k.count, k.eps, mean, var, ma[threadIdx.x], mb[threadIdx.x]);
-    }
-  }
+  __shared__ float sm[8], si[8];
+  if (threadIdx.x < 8) bn_channel_stats(k.sums, plane * 8 + threadIdx.x, k.count, k.eps, sm[threadIdx.x], si[threadIdx.x]);
   __syncthreads();
   float v[16];
 #pragma unroll
@@ -269,15 +248,14 @@ __device__ __forceinline__ void bn_bwd_reduce_body(const BnBwdK& k, int plane, i
       const bool ok = q < k.g.P;
       rg[u] = ok ? ldg_nc_v4(k.dy + ((long long)plane * k.dy_ps + q) * 8) : z;
       rc[u] = ok ? ldg_nc_v4(k.c + ((long long)plane * k.c_ps + q) * 8) : z;
-      ry[u] = (ok && mask_y) ? ldg_nc_v4(k.y + ((long long)plane * k.y_ps + q) * 8) : z;
+      ry[u] = (ok && k.relu) ? ldg_nc_v4(k.y + ((long long)plane * k.y_ps + q) * 8) : z;
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       float g[8], x[8];
       unpack8(rg[u], g);
       unpack8(rc[u], x);
-      if (mask_y) relu_mask8(g, ry[u]);
-      if (mask_c) relu_mask8_from_c(g, x, ma, mb);
+      if (k.relu) relu_mask8(g, ry[u]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         v[2 * i] += g[i];
@@ -295,16 +273,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
 
 // dc = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dres (+)= g; block (0, plane) writes dgamma / dbeta
 __device__ __forceinline__ void bn_bwd_apply_body(const BnBwdK& k, int plane, unsigned bx) {
-  __shared__ float sm[8], si[8], sa[8], s0[8], s1[8], ma[8], mb[8];
-  const bool mask_y = k.relu && k.y != nullptr, mask_c = k.relu && k.y == nullptr;
+  __shared__ float sm[8], si[8], sa[8], s0[8], s1[8];
   if (threadIdx.x < 8) {
     const int ch = plane * 8 + threadIdx.x;
     float mean, invstd;
     bn_channel_stats(k.sums, ch, k.count, k.eps, mean, invstd);
-    if (mask_c) {
-      float mean2, var2;
-      bn_affine(k.sums, k.gamma, k.beta, ch, k.count, k.eps, mean2, var2, ma[threadIdx.x], mb[threadIdx.x]);
-    }
     sm[threadIdx.x] = mean;
     si[threadIdx.x] = invstd;
     sa[threadIdx.x] = k.gamma[ch] * invstd;
@@ -327,8 +300,7 @@ __device__ __forceinline__ void bn_bwd_apply_body(const BnBwdK& k, int plane, un
     float g[8], x[8];
     unpack8(*reinterpret_cast<const uint4*>(k.dy + ((long long)plane * k.dy_ps + p) * 8), g);
     unpack8(ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8), x);
-    if (mask_y) relu_mask8(g, ldg_nc_v4(k.y + ((long long)plane * k.y_ps + p) * 8));
-    if (mask_c) relu_mask8_from_c(g, x, ma, mb);
+    if (k.relu) relu_mask8(g, ldg_nc_v4(k.y + ((long long)plane * k.y_ps + p) * 8));
     if (k.dres_mode == 2) {
       float r[8];
       unpack8(*reinterpret_cast<const uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8), r);
@@ -708,12 +680,11 @@ extern "C" int hrnb_bn_apply(const hrnb_bn_params* p, void* stream) {
 static int make_bwd(const hrnb_bn_bwd_params* p, BnBwdK* k) {
   if (!p || !p->dy || !p->c || !p->sums || !p->gamma || !p->dsums || !p->ws || p->C % 8 || p->C <= 0 || p->C / 8 > kMaxPlanes)
     return fail(HRNB_EINVAL, "bn_bwd: bad params");
-  if (p->relu && !p->y && !p->beta) return fail(HRNB_EINVAL, "bn_bwd: relu needs the unit output y, or beta to rebuild the mask from c");
-  if (p->relu && !p->y && p->dres) return fail(HRNB_EINVAL, "bn_bwd: the mask can only be rebuilt from c for units without a residual input");
+  if (p->relu && !p->y) return fail(HRNB_EINVAL, "bn_bwd: relu needs the unit output y");
   k->dy = (const __nv_bfloat16*)p->dy; k->dy_ps = p->dy_ps;
   k->y = (const __nv_bfloat16*)p->y; k->y_ps = p->y_ps;
   k->c = (const __nv_bfloat16*)p->c; k->c_ps = p->c_ps;
-  k->sums = p->sums; k->gamma = p->gamma; k->beta = p->beta; k->dsums = p->dsums; k->ws = p->ws;
+  k->sums = p->sums; k->gamma = p->gamma; k->dsums = p->dsums; k->ws = p->ws;
   k->dc = (__nv_bfloat16*)p->dc; k->dc_ps = p->dc_ps;
   k->dres = (__nv_bfloat16*)p->dres; k->dres_ps = p->dres_ps; k->dres_mode = p->dres ? p->dres_mode : 0;
   k->dgamma = p->dgamma; k->dbeta = p->dbeta;

@@ -116,14 +116,9 @@ def bn_apply(*a, **k):
     _lib.check(_lib.lib().hrnb_bn_apply(C.byref(p), _lib.stream_ptr()))
 
 
-def bn_bwd_params(dy, y, c, sums, gamma, dsums, dc, dgamma, dbeta, relu=True, dres=None, dres_mode=1, sid=0, beta=None):
-    """beta given and the unit has no residual input: the ReLU mask is rebuilt from c (y is not read at all)"""
+def bn_bwd_params(dy, y, c, sums, gamma, dsums, dc, dgamma, dbeta, relu=True, dres=None, dres_mode=1, sid=0):
     p = BnBwdParams()
     p.dy, p.dy_ps = dy.ptr, dy.ps
-    if relu and beta is not None and dres is None:
-        y = None
-        p.beta = beta.data_ptr()
-    assert not relu or y is not None or p.beta
     p.y, p.y_ps = (y.ptr, y.ps) if (y is not None and relu) else (None, 0)
     p.c, p.c_ps, p.sums, p.gamma, p.dsums = c.ptr, c.ps, sums.data_ptr(), gamma.data_ptr(), dsums.data_ptr()
     p.ws = reduce_ws(dsums.device, sid).data_ptr()

@@ -195,8 +195,7 @@ class TrainPlan:
             if res is not None:
                 dres, dmode = self._gw(res)
             bb = tops.bn_bwd_params(dy, y.v, c, sums, L["gamma"], dsums, dy, L["dgamma"], L["dbeta"], relu=relu,
-                                    dres=dres, dres_mode=dmode, sid=sid,
-                                    beta=L["beta"] if (res is None and e.mask_from_c) else None)
+                                    dres=dres, dres_mode=dmode, sid=sid)
             self.keep.append(bb)
             r = C.byref(bb)
             self._b(lambda: _lib.check(lib.hrnb_bn_bwd_reduce(r, _lib.stream_ptr())), "bn_bwd_reduce:" + key)
@@ -242,8 +241,7 @@ class TrainPlan:
                 self._gr(y)
                 dres, dmode = (None, 0) if res is None else self._gw(res)
                 bbs.append(tops.bn_bwd_params(y.g, y.v, c, L["sums"], L["gamma"], L["dsums"], y.g, L["dgamma"], L["dbeta"],
-                                              relu=relu, dres=dres, dres_mode=dmode, sid=0,
-                                              beta=L["beta"] if (res is None and e.mask_from_c) else None))
+                                              relu=relu, dres=dres, dres_mode=dmode, sid=0))
             barr = (_lib.BnBwdParams * n)(*bbs)
             self.keep += [barr, bbs]
             self._b(lambda: _lib.check(lib.hrnb_bn_backward_batch(barr, n, _lib.stream_ptr())), "bn_bwd_batch:" + keys[0])
@@ -610,11 +608,10 @@ class TrainEngine:
         # BatchNorm batch statistics reduced in the epilogue of the producing conv where the tile shape allows it (cout = BN
         # in {16, 32, 64}: the high-resolution layers); HRNB_FUSE_STATS=0: always the separate bn_stats pass
         self.fuse_stats = os.environ.get("HRNB_FUSE_STATS", "1") != "0"
-        # BatchNorm backward of units without a residual input rebuilds the ReLU mask from the conv output instead of reading
-        # the unit output (two tensor reads less per unit); HRNB_BN_MASK_C=0: always read y
-        self.mask_from_c = os.environ.get("HRNB_BN_MASK_C", "0") == "1"
-        # multi-stream plan: weight-gradient launches on a companion stream per branch (HRNB_WGRAD_STREAMS=0: in line)
-        self.wgrad_streams = int(os.environ.get("HRNB_WGRAD_STREAMS", "0"))
+        # EXPERIMENTAL, off: weight-gradient launches of the multi-stream plan on companion streams (HRNB_WGRAD_STREAMS=1: one
+        # per branch, 2: one shared).  Measured 27.3 vs 28.7 ms/step, but bench runs end in device-side mbarrier time-outs
+        # (a conv kernel whose producer warp waits for weight-stage releases that never come) - see DESIGN.md §5.
+        self.wgrad_streams = int(os.environ.get("HRNB_WGRAD_STREAMS", "2"))
         # single-stream plan: BatchNorm kernels of the branches of a module batched horizontally (HRNB_BN_BATCH=0: off)
         self.bn_batch = os.environ.get("HRNB_BN_BATCH", "1") != "0" if bn_batch is None else bool(bn_batch)
         self.plans = {}

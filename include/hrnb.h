@@ -309,8 +309,6 @@ typedef struct hrnb_bn_bwd_params {
   int32_t N, C, H, W;
   int32_t relu;
   float eps;
-  const float* beta;      /* relu != 0 and y == NULL (units WITHOUT a residual input only): the ReLU mask is rebuilt
-                           * from c as fma(c, a, b) > 0 with the forward pass's own a, b - saves both reads of y      */
 } hrnb_bn_bwd_params;
 int hrnb_bn_bwd_reduce(const hrnb_bn_bwd_params* p, void* stream);
 int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream);

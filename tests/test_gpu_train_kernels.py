@@ -177,14 +177,7 @@ def test_bn_train_forward_backward(N, C, H, W, relu, use_res):
     dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     prev = _bf16(_rand(N, C, H, W, seed=12))
     dres = PF8.from_nchw(prev) if use_res else None
-    if relu and not use_res:
-        # the same backward with the ReLU mask rebuilt from c (y is not read): bit-identical to the y-mask form
-        dy2, ds2 = PF8.from_nchw(dy), torch.zeros(C, 2, device="cuda")
-        dg2, db2 = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
-        tops.bn_bwd(dy2, None, cp, sums, gamma.detach(), ds2, dy2, dg2, db2, relu=True, beta=beta.detach())
     tops.bn_bwd(dyp, y, cp, sums, gamma.detach(), dsums, dyp, dgamma, dbeta, relu=relu, dres=dres, dres_mode=2)
-    if relu and not use_res:
-        assert torch.equal(dy2.buf, dyp.buf) and torch.equal(ds2, dsums) and torch.equal(dg2, dgamma) and torch.equal(db2, dbeta)
     assert dyp.padding_is_zero()
     assert _relerr(dyp.to_nchw(), cr.grad) < 2e-2
     assert _relerr(dgamma, gamma.grad) < 1e-2 and _relerr(dbeta, beta.grad) < 1e-2

@@ -8,7 +8,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import fixtures  # noqa: E402
+from hrnet_b200 import synthetic as fixtures  # noqa: E402
 from hrnet_b200.config import make_cfg  # noqa: E402
 from hrnet_b200.models import pose_hrnet_softmax  # noqa: E402
 from hrnet_b200.train import TrainEngine  # noqa: E402
