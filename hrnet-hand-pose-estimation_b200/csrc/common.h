@@ -14,9 +14,11 @@ unsigned long long* hang_buffer_device_ptr();        // mapped host buffer of th
 int bind_hang_buffer_conv();                         // per translation unit: point its g_hang_buf at the buffer
 int bind_hang_buffer_wgrad();
 // Every kernel that allocates tensor memory asks for at least this much dynamic shared memory, so that no two of them are
-// ever co-resident on one SM (2 x 116 KB > 227 KB).  With concurrent streams a conv CTA holding all 512 TMEM columns and a
-// wgrad CTA blocked in tcgen05.alloc on the same SM deadlocked: the conv's MMA / epilogue warps stopped inside tcgen05
-// instructions, only its producer warp was left waiting on an mbarrier [hang records, round 1: DESIGN.md §5].
+// ever co-resident on one SM (2 x 116 KB > 227 KB): a conv CTA may hold all 512 TMEM columns, and a second CTA blocked in
+// tcgen05.alloc next to it is the one kind of cross-kernel coupling these kernels could have (the TMEM deadlock chain under
+// programmatic dependent launch described in conv_tc.cu was of that kind).  No measurable cost at batch 64 [28.73 vs 28.75
+// ms/step]; it did NOT cure the round-1 mbarrier time-out (that was the producer's prefetch wait, conv_tc.cu).
+// hrnb_debug_set(6, 1) / HRNB_TMEM_SHARE=1 turns the padding off.
 constexpr long long kTmemExclusiveSmem = 116 * 1024;
 extern int g_debug[8];                               // hrnb_debug_set knobs (conv_tc.cu); [4] != 0: PDL for the elementwise / wgrad kernels
 

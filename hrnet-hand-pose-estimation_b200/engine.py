@@ -313,7 +313,8 @@ class HRNetEngine:
         self.use_graph = os.environ.get("HRNB_NO_GRAPH", "0") != "1"
         self.single_stream = os.environ.get("HRNB_SINGLE_STREAM", "0") == "1"
         # programmatic dependent launch of the conv kernels is opt-in (HRNB_PDL=1; 4.16 vs 4.21 ms/step at batch 64): PDL
-        # launches showed rare device-side mbarrier time-outs in the training engine this round (train.py)
+        # launches showed rare device-side mbarrier time-outs in the training engine this round; the cause (conv_tc.cu
+        # producer, prefetched weight stage) is fixed, the soak that would make PDL the default is not done yet (train.py)
         self.pdl = os.environ.get("HRNB_PDL", "0") == "1"
         with torch.cuda.device(self.device):
             _lib.hang_init()

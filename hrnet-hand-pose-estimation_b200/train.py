@@ -598,19 +598,18 @@ class TrainEngine:
         self.use_graph = use_graph and os.environ.get("HRNB_NO_GRAPH", "0") != "1"
         # Default: branches of a HighResolutionModule on parallel streams, plain stream-ordered launches.
         # HRNB_TRAIN_STREAMS=0: single-stream plan with the BatchNorm kernels of a module's branches batched horizontally.
-        # HRNB_TRAIN_PDL=1: programmatic dependent launch (PDL) on every kernel of the step.  Measured at batch 64:
-        # 27.4 ms/step (streams, default), 26.9 (streams + PDL), 29.6 (single stream + PDL), 30.6 (single stream).
-        # PDL is NOT on by default: with it about one bench run in eight (either plan) ended in a device-side mbarrier
-        # time-out - a tcgen05 kernel waiting forever.  One cause was found and fixed this round (TMEM held across
-        # griddepcontrol.wait, conv_tc.cu prologue), a second one is not understood yet; without PDL no run ever hung.
+        # HRNB_TRAIN_PDL=1: programmatic dependent launch (PDL) on every kernel of the step: 23.0 vs 25.0 ms/step at batch 64.
+        # PDL is still opt-in: before the producer fix in conv_tc.cu (the prefetched weight stage must not wait on empty_b)
+        # about one PDL bench run in eight ended in a device-side mbarrier time-out; after it 5 of 5 runs passed, which is
+        # not yet the soak a default needs (profiles/r1_hang_records_wgrad_streams.txt).
         self.multi_stream = os.environ.get("HRNB_TRAIN_STREAMS", "1") != "0" if multi_stream is None else bool(multi_stream)
         self.pdl = os.environ.get("HRNB_TRAIN_PDL", "0") == "1"
         # BatchNorm batch statistics reduced in the epilogue of the producing conv where the tile shape allows it (cout = BN
         # in {16, 32, 64}: the high-resolution layers); HRNB_FUSE_STATS=0: always the separate bn_stats pass
         self.fuse_stats = os.environ.get("HRNB_FUSE_STATS", "1") != "0"
-        # EXPERIMENTAL, off: weight-gradient launches of the multi-stream plan on companion streams (HRNB_WGRAD_STREAMS=1: one
-        # per branch, 2: one shared).  Measured 27.3 vs 28.7 ms/step, but bench runs end in device-side mbarrier time-outs
-        # (a conv kernel whose producer warp waits for weight-stage releases that never come) - see DESIGN.md §5.
+        # Weight-gradient launches of the multi-stream plan run on a companion stream (nothing downstream in the backward
+        # pass reads dW): HRNB_WGRAD_STREAMS=2 (default) one shared stream, 1 one per branch, 0 in line on the branch stream.
+        # Measured at batch 64: 25.0 (shared) / 25.9 (in line) ms/step; one stream per branch was not faster than in line.
         self.wgrad_streams = int(os.environ.get("HRNB_WGRAD_STREAMS", "2"))
         # single-stream plan: BatchNorm kernels of the branches of a module batched horizontally (HRNB_BN_BATCH=0: off)
         self.bn_batch = os.environ.get("HRNB_BN_BATCH", "1") != "0" if bn_batch is None else bool(bn_batch)
