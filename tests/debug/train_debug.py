@@ -1,11 +1,11 @@
 """Debug helper (GPU box): per-parameter gradient parity of one training step against the torch oracle, listed from
-the head backwards so the first broken layer of the backward pass is visible.  python tools/train_debug.py [B H W variant]"""
+the head backwards so the first broken layer of the backward pass is visible.  python tests/debug/train_debug.py [B H W variant]  (test infrastructure: uses the oracle)"""
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import fixtures, hrnet_oracle, train_oracle  # noqa: E402
 from hrnet_b200.config import make_cfg  # noqa: E402

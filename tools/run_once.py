@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 os.environ["HRNB_NO_GRAPH"] = "1"
 import torch  # noqa: E402
 from bench import build_model  # noqa: E402
-from oracle import fixtures  # noqa: E402
+from hrnet_b200 import synthetic as fixtures  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 2

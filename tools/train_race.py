@@ -4,7 +4,7 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import fixtures
+from hrnet_b200 import synthetic as fixtures
 from hrnet_b200 import _lib
 from hrnet_b200.config import make_cfg
 from hrnet_b200.models import pose_hrnet_softmax
