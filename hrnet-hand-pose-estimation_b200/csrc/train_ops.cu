@@ -487,6 +487,84 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* 
   *reinterpret_cast<uint4*>(ds + ((long long)plane * ds_ps + p) * 8) = o;
 }
 
+// Separable form, one block = one image x one channel plane (STAGED: opt-in through hrnb_debug_set(7, 1) until it has been
+// verified on hardware; the gather kernel above stays the default).  The destination-gradient tile of the image is read
+// ONCE with coalesced 16-byte loads into shared memory; pass 1 reduces along x into t[y][sx], pass 2 along y into the source
+// gradient.  The gather kernel re-reads every destination row ~3x per source row and evaluates the interpolation index
+// per (y, x) pair: 342 us for 256 channels 64x64 -> 8x8 at batch 64 (6 % of the HBM roofline, profiles/).
+// shared memory: tables (dH + dW) x 12 B | tile dH*dW x 16 B | t dH*sW x 32 B
+__global__ void __launch_bounds__(256) bilinear_bwd_sep_kernel(const __nv_bfloat16* __restrict__ dd, long long dd_ps, Geo dg,
+                                                              __nv_bfloat16* __restrict__ ds, long long ds_ps, Geo sg, int align,
+                                                              int mode) {
+  extern __shared__ __align__(16) uint8_t sep_smem[];
+  const int dH = dg.H, dW = dg.W, sH = sg.H, sW = sg.W;
+  uint4* tile = reinterpret_cast<uint4*>(sep_smem);                               // [dH][dW]
+  float* t = reinterpret_cast<float*>(sep_smem + (size_t)dH * dW * 16);           // [dH][sW][8]
+  int* y0 = reinterpret_cast<int*>(t + (size_t)dH * sW * 8);                      // [dH] i0, [dH] i1, [dH] l1 (as float)
+  int* y1 = y0 + dH;
+  float* yl = reinterpret_cast<float*>(y1 + dH);
+  int* x0 = reinterpret_cast<int*>(yl + dH);
+  int* x1 = x0 + dW;
+  float* xl = reinterpret_cast<float*>(x1 + dW);
+  const int n = blockIdx.x, plane = blockIdx.y, tid = threadIdx.x;
+  for (int d = tid; d < dH; d += blockDim.x) bil_index(d, sH, dH, align != 0, y0[d], y1[d], yl[d]);
+  for (int d = tid; d < dW; d += blockDim.x) bil_index(d, sW, dW, align != 0, x0[d], x1[d], xl[d]);
+  const __nv_bfloat16* src_plane = dd + (long long)plane * dd_ps * 8;
+  for (int i = tid; i < dH * dW; i += blockDim.x) {
+    const int y = i / dW, x = i - y * dW;
+    tile[i] = ldg_nc_v4(src_plane + (((long long)n * dg.Hp + y + 1) * dg.Wp + x + 1) * 8);
+  }
+  __syncthreads();
+  const int fy = (dH + sH - 1) / sH, fx = (dW + sW - 1) / sW;
+  // pass 1: t[y][sx] = sum_x wx(sx, x) * g[y][x]
+  for (int o = tid; o < dH * sW; o += blockDim.x) {
+    const int y = o / sW, sx = o - y * sW;
+    const int xlo = max(0, (sx - 1) * fx - fx), xhi = min(dW - 1, (sx + 1) * fx + fx);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int x = xlo; x <= xhi; ++x) {
+      const float w = (x0[x] == sx ? 1.f - xl[x] : 0.f) + (x1[x] == sx ? xl[x] : 0.f);
+      if (w == 0.f) continue;
+      float g[8];
+      unpack8(tile[y * dW + x], g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(w, g[i], a[i]);
+    }
+    float4* dst = reinterpret_cast<float4*>(t + (size_t)o * 8);
+    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+  }
+  __syncthreads();
+  // pass 2: dsrc[sy][sx] (+)= sum_y wy(sy, y) * t[y][sx]
+  __nv_bfloat16* out_plane = ds + (long long)plane * ds_ps * 8;
+  for (int o = tid; o < sH * sW; o += blockDim.x) {
+    const int sy = o / sW, sx = o - sy * sW;
+    const int ylo = max(0, (sy - 1) * fy - fy), yhi = min(dH - 1, (sy + 1) * fy + fy);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int y = ylo; y <= yhi; ++y) {
+      const float w = (y0[y] == sy ? 1.f - yl[y] : 0.f) + (y1[y] == sy ? yl[y] : 0.f);
+      if (w == 0.f) continue;
+      const float4* src = reinterpret_cast<const float4*>(t + ((size_t)y * sW + sx) * 8);
+      const float4 u = src[0], v = src[1];
+      a[0] = fmaf(w, u.x, a[0]); a[1] = fmaf(w, u.y, a[1]); a[2] = fmaf(w, u.z, a[2]); a[3] = fmaf(w, u.w, a[3]);
+      a[4] = fmaf(w, v.x, a[4]); a[5] = fmaf(w, v.y, a[5]); a[6] = fmaf(w, v.z, a[6]); a[7] = fmaf(w, v.w, a[7]);
+    }
+    __nv_bfloat16* dst = out_plane + (((long long)n * sg.Hp + sy + 1) * sg.Wp + sx + 1) * 8;
+    if (mode == 2) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(dst), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += r[i];
+    }
+    *reinterpret_cast<uint4*>(dst) = pack8(a);
+  }
+  // the image's share of the zero padding: its row 0 and its column 0
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < sg.Wp + sH; i += blockDim.x) {
+    const long long p = i < sg.Wp ? ((long long)n * sg.Hp) * sg.Wp + i : ((long long)n * sg.Hp + (i - sg.Wp) + 1) * sg.Wp;
+    *reinterpret_cast<uint4*>(out_plane + p * 8) = z;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // phase merge (inverse of phase_split, optionally accumulating): 4 x PF8 [N,C,H/2,W/2] -> PF8 [N,C,H,W]
 // ------------------------------------------------------------------------------------------------
@@ -532,14 +610,25 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const hrnb_pack_job* __
   }
   if (i >= total) return;
   // i = ((((nt*nch + c)*ntap + t)*KC + jj)*BN + n)*8 + e
-  long long r = i;
-  const int e = (int)(r % 8); r /= 8;
-  const int n = (int)(r % j.BN); r /= j.BN;
-  const int jj = (int)(r % j.KC); r /= j.KC;
-  const int t = (int)(r % j.ntap); r /= j.ntap;
   const int nch = (j.lcin / 8) / j.KC;
-  const int c = (int)(r % nch); r /= nch;
-  const int nt = (int)r;
+  int e, n, jj, t, c, nt;
+  if (total <= 0xffffffffLL) {     // uniform per job: 32-bit unsigned divisions (five 64-bit ones per element were the kernel's cost)
+    unsigned r = (unsigned)i;
+    e = (int)(r & 7u); r >>= 3;
+    unsigned q = r / (unsigned)j.BN; n = (int)(r - q * (unsigned)j.BN); r = q;
+    q = r / (unsigned)j.KC; jj = (int)(r - q * (unsigned)j.KC); r = q;
+    q = r / (unsigned)j.ntap; t = (int)(r - q * (unsigned)j.ntap); r = q;
+    q = r / (unsigned)nch; c = (int)(r - q * (unsigned)nch);
+    nt = (int)q;
+  } else {
+    long long r = i;
+    e = (int)(r % 8); r /= 8;
+    n = (int)(r % j.BN); r /= j.BN;
+    jj = (int)(r % j.KC); r /= j.KC;
+    t = (int)(r % j.ntap); r /= j.ntap;
+    c = (int)(r % nch); r /= nch;
+    nt = (int)r;
+  }
   const int lco = nt * j.BN + n;
   const int lci = (c * j.KC + jj) * 8 + e;
   const int co = j.transpose ? lci : lco, ci = j.transpose ? lco : lci;
@@ -821,6 +910,22 @@ extern "C" int hrnb_bilinear_up_bwd(const void* d_dst, int64_t d_dst_ps, int32_t
   if (!d_dst || !d_src || C % 8 || (mode != 1 && mode != 2)) return fail(HRNB_EINVAL, "bilinear_bwd: bad params");
   const Geo dg = make_geo(N, dH, dW), sg = make_geo(N, sH, sW);
   dim3 grid((unsigned)((sg.P + 255) / 256), C / 8);
+  const size_t sep_smem = (size_t)dH * dW * 16 + (size_t)dH * sW * 32 + (size_t)(dH + dW) * 12;
+  if (hrnb::g_debug[7] != 0 && sep_smem <= 200 * 1024) {      // staged separable kernel (see bilinear_bwd_sep_kernel)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(bilinear_bwd_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return fail_cuda(e, "bilinear_bwd: cudaFuncSetAttribute");
+      attr_set[dev] = true;
+    }
+    bilinear_bwd_sep_kernel<<<dim3((unsigned)N, C / 8), 256, sep_smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)d_dst, d_dst_ps, dg, (__nv_bfloat16*)d_src, d_src_ps, sg, align_corners, mode);
+    count_launch();
+    return check_launch("bilinear_bwd_sep_kernel");
+  }
   bilinear_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_dst, d_dst_ps, dg,
                                                                (__nv_bfloat16*)d_src, d_src_ps, sg, align_corners, mode);
   count_launch();
