@@ -137,6 +137,7 @@ _SIGS = {
     "hrnb_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "hrnb_adam_tick": (C.c_int, [_vp, _vp, _vp]),
     "hrnb_grad_to_natural": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "hrnb_triangulate_dlt": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "hrnb_last_error": (C.c_char_p, []),
     "hrnb_abi_version": (C.c_int, []),
     "hrnb_launch_count": (_i64, []),

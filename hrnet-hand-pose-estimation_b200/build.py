@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhrnb.so")
 STAMP = os.path.join(HERE, ".libhrnb.stamp")
-SOURCES = ["api.cu", "conv_tc.cu", "wgrad_tc.cu", "elementwise.cu", "train_ops.cu", "decode_loss.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "wgrad_tc.cu", "elementwise.cu", "train_ops.cu", "decode_loss.cu", "triangulate.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",

@@ -345,6 +345,15 @@ int hrnb_adam_tick(float* hyper_dev, int64_t* step_dev, void* stream);
 int hrnb_grad_to_natural(const float* grads, float* out, const hrnb_param_seg* segs_dev, const int32_t* block_seg_dev,
                          int32_t nblocks, void* stream);
 
+/* ---- algebraic (DLT) triangulation: SURVEY §8 row (f), staged in round 1 ------------------------- */
+/* Replaces the per-joint loop of AlgebraicTriangulationNet.forward (lib/models/triangulation.py:258-261) over
+ * DLT_sii_pytorch (lib/utils/misc.py:64-97) + homogeneous_to_euclidean (lib/utils/misc.py:28-35) with one launch.
+ * points [B][V][J][2] image coordinates, proj [B][V][3][4] projection matrices, bk0 [J][B][4] unit start vectors of the
+ * shifted inverse iteration (the reference draws torch.rand(B,4,1) per joint on the host and normalises it),
+ * out [B][J][3] euclidean 3-D joints; all fp32 device pointers. V >= 2, iterations >= 1 (reference: 2). */
+int hrnb_triangulate_dlt(const float* points, const float* proj, const float* bk0, int32_t B, int32_t V, int32_t J,
+                         int32_t iterations, float* out, void* stream);
+
 /* ---- misc --------------------------------------------------------------------------------------- */
 const char* hrnb_last_error(void);
 int hrnb_abi_version(void);

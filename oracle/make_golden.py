@@ -238,7 +238,37 @@ def train_fixture(name, yaml_rel, variant, B=2, H=256, W=256, trainable_temp=Fal
     print(name, "ok; oracle train step == reference; worst grad rel err %.2e; losses" % worst, rec["losses"])
 
 
+def triangulation_fixture():
+    """the UNMODIFIED lib/utils/misc.py DLT_sii_pytorch, called per joint exactly like
+    lib/models/triangulation.py:258-261, with the removed torch.solve(b, A) mapped onto torch.linalg.solve(A, b)."""
+    from oracle import triangulation_oracle as T
+    ref_shim.install()
+    import utils.misc as M
+    torch.solve = lambda b, A: (torch.linalg.solve(A, b), None)     # the only shim: argument order of the removed API
+    rec = {}
+    for name, (B, V, J, seed, noise) in {"mhp4": (6, 4, 21, 11, 1.5), "two_views": (3, 2, 21, 12, 0.5),
+                                         "eight_views_j20": (2, 8, 20, 13, 3.0)}.items():
+        P = fixtures.cameras(B, V, seed=seed)
+        X, uv = fixtures.multiview_joints(P, J, seed=seed + 100, noise_px=noise)
+        torch.manual_seed(seed)
+        ref = torch.cat([M.DLT_sii_pytorch(uv[:, :, k].clone(), P.clone()).unsqueeze(1) for k in range(J)], dim=1)
+        bk0 = T.start_vectors(B, J, seed)
+        ours = T.triangulate_joints(uv.numpy(), P.numpy(), bk0)
+        err = np.abs(ours - ref.numpy()).max() / np.abs(ref.numpy()).max()
+        assert err < 2e-5, (name, err)
+        svd = torch.stack([M.triangulate_from_multiple_views_svd(P.clone(), uv[:, :, k].clone()) for k in range(J)], dim=1)
+        assert np.abs(T.svd_triangulation(uv[:, :, 0].numpy(), P.numpy()) - svd[:, 0].numpy()).max() < 1e-2
+        rec.update({name + "/proj": P.numpy(), name + "/points": uv.numpy(), name + "/bk0": bk0, name + "/seed": np.int64(seed),
+                    name + "/ref": ref.numpy(), name + "/svd": svd.numpy(), name + "/gt": X.numpy()})
+        print("triangulation", name, "oracle == reference (rel %.1e); |sii - svd| max %.2e; |sii - gt| max %.2f"
+              % (err, np.abs(ref.numpy() - svd.numpy()).max(), np.abs(ref.numpy() - X.numpy()).max()))
+    np.savez_compressed(os.path.join(GOLD, "triangulation.npz"), **rec)
+
+
 if __name__ == "__main__":
+    if "--triangulation-only" in sys.argv:
+        triangulation_fixture()
+        sys.exit(0)
     if "--train-only" in sys.argv:
         train_fixture("train_w32_softmax", "experiments/RHD/RHD_HRNet_w32_softmax_hm-pose2dloss_v1.yaml", "softmax",
                       trainable_temp=True)
@@ -257,3 +287,4 @@ if __name__ == "__main__":
                 "softmax", H=128, W=96, B=2)
     train_fixture("train_w32_softmax", Y, "softmax", trainable_temp=True)
     train_fixture("train_w32_raw", YR, "raw")
+    triangulation_fixture()

@@ -93,3 +93,19 @@ def test_product_synthetic_data_equals_the_test_fixtures():
     assert torch.equal(synthetic.images(2, 64, 96, seed=5), fixtures.images(2, 64, 96, seed=5))
     for a, b in zip(synthetic.targets(3, 21, 16, 24, seed=7), fixtures.targets(3, 21, 16, 24, seed=7)):
         assert torch.equal(a, b)
+
+
+def test_triangulation_mirror_host_logic():
+    """row (f) drop-in: same start-vector stream as the reference's per-joint loop, no CPU fallback"""
+    import numpy as np
+    import pytest
+    import torch
+    from hrnet_b200.utils import misc
+    from oracle import triangulation_oracle as T
+    torch.manual_seed(5)
+    mine = misc._start_vectors(3, 4, "cpu").numpy()
+    assert np.array_equal(mine, T.start_vectors(3, 4, 5))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        misc.DLT_sii_pytorch(torch.zeros(2, 4, 2), torch.zeros(2, 4, 3, 4))
+    h = torch.tensor([[2.0, 4.0, 6.0, 2.0]])
+    assert torch.equal(misc.homogeneous_to_euclidean(h), torch.tensor([[1.0, 2.0, 3.0]]))

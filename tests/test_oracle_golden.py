@@ -154,3 +154,24 @@ def test_train_oracle_reproduces_reference_training_step(golden_dir, name, varia
     for k in ("bn1", "stage3.0.branches.1.2.bn1", "last_layer.1"):
         for s in (".running_mean", ".running_var"):
             assert np.allclose(o["state"][k + s].numpy(), g["after/" + k + s], rtol=1e-4, atol=1e-6), k + s
+
+
+def test_triangulation_oracle_matches_reference_golden(golden_dir):
+    """oracle/triangulation_oracle.py against the values of the unmodified reference DLT_sii_pytorch
+    (lib/utils/misc.py:64-97, called per joint like lib/models/triangulation.py:258-261) stored by oracle/make_golden.py;
+    the start vectors are re-drawn from the recorded seed; edge cases: two views, 8 views, J = 20."""
+    from oracle import triangulation_oracle as T
+    g = _load(golden_dir, "triangulation.npz")
+    for case in ("mhp4", "two_views", "eight_views_j20"):
+        P, uv, ref = g[case + "/proj"], g[case + "/points"], g[case + "/ref"]
+        B, V, J, _ = uv.shape
+        bk0 = T.start_vectors(B, J, int(g[case + "/seed"]))
+        assert np.array_equal(bk0, g[case + "/bk0"])
+        assert np.allclose(np.linalg.norm(bk0, axis=-1), 1.0, atol=1e-6)
+        out = T.triangulate_joints(uv, P, bk0)
+        scale = np.abs(ref).max()
+        assert np.abs(out - ref).max() < 2e-5 * scale, case
+        # two inverse iterations land on the exact smallest singular vector up to fp32 conditioning, and near the truth
+        svd = np.stack([T.svd_triangulation(uv[:, :, k], P) for k in range(J)], axis=1)
+        assert np.abs(svd - g[case + "/svd"]).max() < 2e-2
+        assert np.abs(out - svd).max() < 0.5 and np.abs(out - g[case + "/gt"]).max() < 10.0

@@ -53,3 +53,29 @@ def test_separable_bilinear_backward(align, N, C, sh, sw, dh, dw):
     assert (ds.to_nchw() - src.grad).abs().max().item() < 1e-2 * scale
     assert (ds.to_nchw() - ref_kernel.to_nchw()).abs().max().item() < 1e-2 * scale
     assert (acc.to_nchw() - (src.grad + prev)).abs().max().item() < 1.5e-2 * max(scale, prev.abs().max().item())
+
+
+@staged
+@pytest.mark.parametrize("case", ["mhp4", "two_views", "eight_views_j20"])
+def test_dlt_triangulation_matches_reference_golden(case):
+    """hrnb_triangulate_dlt (one launch for all joints) against the values of the UNMODIFIED reference DLT_sii_pytorch called
+    per joint (tests/golden/triangulation.npz, seeded start vectors) and against the oracle; fp32 tolerance 1e-4 of the
+    coordinate scale (the numpy emulation of the kernel's arithmetic sits at 4e-6)."""
+    import os
+    import numpy as np
+    from hrnet_b200.utils import misc
+    from oracle import triangulation_oracle as T
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "triangulation.npz"))
+    P, uv, bk0, ref = (torch.from_numpy(g[case + "/" + k]).cuda() for k in ("proj", "points", "bk0", "ref"))
+    out = misc.triangulate_joints(uv, P, start_vectors=bk0)
+    scale = ref.abs().max().item()
+    assert (out - ref).abs().max().item() < 1e-4 * scale
+    ours = T.triangulate_joints(uv.cpu().numpy(), P.cpu().numpy(), bk0.cpu().numpy())
+    assert np.abs(out.cpu().numpy() - ours).max() < 1e-4 * scale
+    # the drop-in entry points draw the reference's random start vectors themselves
+    torch.manual_seed(int(g[case + "/seed"]))
+    again = misc.triangulate_joints(uv, P)
+    assert (again - ref).abs().max().item() < 1e-4 * scale
+    torch.manual_seed(int(g[case + "/seed"]))
+    one = misc.DLT_sii_pytorch(uv[:, :, 0], P)
+    assert (one - ref[:, 0]).abs().max().item() < 1e-4 * scale
