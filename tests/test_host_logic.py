@@ -109,3 +109,23 @@ def test_triangulation_mirror_host_logic():
         misc.DLT_sii_pytorch(torch.zeros(2, 4, 2), torch.zeros(2, 4, 3, 4))
     h = torch.tensor([[2.0, 4.0, 6.0, 2.0]])
     assert torch.equal(misc.homogeneous_to_euclidean(h), torch.tensor([[1.0, 2.0, 3.0]]))
+
+
+def test_fused_statistics_eligibility_rule():
+    """which conv launches may also reduce the BatchNorm statistics (include/hrnb.h stats_sums): one N tile of 16 / 32 / 64
+    channels on the flat-shift PF8 path, no residual, no ReLU"""
+    from hrnet_b200 import _lib
+    from hrnet_b200.ops import stats_eligible
+
+    def params(cout, bn, flags=0, res=None):
+        p = _lib.ConvParams()
+        p.cout, p.BN, p.flags, p.res = cout, bn, flags, res
+        return p
+    assert stats_eligible(params(32, 32)) and stats_eligible(params(64, 64)) and stats_eligible(params(16, 16))
+    assert stats_eligible(params(64, 64, _lib.HRNB_CONV_IN_PHASES))          # stride 2 over phase-split input: flat-shift
+    assert not stats_eligible(params(64, 32))                                 # two N tiles
+    assert not stats_eligible(params(128, 128)) and not stats_eligible(params(48, 48))
+    assert not stats_eligible(params(32, 32, _lib.HRNB_CONV_RELU))
+    assert not stats_eligible(params(32, 32, _lib.HRNB_CONV_GATHER))
+    assert not stats_eligible(params(32, 32, _lib.HRNB_CONV_OUT_NCHW))
+    assert not stats_eligible(params(32, 32, 0, res=0x1000))
