@@ -56,6 +56,9 @@ def arch_from_cfg(cfg):
         c = list(_get(st, "NUM_CHANNELS"))
         if c != ch4[:len(c)]:
             raise ValueError("stage channel tables must be prefixes of STAGE4.NUM_CHANNELS")
+    if any(int(c) % 16 for c in ch4):
+        raise ValueError("NUM_CHANNELS %s: the sm_100a kernels need every branch width to be a multiple of 16 (K step of the "
+                         "bf16 tensor-core instruction); HRNet-W32 / W48 / W64 qualify, W18 (18/36/72/144) does not" % (ch4,))
     try:
         nj = _get(model, "NUM_JOINTS")
     except (KeyError, AttributeError):

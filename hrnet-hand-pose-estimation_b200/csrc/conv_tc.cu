@@ -28,6 +28,7 @@
 //   warps 2..5  : epilogue  (tcgen05.ld -> +bias -> +residual -> ReLU -> bf16 -> coalesced 16 B stores);
 //                 the residual of the next 16-channel group is prefetched while the current one is finished
 //   warps 6..9  : (GATHER only) cp.async gather producers, one thread per A row
+#include <atomic>
 #include "ptx.cuh"
 #include "common.h"
 
@@ -792,8 +793,10 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (smem < 0) return (int)smem;
   const bool gather = (p->flags & HRNB_CONV_GATHER) != 0;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[64][28] = {};
-  static int sm_count[64] = {};
+  // per-device launch state: written once per (device, variant), read on every launch, possibly from one host thread per
+  // GPU (nn.DataParallel calls forward that way, tools/train.py:254) -> atomics; cudaFuncSetAttribute itself is idempotent
+  static std::atomic<unsigned char> attr_set[64][28] = {};
+  static std::atomic<int> sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
@@ -815,20 +818,20 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
 #undef HRNB_PICK
   if (!fn) return fail(HRNB_EINVAL, "conv: KC must be one of 2, 4, 6, 8, 12, 16, 32");
   const int variant = ksi * 4 + (gather ? 2 : (nchw_out ? 1 : (stats ? 3 : 0)));
-  if (!attr_set[dev][variant]) {
+  if (!attr_set[dev][variant].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "conv: cudaFuncSetAttribute");
-    attr_set[dev][variant] = true;
+    attr_set[dev][variant].store(1, std::memory_order_release);
   }
-  if (sm_count[dev] == 0) {
-    int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    sm_count[dev] = n;
+  int nsm = sm_count[dev].load(std::memory_order_relaxed);
+  if (nsm == 0) {
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
+    sm_count[dev].store(nsm, std::memory_order_relaxed);
   }
   // persistent grid: one or two CTAs per SM (two when shared memory and TMEM columns allow it)
   int per_sm = (kCtasPerSm == 2 && !gather && smem <= 110 * 1024 && 2 * k.tmem_cols <= 512) ? 2 : 1;
   if (g_debug[1] > 0) per_sm = g_debug[1] == 1 ? 1 : per_sm;   // debug: force one CTA per SM
-  int grid = sm_count[dev] * per_sm;
+  int grid = nsm * per_sm;
   if (grid > k.num_tiles) grid = k.num_tiles;
   if (stats && grid > kStatsMaxCtas) return fail(HRNB_EINVAL, "conv: fused statistics support at most 320 CTAs");
   cudaLaunchConfig_t cfg = {};

@@ -18,6 +18,7 @@
 // consecutive floats of the [tap][cin][cout] gradient layout.
 //
 // Warp roles: warp 0 bulk-copy producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 epilogue.
+#include <atomic>
 #include "ptx.cuh"
 #include "common.h"
 
@@ -402,14 +403,14 @@ extern "C" int hrnb_wgrad(const hrnb_wgrad_params* p, void* stream) {
 }
 
 static int launch_wgrad(const WgradK& k, int grid, long long smem, cudaStream_t stream) {
-  static bool attr_set[64] = {};
+  static std::atomic<unsigned char> attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
-  if (!attr_set[dev]) {
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "wgrad: cudaFuncSetAttribute");
-    attr_set[dev] = true;
+    attr_set[dev].store(1, std::memory_order_release);
   }
   if (smem < kTmemExclusiveSmem && hrnb::g_debug[6] == 0) smem = kTmemExclusiveSmem;   // one TMEM-holding CTA per SM (common.h)
   launch_pdl(wgrad_tc_kernel, dim3((unsigned)grid), dim3(kWgThreads), (size_t)smem, (cudaStream_t)stream, k);

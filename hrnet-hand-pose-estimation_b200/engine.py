@@ -25,14 +25,17 @@ from ._lib import FuseParams
 EPS = 1e-5
 
 
-def _fold(sd, bn_key, conv_bias=None):
-    g, b = sd[bn_key + ".weight"].float(), sd[bn_key + ".bias"].float()
-    m, v = sd[bn_key + ".running_mean"].float(), sd[bn_key + ".running_var"].float()
+def _fold(sd, bn_key, conv_bias=None, device=None):
+    """eval-mode BatchNorm as per-channel (scale, shift), computed on the HOST in fp32 (a few hundred floats per layer) and
+    uploaded: the device only ever runs the library's own kernels while an engine is built (the pack kernel folds `scale`
+    into the bf16 weights, `shift` becomes the epilogue bias)"""
+    g, b = sd[bn_key + ".weight"].float().cpu(), sd[bn_key + ".bias"].float().cpu()
+    m, v = sd[bn_key + ".running_mean"].float().cpu(), sd[bn_key + ".running_var"].float().cpu()
     scale = g / torch.sqrt(v + EPS)
     shift = b - m * scale
     if conv_bias is not None:
-        shift = shift + conv_bias.float() * scale
-    return scale, shift
+        shift = shift + conv_bias.float().cpu() * scale
+    return scale.to(device), shift.to(device)
 
 
 class _Step:
@@ -347,13 +350,13 @@ class HRNetEngine:
             w = sd[k + ".weight"].float().contiguous()
             cb = sd.get(k + ".bias")
             if k in bn_after:
-                scale, shift = _fold(sd, bn_after[k], cb)
+                scale, shift = _fold(sd, bn_after[k], cb, w.device)
             else:
                 scale, shift = None, (cb.float() if cb is not None else None)
             if k == "conv1":          # 3x3x3 stem conv == 1x1 conv over the 27(+5 zero)-channel im2col slab
-                w32 = torch.zeros((64, 32, 1, 1), dtype=torch.float32, device=w.device)
-                w32[:, :27, 0, 0] = w.reshape(64, 27)
-                self.layers[k] = ConvLayer(w32, scale, shift, stride=1, relu=True)
+                w32 = torch.zeros((64, 32, 1, 1), dtype=torch.float32)
+                w32[:, :27, 0, 0] = w.reshape(64, 27).cpu()
+                self.layers[k] = ConvLayer(w32.to(w.device), scale, shift, stride=1, relu=True)
                 continue
             leaf = k.rsplit(".", 1)[-1]
             # residual convs (block conv2 / bottleneck conv3) apply ReLU after the add -> flag set

@@ -112,3 +112,59 @@ class FlatParams:
         _lib.check(_lib.lib().hrnb_grad_to_natural(self.grads.data_ptr(), nat.data_ptr(), self.segs_dev.data_ptr(),
                                                    self.block_seg_dev.data_ptr(), self.nblocks, _lib.stream_ptr()))
         return [nat[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.p_offs)]
+
+    # ---- checkpointing (tools/train.py:285,375-383: checkpoint['optimizer'] = optimizer.state_dict()) -----------------
+    def _trainable(self):
+        """indices of the parameters a reference optimizer would hold: filter(requires_grad, model.parameters())
+        (lib/utils/utils.py:71-92), in named_parameters() order"""
+        return [i for i, p in enumerate(self.params) if p.requires_grad]
+
+    def state_dict(self):
+        """torch.optim.Adam-compatible state dict (index-keyed `state`, one param group): a checkpoint written by the fused
+        optimizer resumes under the reference's torch.optim.Adam and vice versa."""
+        lr, b1, b2, eps, wd = (float(x) for x in self.hyper[:5].cpu())
+        step = int(self.step.item())
+        idx = self._trainable()
+        state = {}
+        if step > 0:
+            for j, i in enumerate(idx):
+                off, n, shape = self.p_offs[i], self.params[i].numel(), self.params[i].shape
+                state[j] = {"step": torch.tensor(float(step)),
+                            "exp_avg": self.m[off:off + n].view(shape).clone(),
+                            "exp_avg_sq": self.v[off:off + n].view(shape).clone()}
+        group = {"lr": lr, "betas": (b1, b2), "eps": eps, "weight_decay": wd, "amsgrad": False, "maximize": False,
+                 "params": list(range(len(idx)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """inverse of state_dict(); accepts the optimizer state of a reference checkpoint (same parameter order)."""
+        groups = sd["param_groups"]
+        if len(groups) != 1:
+            raise ValueError("the fused Adam holds one parameter group (the reference builds one, lib/utils/utils.py:71-92)")
+        g = groups[0]
+        idx = self._trainable()
+        if len(g["params"]) != len(idx):
+            raise ValueError("optimizer state holds %d parameters, the network has %d trainable ones" % (len(g["params"]), len(idx)))
+        if g.get("amsgrad", False):
+            raise ValueError("amsgrad is not supported by the fused Adam")
+        self.hyper[0], self.hyper[1], self.hyper[2] = float(g["lr"]), float(g["betas"][0]), float(g["betas"][1])
+        self.hyper[3], self.hyper[4] = float(g["eps"]), float(g["weight_decay"])
+        steps = set()
+        self.m.zero_()
+        self.v.zero_()
+        for j, i in enumerate(idx):
+            st = sd["state"].get(g["params"][j])
+            if st is None:
+                continue
+            off, n = self.p_offs[i], self.params[i].numel()
+            if st["exp_avg"].numel() != n:
+                raise ValueError("optimizer state of parameter %d has %d elements, expected %d" % (j, st["exp_avg"].numel(), n))
+            self.m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ (%s): the fused Adam keeps one step counter" % sorted(steps))
+        step = steps.pop() if steps else 0
+        self.step.fill_(step)
+        b1, b2 = float(g["betas"][0]), float(g["betas"][1])
+        self.hyper[5], self.hyper[6] = 1.0 - b1 ** step if step else 1.0, 1.0 - b2 ** step if step else 1.0

@@ -49,6 +49,12 @@ def _materialise(root, specs):
         else:
             leaf = nn.BatchNorm2d(sp.ch, momentum=BN_MOMENTUM)
         node.add_module(parts[-1], leaf)
+    # The reference builds `downsample` BEFORE the Bottleneck (pose_hrnet.py:399-410: same RNG draw order as the spec table)
+    # but the block registers it LAST (pose_hrnet.py:66-76): named_parameters() / modules() order - what an index-keyed
+    # optimizer.state_dict() and init_weights' walk depend on - must follow the registration order.
+    for blk in root._modules["layer1"]._modules.values():
+        if "downsample" in blk._modules:
+            blk._modules["downsample"] = blk._modules.pop("downsample")      # re-insert = move to the end
 
 
 class _TrainForward(torch.autograd.Function):
@@ -62,7 +68,7 @@ class _TrainForward(torch.autograd.Function):
         eng = model.train_engine()
         want = model.return_features
         p = eng.forward(x, want_features=want)
-        ctx.model, ctx.plan = model, p
+        ctx.model, ctx.plan, ctx.generation = model, p, p.generation
         ctx.set_materialize_grads(False)
         out = p.out["heatmap"] if model.variant == "softmax" else p.out["logits"]
         feat = p.feat.clone() if want else x.new_zeros(())
@@ -73,8 +79,14 @@ class _TrainForward(torch.autograd.Function):
     def backward(ctx, d_out, d_feat):
         model, p = ctx.model, ctx.plan
         eng = model.train_engine()
-        if d_feat is not None and bool((d_feat != 0).any()):
-            raise NotImplementedError("gradients through the inter_feat output are not supported by the B200 training engine")
+        if p.generation != ctx.generation:
+            # one TrainPlan per (batch, H, W) holds the activations of the LAST train-mode forward at that shape; a second
+            # forward (siamese / multi-view / consistency losses, or a no_grad train-mode forward in between) overwrote them
+            raise RuntimeError(
+                "the B200 training engine keeps one set of saved activations per input shape: this backward belongs to "
+                "forward #%d of that shape, but forward #%d has run since and overwrote them. Run backward() before the "
+                "next train-mode forward of the same shape (or concatenate the inputs into one batch); see INTEGRATION.md."
+                % (ctx.generation, p.generation))
         if d_out is None:
             d_out = torch.zeros_like(p.out["logits"])
         with torch.cuda.device(eng.device):
@@ -111,6 +123,7 @@ class PoseHighResolutionNet(nn.Module):
         self._tensors = None
         self._train_engine = None
         self._train_key = None
+        self._train_epoch = 0         # bumped by the training engine on every train-mode forward / step (stale-fold guard)
         self.return_features = True   # set False to skip materialising the NCHW fp32 feature output
         self.static_outputs = False   # True: return the engine's static buffers (overwritten by the next call)
 
@@ -156,7 +169,7 @@ class PoseHighResolutionNet(nn.Module):
     def _param_versions(self):
         if self._tensors is None:
             self._tensors = list(self.parameters()) + list(self.buffers())
-        return sum(t._version for t in self._tensors), len(self._tensors)
+        return sum(t._version for t in self._tensors), len(self._tensors), self._train_epoch
 
     def _weights_version(self):
         """version counter of the parameters only (buffers are updated by the training kernels themselves)"""

@@ -41,18 +41,27 @@ def gather_joints(local, n_total, group=None):
 
 
 class GradAllReduce:
-    """Sum-all-reduce of the flat gradient buffer in `n_buckets` contiguous buckets (bucket boundaries aligned to 128
-    elements).  With one bucket this is a single collective per step; more buckets let the caller overlap the exchange
-    of already finished buckets with the rest of the backward pass.  `mean_scale` is what FlatParams.set_grad_scale
-    must be given so that the optimizer sees the DDP-style mean."""
+    """Sum-all-reduce of the flat gradient buffer.  `mean_scale` is what FlatParams.set_grad_scale must be given so that
+    the optimizer sees the DDP-style mean.
 
-    def __init__(self, n_elems, n_buckets=1, group=None):
+    Two forms:
+      * `ar(flat_grads)`: the whole buffer in `n_buckets` contiguous buckets on the current stream (host logic / CPU tests);
+      * overlapped (CUDA, `device` given): `launch(flat_grads, lo, hi)` all-reduces one bucket on a communication stream
+        that first waits for everything queued on the current stream so far, `finish()` makes the current stream wait for
+        all launched buckets.  TrainEngine.train_step calls `launch` after each backward segment (head + stage 4, stage 3,
+        the rest), so every bucket but the last small one travels under the remaining backward kernels."""
+
+    def __init__(self, n_elems, n_buckets=1, group=None, device=None):
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         n_buckets = max(1, int(n_buckets))
         step = (n_elems + n_buckets - 1) // n_buckets
         step = (step + 127) // 128 * 128
         self.bounds = [(lo, min(n_elems, lo + step)) for lo in range(0, n_elems, step)]
+        self.overlap = device is not None and torch.device(device).type == "cuda"
+        self.comm = torch.cuda.Stream(device=device) if self.overlap else None
+        self.device = device
+        self.launched = []
 
     @property
     def mean_scale(self):
@@ -64,3 +73,17 @@ class GradAllReduce:
         for lo, hi in self.bounds:
             dist.all_reduce(flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         return flat_grads
+
+    def launch(self, flat_grads, lo, hi):
+        self.launched.append((lo, hi))
+        if self.world == 1 or hi <= lo:
+            return
+        main = torch.cuda.current_stream(self.device)
+        self.comm.wait_stream(main)
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(flat_grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self):
+        self.launched = []
+        if self.world > 1:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)

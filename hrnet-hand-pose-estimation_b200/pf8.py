@@ -14,14 +14,41 @@ from . import _lib
 _CANARY = int(os.environ.get("HRNB_CANARY", "0"))    # debug: NaN margins (elements) around every PF8 allocation
 
 
+class _Arena:
+    """Zero-filled device memory handed out in 256-byte-aligned slices of large chunks: a launch plan owns several hundred
+    PF8 tensors, and one fill kernel per tensor made plan construction a stream of ATen launches.  A chunk is released by
+    the caching allocator when the last tensor carved from it dies (slices keep the chunk's storage alive)."""
+    CHUNK = 256 << 20
+
+    def __init__(self):
+        self.cur = {}        # device -> [chunk tensor (uint8), bytes used]
+
+    def take(self, nbytes, device):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        nbytes = (nbytes + 255) // 256 * 256
+        if nbytes >= self.CHUNK // 4:
+            return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        slot = self.cur.get(device)
+        if slot is None or slot[1] + nbytes > slot[0].numel():
+            slot = self.cur[device] = [torch.zeros(self.CHUNK, dtype=torch.uint8, device=device), 0]
+        out = slot[0][slot[1]:slot[1] + nbytes]
+        slot[1] += nbytes
+        return out
+
+
+_ARENA = _Arena()
+
+
 def _alloc(shape, device):
-    """zero-filled bf16 buffer; with HRNB_CANARY=n it sits between two n-element NaN margins so that any kernel
-    reading outside a PF8 allocation produces NaNs deterministically (debug aid, tools/train_small.py)"""
-    if not _CANARY:
-        return torch.zeros(shape, dtype=torch.bfloat16, device=device)
+    """zero-filled bf16 buffer (a slice of the arena); with HRNB_CANARY=n it sits between two n-element NaN margins so that
+    any kernel reading outside a PF8 allocation produces NaNs deterministically (debug aid)"""
     n = 1
     for d in shape:
         n *= d
+    if not _CANARY:
+        return _ARENA.take(n * 2, device)[:n * 2].view(torch.bfloat16).view(shape)
     raw = torch.full((n + 2 * _CANARY,), float("nan"), dtype=torch.bfloat16, device=device)
     body = raw[_CANARY:_CANARY + n]
     body.zero_()

@@ -55,3 +55,58 @@ class StreamingPredictor:
         for s in pending:
             s["done"].synchronize()
             yield s["out"]
+
+
+class StreamingTrainer:
+    """Training over host batches: `StreamingTrainer(engine).run(batches)` takes an iterable of pinned host tuples
+    (images [B,3,H,W], gt heat maps [B,J,h,w], gt joints [B,J,2], visibility [B,J]) and yields, per step and in order,
+    the losses [total, heat-map, pose2d] as a host tensor.  What lib/core/function.py:24-162 (train_helper) does per
+    iteration - .cuda() the batch, forward, losses, backward, optimizer step, .item() the losses - with the copies taken
+    off the critical path: two device input slots filled by a copy stream (the H2D of batch i+1 runs under the network of
+    batch i) and the losses of step i read back while step i+1 is already queued (the reference's .item() per term per
+    step, function.py:1375, stalls the GPU instead).  Every step still pays its own H2D copy and its own D2H read."""
+
+    def __init__(self, engine, allreduce=None, depth=2):
+        self.engine, self.allreduce, self.depth = engine, allreduce, depth
+        self.device = engine.device
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._slots = None
+
+    def _ensure(self, host):
+        shapes = tuple(tuple(t.shape) for t in host)
+        if self._slots is None or self._slots[0]["shapes"] != shapes:
+            self._slots = [dict(shapes=shapes, dev=[torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host],
+                                out=torch.empty(3, dtype=torch.float32).pin_memory(), copied=torch.cuda.Event(),
+                                done=torch.cuda.Event(), used=False) for _ in range(self.depth)]
+
+    def run(self, batches):
+        main = torch.cuda.current_stream(self.device)
+        pending = []
+        i = 0
+        for host in batches:
+            self._ensure(host)
+            s = self._slots[i % self.depth]
+            if s["used"]:
+                if pending and pending[0] is s:          # results are handed out in order, before their slot is reused
+                    pending.pop(0)
+                    s["done"].synchronize()
+                    yield s["out"]
+                self.copy_stream.wait_event(s["done"])
+            with torch.cuda.stream(self.copy_stream):
+                for d, h in zip(s["dev"], host):
+                    d.copy_(h, non_blocking=True)
+                s["copied"].record(self.copy_stream)
+            main.wait_event(s["copied"])
+            p = self.engine.train_step(*s["dev"], allreduce=self.allreduce)
+            s["out"].copy_(p.losses, non_blocking=True)
+            s["done"].record(main)
+            s["used"] = True
+            pending.append(s)
+            if len(pending) >= self.depth:               # keep at most depth-1 steps in flight behind the consumer
+                o = pending.pop(0)
+                o["done"].synchronize()
+                yield o["out"]
+            i += 1
+        for s in pending:
+            s["done"].synchronize()
+            yield s["out"]

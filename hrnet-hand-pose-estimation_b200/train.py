@@ -59,6 +59,8 @@ class TrainPlan:
         self.x = torch.zeros((B, 3, H, W), dtype=torch.float32, device=self.dev)
         self.graphs = {}
         self.conv_out = {}      # conv key -> PF8 conv output (pre-BN) kept for the backward pass
+        self.cuts = []          # (first parameter prefix whose gradients are final, index into self.bwd): all-reduce bucket cuts
+        self.generation = 0     # bumped by every forward that overwrites the saved activations (models/_hrnet.py checks it)
         self._build()
 
     # ---- helpers ------------------------------------------------------------------------------------------
@@ -353,6 +355,9 @@ class TrainPlan:
         for s, nmod in zip((2, 3, 4), arch.modules):
             nb = s
             if s > 2:
+                # everything recorded on the tape AFTER this point (transition{s-1}, stage s, ..., head) has its parameter
+                # gradients final once the backward pass comes back here: a cut for the bucketed gradient all-reduce
+                self.tape.append(lambda tag="transition%d." % (s - 1): self.cuts.append((tag, len(self.bwd))))
                 self.on(nb - 2)
                 ph = self.split(xs[-1])
                 self.fwait(nb - 1, nb - 2)
@@ -565,8 +570,22 @@ class TrainPlan:
         for fn in self.loss_steps:
             fn()
 
-    def run_backward(self):
-        self._run(self.bwd)
+    def run_backward(self, lo=0, hi=None):
+        self._run(self.bwd[lo:hi])
+
+    def ar_segments(self):
+        """backward list split at the all-reduce cuts -> [(bwd lo, bwd hi, grad lo, grad hi)]: once bwd[lo:hi] has run, the
+        gradient elements [grad lo, grad hi) of the flat buffer are final (the buffer is in named_parameters() order: stem ...
+        stage4, head; the backward pass walks it from the end)"""
+        flat, names = self.eng.flat, self.eng.param_names
+        out, prev_b, prev_g = [], 0, flat.n_grads
+        for tag, bidx in self.cuts:                 # in backward order: "transition3." first, then "transition2."
+            first = min(i for i, n in enumerate(names) if n.startswith(tag))
+            g0 = flat.g_offs[first]
+            out.append((prev_b, bidx, g0, prev_g))
+            prev_b, prev_g = bidx, g0
+        out.append((prev_b, len(self.bwd), 0, prev_g))
+        return out
 
     def _graphed(self, name, body):
         if not self.eng.use_graph:
@@ -576,7 +595,8 @@ class TrainPlan:
             body()                       # warm-up outside capture (function attributes, lazy module loads)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: the NCCL watchdog thread may poll events of an in-flight gradient all-reduce during the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 body()
             self.graphs[name] = g
             return                       # the warm-up run already produced this step's results ... replay for state parity
@@ -623,6 +643,7 @@ class TrainEngine:
         model, dev = self.model, self.device
         named = list(model.named_parameters())
         index = {n: i for i, (n, _) in enumerate(named)}
+        self.param_names = [n for n, _ in named]
         specs = A.layer_specs(self.arch)
         convs = [sp for sp in specs if isinstance(sp, A.Conv)]
         conv_meta = {}
@@ -724,12 +745,19 @@ class TrainEngine:
             d["dgrad"] = self.dgrad_s2(key, wo + 1)
 
     # ---- public steps ---------------------------------------------------------------------------------------
+    def _touch_model(self):
+        """every train-mode forward rewrites the BatchNorm running statistics through raw pointers (and graph replays do not
+        bump tensor versions): tell the module so that a following model.eval() forward re-folds its weights"""
+        self.model._train_epoch = getattr(self.model, "_train_epoch", 0) + 1
+
     def repack(self):
         self.repacker.run()
 
     def forward(self, x, want_features=False):
         B, _, H, W = x.shape
         p = self.plan(B, H, W)
+        p.generation += 1
+        self._touch_model()
         p.x.copy_(x, non_blocking=True)
         p._graphed("fwd%d" % int(want_features), lambda: p.run_forward(want_features))
         return p
@@ -743,6 +771,8 @@ class TrainEngine:
         Returns the plan (losses in plan.losses = [total, heat-map, pose2d])."""
         B, _, H, W = x.shape
         p = self.plan(B, H, W)
+        p.generation += 1
+        self._touch_model()
         p.x.copy_(x, non_blocking=True)
         p.gt_heat.copy_(gt_heat, non_blocking=True)
         if gt_xy is not None:
@@ -750,13 +780,28 @@ class TrainEngine:
         if vis is not None:
             p.vis.copy_(vis, non_blocking=True)
 
-        def body():
-            p.run_forward(False)
-            p.run_loss()
-            p.run_backward()
-        p._graphed("step", body)
-        if allreduce is not None:
-            allreduce(self.flat.grads)
+        if allreduce is not None and getattr(allreduce, "overlap", False):
+            # data-parallel step: the backward pass is replayed in segments (head + stage 4 | stage 3 | the rest); the
+            # gradient bucket a segment completes is all-reduced on the communication stream while the next segment runs
+            # (what DDP's bucketed hooks do for the reference, tools/train.py:239-244)
+            segs = p.ar_segments()
+            for si, (blo, bhi, glo, ghi) in enumerate(segs):
+                def body(si=si, blo=blo, bhi=bhi):
+                    if si == 0:
+                        p.run_forward(False)
+                        p.run_loss()
+                    p.run_backward(blo, bhi)
+                p._graphed("seg%d" % si, body)
+                allreduce.launch(self.flat.grads, glo, ghi)
+            allreduce.finish()
+        else:
+            def body():
+                p.run_forward(False)
+                p.run_loss()
+                p.run_backward()
+            p._graphed("step", body)
+            if allreduce is not None:
+                allreduce(self.flat.grads)
         if optimizer_step:
             def opt():
                 self.flat.adam_step()

@@ -30,6 +30,21 @@ def _is_bn_affine(k, sd):
     return (stem + ".running_mean") in sd
 
 
+def contract_state_dict(sd, factor=0.05):
+    """Scale the gamma of every residual-closing BatchNorm (BasicBlock bn2, Bottleneck bn3) and of every fuse-layer
+    BatchNorm by `factor`: each block becomes x + small * f(x), so the random-init network no longer amplifies a 0.2 %
+    bf16 rounding of its activations into O(1) gradient changes (deep BatchNorm networks at initialisation do; see
+    DESIGN.md §2).  Gives a WELL-CONDITIONED training case that can be compared with the fp32 reference directly."""
+    import re
+    for k in sorted(sd):
+        if not k.endswith(".weight") or sd[k].dim() != 1:
+            continue
+        if re.search(r"branches\.\d+\.\d+\.bn2\.weight$", k) or re.search(r"layer1\.\d+\.bn3\.weight$", k) or \
+                (".fuse_layers." in k and k.endswith(".1.weight")):
+            sd[k].mul_(factor)
+    return sd
+
+
 def sharpen_head(sd, factor=50.0):
     """Second weight set with peaky heat maps (default-init logits are nearly flat)."""
     sd["last_layer.3.weight"].mul_(factor)

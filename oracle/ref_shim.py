@@ -19,7 +19,21 @@ import numpy as np
 import torch
 import yaml
 
-REF_ROOT = os.environ.get("HRNB_REFERENCE_ROOT", "/root/reference")
+VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py (git-ignored copy)
+
+
+def _resolve_root():
+    """HRNB_REFERENCE_ROOT, else /root/reference (authoring container), else the verbatim copy oracle/build_ref.py made
+    (the only one present on the GPU box; used by bench.py's reference arm)"""
+    env = os.environ.get("HRNB_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/lib/models"):
+        return "/root/reference"
+    return VENDORED
+
+
+REF_ROOT = _resolve_root()
 
 
 def available():

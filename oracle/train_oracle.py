@@ -21,7 +21,7 @@ def _is_param(k, v):
 
 
 def train_step(sd, x, gt_heat, gt_xy, vis, arch, variant, f_hm=1.0, f_p2d=0.1, trainable_temp=False, lr=1e-3,
-               weight_decay=1e-4, adam=True, conv_values=None):
+               weight_decay=1e-4, adam=True, conv_values=None, opt_state=None):
     """sd: reference-layout state_dict (tensors are cloned).  Returns dict(losses=(total, hm, p2d), grads={key: tensor},
     state={key: tensor after the step (parameters after one Adam step, updated running statistics)}, logits=...).
 
@@ -60,11 +60,18 @@ def train_step(sd, x, gt_heat, gt_xy, vis, arch, variant, f_hm=1.0, f_p2d=0.1, t
     leaves = {k: t for k, t in st.items() if torch.is_tensor(t) and t.requires_grad}
     grads = dict(zip(leaves, torch.autograd.grad(total, list(leaves.values()), allow_unused=True)))
     grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in grads.items()}
+    new_opt_state = None
     if adam:
         opt = torch.optim.Adam(list(leaves.values()), lr=lr, weight_decay=weight_decay)
+        if opt_state is not None:           # multi-step trajectories: carry the Adam moments / step count over
+            opt.load_state_dict(opt_state)
         for k, t in leaves.items():
             t.grad = grads[k].clone()
         opt.step()
+        new_opt_state = opt.state_dict()
     state = {k: t.detach() for k, t in st.items()}
-    return {"losses": (float(total), float(l_hm), float(l_p2d)), "grads": grads, "state": state,
-            "logits": logits.detach()}
+    for k in list(state):                   # nn.BatchNorm2d(train) also counts its batches
+        if k.endswith("num_batches_tracked"):
+            state[k] = state[k] + 1
+    return {"losses": (float(total.detach()), float(l_hm.detach()), float(l_p2d.detach())), "grads": grads, "state": state,
+            "logits": logits.detach(), "opt_state": new_opt_state}

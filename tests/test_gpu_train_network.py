@@ -250,3 +250,150 @@ def test_multi_stream_plan_equals_single_stream():
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     for a, b in zip(res[0][2], res[1][2]):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(a.abs().max()) + 1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# WELL-CONDITIONED training cases: compared with the fp32 reference DIRECTLY (no linearisation).
+# The golden files come from the unmodified reference (oracle/make_golden.py train_conditioned_fixture):
+#   *_contractive : residual-closing / fuse BatchNorm gammas x 0.05 (fixtures.contract_state_dict) - the random-init net no
+#                   longer amplifies bf16 rounding chaotically;
+#   *_warm        : the weights after 60 Adam steps of the reference (the trajectory's losses are golden too).
+# Bounds are what the bf16 activation / gradient storage delivers on B200 (measured values -> gpurun_out/parity_report.jsonl).
+# ---------------------------------------------------------------------------------------------------------------------
+COND_COS_MIN = 0.95         # every parameter tensor with a non-negligible gradient
+COND_COS_MEDIAN = 0.99      # median over tensors
+COND_L2_MEDIAN = 0.10
+
+
+def _conditioned_model(g, variant):
+    from oracle import fixtures
+    from hrnet_b200.config import make_cfg
+    from hrnet_b200.models import pose_hrnet, pose_hrnet_softmax
+    B, H, W, width = int(g["B"]), int(g["H"]), int(g["W"]), int(g["width"])
+    cfg = make_cfg(width, softmax=(variant == "softmax"), trainable_softmax=True, image_size=(H, W))
+    torch.manual_seed(0)
+    m = (pose_hrnet_softmax if variant == "softmax" else pose_hrnet).get_pose_net(cfg, is_train=False)
+    sd = m.state_dict()
+    fixtures.perturb_state_dict(sd)
+    if float(g["contract"]) > 0:
+        fixtures.contract_state_dict(sd, float(g["contract"]))
+    m.load_state_dict(sd)
+    return m, cfg, {k: v.clone() for k, v in m.state_dict().items()}, (B, H, W)
+
+
+def _warm_oracle(g, cfg, sd, variant, B, H, W):
+    """the reference's warm-up trajectory re-run with the (pinned) oracle port on the host; checked against the golden
+    losses and weight checksums before anything is compared with it"""
+    from oracle import hrnet_oracle, train_oracle
+    from oracle.make_golden import warm_batch
+    arch = hrnet_oracle.Arch.from_cfg(cfg)
+    ostate, losses = None, []
+    for s in range(int(g["warm_steps"])):
+        x, gt, xy, vis = warm_batch(s, B, H, W)
+        o = train_oracle.train_step(sd, x, gt, xy, vis, arch, variant, trainable_temp=True, opt_state=ostate)
+        sd, ostate = o["state"], o["opt_state"]
+        losses.append(o["losses"])
+    if losses:
+        # two fp32 runs of this trajectory do not stay together (the UNMODIFIED reference with 3 instead of 8 host threads is
+        # 1.5 % off in the pose2d loss after 16 steps, profiles/r2_reference_self_chaos.txt): loose check on the port's run
+        rel = np.abs(np.array(losses) - g["trajectory"]) / np.abs(g["trajectory"])
+        assert rel[:, 0].max() < 2e-2 and rel[:, 2].max() < 0.15, ("oracle warm-up trajectory left the reference's", rel.max(0))
+        assert np.allclose(losses[0], g["trajectory"][0], rtol=1e-4)      # step 0 (identical weights) is tight
+    return sd
+
+
+@pytest.mark.parametrize("name,variant", [("train_w32_softmax_contractive", "softmax"), ("train_w32_softmax_warm", "softmax"),
+                                          ("train_w48_raw_contractive", "raw")])
+def test_conditioned_gradients_against_fp32_reference(golden_dir, name, variant):
+    from oracle import fixtures, hrnet_oracle, train_oracle
+    from hrnet_b200.train import TrainEngine
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m, cfg, sd, (B, H, W) = _conditioned_model(g, variant)
+    sd = _warm_oracle(g, cfg, sd, variant, B, H, W)
+    m.load_state_dict(sd)
+    warm = int(g["warm_steps"]) > 0
+    if not warm:
+        for k in g["keys"]:                  # the weights under test are exactly the reference's (sampled check)
+            k = str(k)
+            assert np.allclose(fixtures.sample(sd[k]).numpy(), g["weight/" + k], rtol=1e-6, atol=1e-8), k
+    x = fixtures.images(B, H, W)
+    gt, xy, vis = fixtures.targets(B, 21, H // 4, W // 4)
+    eng = TrainEngine(m.cuda().train(), use_graph=False)
+    p = eng.train_step(x.cuda(), gt.cuda(), xy.cuda(), vis.cuda(), optimizer_step=False)
+    torch.cuda.synchronize()
+    losses = p.losses.cpu().numpy()
+    nl = 3 if variant == "softmax" else 2
+    if not warm:
+        assert np.allclose(losses[:nl], g["losses"][:nl], rtol=5e-3), (losses, g["losses"])
+    names = [n for n, _ in m.named_parameters()]
+    nat = dict(zip(names, eng.flat.natural_grads()))
+    # (1) the sampled gradients of the UNMODIFIED reference (identical weights: the cases without a warm-up)
+    gmax = float(g["gmax_all"].max())
+    stats = []
+    for k in ([] if warm else g["keys"]):
+        k = str(k)
+        ref = torch.from_numpy(g["grad/" + k])
+        if float(ref.abs().max()) <= 1e-4 * gmax:
+            continue
+        l2, cos = _cmp(fixtures.sample(nat[k].cpu()), ref)
+        stats.append((cos, l2, k))
+        _report(name + ":" + k, grad_rel_l2=l2, grad_cos=cos)
+    # (2) every parameter tensor against the fp32 oracle step at the same weights (the oracle is pinned to the reference at
+    #     exactly these weights by make_golden: worst cosine > 0.999) - NOT linearised: plain fp32 forward and backward
+    o = train_oracle.train_step(sd, x, gt, xy, vis, hrnet_oracle.Arch.from_cfg(cfg), variant, trainable_temp=True, adam=False)
+    norms = dict(zip([str(k) for k in g["all_keys"]], g["gnorm_all"]))
+    allstats = []
+    for k, ref in o["grads"].items():
+        if float(ref.abs().max()) <= 1e-4 * gmax:
+            continue                      # mathematically-zero gradients (bias before BatchNorm, softmax shift invariance)
+        if not warm:
+            assert abs(float(ref.double().norm()) - norms[k]) <= 2e-3 * norms[k] + 1e-12, ("oracle != reference gradient norm", k)
+        l2, cos = _cmp(nat[k].cpu(), ref)
+        allstats.append((cos, l2, k))
+    allstats.sort()
+    cs = np.array([c for c, _, _ in allstats])
+    ls = np.array([l for _, l, _ in allstats])
+    _report(name, n_tensors=len(allstats), cos_min=float(cs.min()), cos_p01=float(np.percentile(cs, 1)), cos_median=float(np.median(cs)),
+            frac_cos_ge_099=float((cs >= 0.99).mean()), l2_median=float(np.median(ls)), l2_max=float(ls.max()),
+            worst=[(round(c, 4), round(l, 3), k) for c, l, k in allstats[:5]], loss=losses.tolist(), loss_ref=g["losses"].tolist())
+    assert cs.min() >= COND_COS_MIN, allstats[:8]
+    assert np.median(cs) >= COND_COS_MEDIAN and np.median(ls) <= COND_L2_MEDIAN, (float(np.median(cs)), float(np.median(ls)))
+    assert np.allclose(losses[:nl], np.array(o["losses"])[:nl], rtol=5e-3), (losses, o["losses"])
+    if stats:
+        assert min(c for c, _, _ in stats) >= COND_COS_MIN, sorted(stats)[:5]
+
+
+def test_loss_trajectory_against_reference(golden_dir):
+    """60 fused training steps (forward, losses, backward, Adam, re-pack; CUDA graph replays) from the reference's initial
+    weights on the reference's batches: the three loss curves must follow the UNMODIFIED reference's (golden trajectory of
+    train_w32_softmax_warm.npz) and the weights must end up where the reference's did."""
+    from oracle import fixtures
+    from oracle.make_golden import warm_batch
+    from hrnet_b200.train import TrainEngine
+    g = np.load(os.path.join(golden_dir, "train_w32_softmax_warm.npz"))
+    m, cfg, sd, (B, H, W) = _conditioned_model(g, "softmax")
+    eng = TrainEngine(m.cuda().train(), lr=1e-3, weight_decay=1e-4, loss_factors=(1.0, 0.1), use_graph=True)
+    traj = []
+    for s in range(int(g["warm_steps"])):
+        x, gt, xy, vis = warm_batch(s, B, H, W)
+        p = eng.train_step(x.cuda(), gt.cuda(), xy.cuda(), vis.cuda())
+        traj.append(p.losses.cpu().numpy().copy())
+    traj = np.array(traj, dtype=np.float64)
+    ref = g["trajectory"]
+    rel = np.abs(traj - ref) / np.abs(ref)
+    _report("trajectory_w32_softmax_60_steps", max_rel_total=float(rel[:, 0].max()), max_rel_hm=float(rel[:, 1].max()),
+            max_rel_p2d=float(rel[:, 2].max()), first=traj[0].tolist(), last=traj[-1].tolist(), ref_last=ref[-1].tolist())
+    assert rel[:, 0].max() < 2e-2 and rel[:, 1].max() < 2e-2, (rel[:, 0].max(), rel[:, 1].max())
+    # the pose2d term alone (10 % of the total): two fp32 runs of the UNMODIFIED reference (8 vs 3 host threads) already
+    # differ by 1.5 % after 16 steps (profiles/r2_reference_self_chaos.txt)
+    assert rel[:, 2].max() < 0.15, rel[:, 2].max()
+    # the weights after 60 steps: Adam's first steps move every element by ~lr regardless of the gradient's size, so
+    # compare the UPDATE direction (w_60 - w_0) with the reference's
+    cur = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    for k in ("last_layer.3.weight", "last_layer.0.weight", "stage4.2.fuse_layers.0.3.0.weight", "stage2.0.branches.0.0.conv1.weight",
+              "conv2.weight"):
+        d_ref = torch.from_numpy(g["weight/" + k]) - fixtures.sample(sd[k])
+        d_got = fixtures.sample(cur[k]) - fixtures.sample(sd[k])
+        l2, cos = _cmp(d_got, d_ref)
+        _report("trajectory_update:" + k, rel_l2=l2, cos=cos)
+        assert cos > 0.8, (k, l2, cos)

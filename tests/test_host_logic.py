@@ -129,3 +129,40 @@ def test_fused_statistics_eligibility_rule():
     assert not stats_eligible(params(32, 32, _lib.HRNB_CONV_GATHER))
     assert not stats_eligible(params(32, 32, _lib.HRNB_CONV_OUT_NCHW))
     assert not stats_eligible(params(32, 32, 0, res=0x1000))
+
+
+def test_named_parameter_and_module_order_match_the_reference():
+    """an index-keyed optimizer.state_dict() of a reference checkpoint (tools/train.py:285,380) must line up
+    with our parameters, and init_weights' walk over modules() must draw the RNG in the reference's order"""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref_hrnet, ref_softmax, *_ = ref_shim.modules()
+    for mod_ref, mod_ours, yaml_rel in ((ref_softmax, pose_hrnet_softmax, "experiments/RHD/RHD_HRNet_w32_softmax_hm-pose2dloss_v1.yaml"),
+                                        (ref_hrnet, pose_hrnet, "experiments/RHD/RHD_HRNet_w32_max_hmloss_v1.yaml")):
+        cfg = ref_shim.load_cfg(yaml_rel)
+        ref = mod_ref.get_pose_net(cfg, is_train=False)
+        ours = mod_ours.get_pose_net(cfg, is_train=False)
+        assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
+        assert [n for n, _ in ours.named_buffers()] == [n for n, _ in ref.named_buffers()]
+        assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+        # init_weights (normal std 0.001, BN constants) under the same seed gives the same tensors
+        torch.manual_seed(3); ref.init_weights("")
+        torch.manual_seed(3); ours.init_weights("")
+        for (k, a), (_, b) in zip(ours.state_dict().items(), ref.state_dict().items()):
+            assert torch.equal(a, b), k
+
+
+def test_unsupported_widths_fail_early_with_a_clear_message():
+    from hrnet_b200.config import make_cfg
+    with pytest.raises(ValueError, match="multiple of 16"):
+        pose_hrnet.get_pose_net(make_cfg(18, softmax=False), is_train=False)
+
+
+def test_grad_allreduce_bucket_bounds_and_cpu_form():
+    from hrnet_b200.parallel import GradAllReduce
+    ar = GradAllReduce(1000, n_buckets=3)
+    assert ar.bounds[0][0] == 0 and ar.bounds[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(ar.bounds[:-1], ar.bounds[1:]))
+    assert not ar.overlap and ar.mean_scale == 1.0
+    t = torch.arange(1000, dtype=torch.float32)
+    assert torch.equal(ar(t.clone()), t)          # world 1: identity

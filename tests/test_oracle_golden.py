@@ -175,3 +175,50 @@ def test_triangulation_oracle_matches_reference_golden(golden_dir):
         svd = np.stack([T.svd_triangulation(uv[:, :, k], P) for k in range(J)], axis=1)
         assert np.abs(svd - g[case + "/svd"]).max() < 2e-2
         assert np.abs(out - svd).max() < 0.5 and np.abs(out - g[case + "/gt"]).max() < 10.0
+
+
+@pytest.mark.parametrize("name,variant", [("train_w32_softmax_contractive", "softmax"), ("train_w48_raw_contractive", "raw")])
+def test_train_oracle_reproduces_conditioned_reference_goldens(golden_dir, name, variant):
+    """the well-conditioned training goldens (oracle/make_golden.py train_conditioned_fixture, generated by the UNMODIFIED
+    reference): the oracle port reproduces their losses and (sampled) gradients from the seeded + contracted weights"""
+    from oracle import hrnet_oracle, train_oracle
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, H, W, width = int(g["B"]), int(g["H"]), int(g["W"]), int(g["width"])
+    cfg = make_cfg(width, softmax=(variant == "softmax"), trainable_softmax=True, image_size=(H, W))
+    torch.manual_seed(0)
+    sd = (pose_hrnet_softmax if variant == "softmax" else pose_hrnet).get_pose_net(cfg, is_train=False).state_dict()
+    fixtures.perturb_state_dict(sd)
+    fixtures.contract_state_dict(sd, float(g["contract"]))
+    for k in g["keys"]:
+        assert np.allclose(fixtures.sample(sd[str(k)]).numpy(), g["weight/" + str(k)], rtol=1e-6, atol=1e-8), k
+    x = fixtures.images(B, H, W)
+    gt, xy, vis = fixtures.targets(B, 21, H // 4, W // 4)
+    o = train_oracle.train_step(sd, x, gt, xy, vis, hrnet_oracle.Arch.from_cfg(cfg), variant, trainable_temp=True, adam=False)
+    assert np.allclose(o["losses"], g["losses"], rtol=1e-4)
+    gmax = float(g["gmax_all"].max())
+    norms = dict(zip([str(k) for k in g["all_keys"]], g["gnorm_all"]))
+    for k in g["keys"]:
+        k = str(k)
+        ref = g["grad/" + k]
+        assert np.abs(fixtures.sample(o["grads"][k]).numpy() - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1e-4 * gmax), k
+    for k, v in o["grads"].items():
+        if float(v.abs().max()) > 1e-4 * gmax:
+            assert np.isclose(float(v.double().norm()), norms[k], rtol=2e-3), k
+
+
+def test_warm_golden_records_the_reference_trajectory(golden_dir):
+    """train_w32_softmax_warm.npz: 60-step loss trajectory of the unmodified reference + the oracle port's deviation from
+    it (chaos floor, recorded by make_golden) + step 0 reproduced here by the oracle port"""
+    from oracle import hrnet_oracle, train_oracle
+    from oracle.make_golden import warm_batch
+    g = np.load(os.path.join(golden_dir, "train_w32_softmax_warm.npz"))
+    assert g["trajectory"].shape == (int(g["warm_steps"]), 3) and int(g["warm_steps"]) == 60
+    assert 0 < float(g["oracle_vs_ref_traj_dev"]) < 0.15 and float(g["oracle_vs_ref_worst_cos"]) > 0.99999
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    cfg = make_cfg(32, softmax=True, trainable_softmax=True, image_size=(H, W))
+    torch.manual_seed(0)
+    sd = pose_hrnet_softmax.get_pose_net(cfg, is_train=False).state_dict()
+    fixtures.perturb_state_dict(sd)
+    o = train_oracle.train_step(sd, *warm_batch(0, B, H, W), hrnet_oracle.Arch.from_cfg(cfg), "softmax", trainable_temp=True)
+    assert np.allclose(o["losses"], g["trajectory"][0], rtol=1e-4)
+    assert o["opt_state"] is not None and int(o["state"]["bn1.num_batches_tracked"]) == 1
