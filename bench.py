@@ -296,7 +296,7 @@ def workload_config(args, batch, note=None):
               % (var, args.width, args.height, args.img_width, args.config - 1 if args.config else 1,
                  "softmax + soft-argmax, HeatmapLoss + 0.1*pose2d loss" if (args.variant == "softmax" and args.loss == "hm+pose2d")
                  else "HeatmapLoss", "bucketed NCCL gradient all-reduce overlapped with the backward pass, " if args.gpus > 1 else "", batch))
-        par = "dp%d (batch sharded, fp32 gradient all-reduce in 2 buckets per step)" % args.gpus
+        par = "dp%d (batch sharded, fp32 gradient sum-all-reduce in 3 buckets per step, overlapped with the backward pass)" % args.gpus
     elif args.mode == "mhp":
         wl = ("MHP multi-view %s HRNet-W%d %dx%d, 4 views per sample: forward + soft-argmax + algebraic (SII-DLT) triangulation "
               "(BASELINE configs[3]), %d samples (%d images) per GPU" % (var, args.width, args.height, args.img_width, batch, 4 * batch))
@@ -786,7 +786,7 @@ def main():
     ap.add_argument("--detail", default=None, help="write per-launch timings (json) here")
     args = ap.parse_args()
     preset = CONFIGS[args.config or 2]
-    for k, v in dict(loss="hm+pose2d", trainable_temp=False, **preset).items():
+    for k, v in dict(dict(loss="hm+pose2d", trainable_temp=False), **preset).items():
         if getattr(args, k, None) is None:
             setattr(args, k, v)
     if args.variant == "raw":

@@ -138,6 +138,12 @@ _SIGS = {
     "hrnb_adam_tick": (C.c_int, [_vp, _vp, _vp]),
     "hrnb_grad_to_natural": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "hrnb_triangulate_dlt": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hrnb_triangulate_dlt_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hrnb_gen_heatmaps": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.c_float, _vp, _vp]),
+    "hrnb_stem_im2col_u8": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _i64, _i32, _i32, _i32, _vp]),
+    "hrnb_flip_merge": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hrnb_maxpool2_relu": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "hrnb_gap_mlp": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "hrnb_last_error": (C.c_char_p, []),
     "hrnb_abi_version": (C.c_int, []),
     "hrnb_launch_count": (_i64, []),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhrnb.so")
 STAMP = os.path.join(HERE, ".libhrnb.stamp")
-SOURCES = ["api.cu", "conv_tc.cu", "wgrad_tc.cu", "elementwise.cu", "train_ops.cu", "decode_loss.cu", "triangulate.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "wgrad_tc.cu", "elementwise.cu", "train_ops.cu", "decode_loss.cu", "triangulate.cu", "glue.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
@@ -57,5 +57,21 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """experiment builds (tools/): the same sources with extra -D flags into hrnet-hand-pose-estimation_b200/<name>, selected
+    at run time with HRNB_LIB=<name>"""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(HERE, name)
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -136,6 +136,14 @@ class Plan:
         def stem(lib=lib, x=x, cols=cols, B=B, H=self.H, W=self.W):
             _lib.check(lib.hrnb_stem_im2col(x.data_ptr(), cols.ptr, cols.ps, B, H, W, _lib.stream_ptr()))
         self._op(0, stem, "conv1.im2col")
+        # uint8 NHWC input with ToTensor + Normalize folded into the im2col (lib/dataset/transforms/build.py:82-85): SURVEY §8 f3
+        self.x_u8 = None
+        self.norm = None
+
+        def stem_u8(lib=lib, cols=cols, B=B, H=self.H, W=self.W):
+            mean, std = self.norm
+            _lib.check(lib.hrnb_stem_im2col_u8(self.x_u8.data_ptr(), mean, std, cols.ptr, cols.ps, B, H, W, _lib.stream_ptr()))
+        self.stem_u8 = stem_u8
         t1 = self._conv(0, L["conv1"], cols, self._phases(64, H2, W2), name="conv1")
         cur = self._conv(0, L["conv2"], t1, self._buf(64, H4, W4), name="conv2")
 
@@ -266,7 +274,7 @@ class Plan:
         self.out["features"] = feat
 
     # ---- execution ----------------------------------------------------------------------------------
-    def _run_steps(self, want_features):
+    def _run_steps(self, want_features, u8=False):
         main = torch.cuda.current_stream()
         side = self.engine.side_streams
         streams = [main] + side
@@ -275,7 +283,7 @@ class Plan:
         for st in self.steps:
             if st.kind == "op":
                 if st.sid == 0:
-                    st.fn()
+                    (self.stem_u8 if (u8 and st.name == "conv1.im2col") else st.fn)()
                 else:
                     with torch.cuda.stream(streams[st.sid]):
                         st.fn()
@@ -289,20 +297,20 @@ class Plan:
     def launches(self, want_features):
         return self.n_launch + (1 if want_features else 0)
 
-    def run(self, want_features=True, use_graph=True):
+    def run(self, want_features=True, use_graph=True, u8=False):
         if not use_graph:
-            self._run_steps(want_features)
+            self._run_steps(want_features, u8)
             return self.out
-        key = bool(want_features)
+        key = (bool(want_features), bool(u8))
         if self.graph is None:
             self.graph = {}
         if key not in self.graph:
             # warm-up outside capture (sets function attributes, loads modules), then capture
-            self._run_steps(want_features)
+            self._run_steps(want_features, u8)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._run_steps(want_features)
+                self._run_steps(want_features, u8)
             self.graph[key] = g
         self.graph[key].replay()
         return self.out
@@ -315,10 +323,9 @@ class HRNetEngine:
         self.plans = {}
         self.use_graph = os.environ.get("HRNB_NO_GRAPH", "0") != "1"
         self.single_stream = os.environ.get("HRNB_SINGLE_STREAM", "0") == "1"
-        # programmatic dependent launch of the conv kernels is opt-in (HRNB_PDL=1; 4.16 vs 4.21 ms/step at batch 64): PDL
-        # launches showed rare device-side mbarrier time-outs in the training engine this round; the cause (conv_tc.cu
-        # producer, prefetched weight stage) is fixed, the soak that would make PDL the default is not done yet (train.py)
-        self.pdl = os.environ.get("HRNB_PDL", "0") == "1"
+        # programmatic dependent launch of the conv kernels: default on since the round-2 soak (train.py); neutral for the
+        # graph-replayed inference plan (13.12 vs 13.13 ms at batch 256), kept on so both engines run one launch mode.  HRNB_PDL=0: off
+        self.pdl = os.environ.get("HRNB_PDL", "1") != "0"
         with torch.cuda.device(self.device):
             _lib.hang_init()
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
@@ -372,6 +379,25 @@ class HRNetEngine:
             with torch.cuda.device(self.device):
                 self.plans[key] = Plan(self, B, H, W)
         return self.plans[key]
+
+    def forward_u8(self, images, mean, std, want_features=True):
+        """images: [B,H,W,3] uint8 CUDA tensor (what the data loader holds before ToTensor + Normalize); the normalisation of
+        lib/dataset/transforms/build.py:82-85 is applied inside the stem's im2col kernel, so the 4x larger fp32 NCHW image
+        tensor the reference uploads never exists."""
+        import ctypes as C_
+        if images.dim() != 4 or images.shape[3] != 3 or images.dtype != torch.uint8:
+            raise ValueError("expected uint8 images [B, H, W, 3]")
+        B, H, W, _ = images.shape
+        p = self.plan(B, H, W)
+        with torch.cuda.device(self.device):
+            if p.x_u8 is None:
+                p.x_u8 = torch.zeros((B, H, W, 3), dtype=torch.uint8, device=self.device)
+            norm = ((C_.c_float * 3)(*[float(v) for v in mean]), (C_.c_float * 3)(*[float(v) for v in std]))
+            if p.norm is not None and (list(p.norm[0]) != list(norm[0]) or list(p.norm[1]) != list(norm[1])):
+                p.graph = None                      # the constants are baked into the captured launch
+            p.norm = norm
+            p.x_u8.copy_(images, non_blocking=True)
+            return p.run(want_features, self.use_graph, u8=True)
 
     def forward(self, x, want_features=True):
         """x: [B,3,H,W] float32 CUDA NCHW.  Returns the plan's static output tensors (overwritten by the next

@@ -34,8 +34,12 @@ class Node(nn.Module):
         raise RuntimeError("sub-modules of the B200 HRNet are parameter holders; call the network's forward")
 
 
-def _materialise(root, specs):
+def _materialise(root, specs, before=None):
+    """before: {spec key: callable} run right before that layer is created (subclasses that register extra modules at the
+    point of the construction order - and of the seeded RNG stream - where the reference creates them)"""
     for sp in specs:
+        if before and sp.key in before:
+            before[sp.key]()
         parts = sp.key.split(".")
         node = root
         for comp in parts[:-1]:
@@ -67,12 +71,13 @@ class _TrainForward(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         eng = model.train_engine()
         want = model.return_features
-        p = eng.forward(x, want_features=want)
+        p = eng.forward(x, want_features=want, feat_grad=bool(want and model.feat_requires_grad))
         ctx.model, ctx.plan, ctx.generation = model, p, p.generation
         ctx.set_materialize_grads(False)
         out = p.out["heatmap"] if model.variant == "softmax" else p.out["logits"]
         feat = p.feat.clone() if want else x.new_zeros(())
-        ctx.mark_non_differentiable(feat) if not want else None
+        if not want:
+            ctx.mark_non_differentiable(feat)
         return out.clone(), feat
 
     @staticmethod
@@ -105,12 +110,12 @@ class PoseHighResolutionNet(nn.Module):
     """variant 'raw'     : forward -> (logits, stage3_branch0)                  [pose_hrnet.py:568]
        variant 'softmax' : forward -> (heatmap, concat_feat, trainable_temp)    [pose_hrnet_softmax.py:528]"""
 
-    def __init__(self, cfg, variant="raw", **kwargs):
+    def __init__(self, cfg, variant="raw", before=None, **kwargs):
         super().__init__()
         self.variant = variant
         self.arch = A.arch_from_cfg(cfg)
         self.specs = A.layer_specs(self.arch)
-        _materialise(self, self.specs)
+        _materialise(self, self.specs, before)
         extra = cfg["MODEL"]["EXTRA"]
         self.pretrained_layers = extra["PRETRAINED_LAYERS"] if "PRETRAINED_LAYERS" in extra else ["*"]
         # keep the reference's index layout: transitionN[i] is None where the branch passes through
@@ -125,6 +130,7 @@ class PoseHighResolutionNet(nn.Module):
         self._train_key = None
         self._train_epoch = 0         # bumped by the training engine on every train-mode forward / step (stale-fold guard)
         self.return_features = True   # set False to skip materialising the NCHW fp32 feature output
+        self.feat_requires_grad = False   # True: loss.backward() may flow through the returned feature tensor (train mode)
         self.static_outputs = False   # True: return the engine's static buffers (overwritten by the next call)
 
     # ---- reference API -----------------------------------------------------------------------------
@@ -171,6 +177,10 @@ class PoseHighResolutionNet(nn.Module):
             self._tensors = list(self.parameters()) + list(self.buffers())
         return sum(t._version for t in self._tensors), len(self._tensors), self._train_epoch
 
+    def engine_parameters(self):
+        """[(name, parameter)] the CUDA engines own, in named_parameters() order (subclasses with add-on heads exclude theirs)"""
+        return list(self.named_parameters())
+
     def _weights_version(self):
         """version counter of the parameters only (buffers are updated by the training kernels themselves)"""
         return sum(p._version for p in self.parameters())
@@ -207,7 +217,7 @@ class PoseHighResolutionNet(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("input must be a CUDA tensor (no CPU fallback)")
         if self.training:
-            params = list(self.parameters())
+            params = [p for _, p in self.engine_parameters()]
             out, feat = _TrainForward.apply(self, x, *params)
             feat = feat if self.return_features else None
             if self.variant == "softmax":
@@ -216,6 +226,23 @@ class PoseHighResolutionNet(nn.Module):
         eng = self.engine()
         out = eng.forward(x, want_features=self.return_features)
         # the engine's outputs are static CUDA-graph buffers; hand out copies unless told otherwise
+        get = (lambda k: out[k]) if self.static_outputs else (lambda k: out[k].clone())
+        feat = get("features") if self.return_features else None
+        if self.variant == "softmax":
+            return get("heatmap"), feat, self.trainable_temp
+        return get("logits"), feat
+
+
+    IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)       # lib/dataset/transforms/build.py:85
+
+    def forward_images(self, images_u8, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        """eval-mode forward on raw uint8 NHWC images [B,H,W,3]: ToTensor + Normalize (lib/dataset/transforms/build.py:82-85)
+        are applied inside the stem kernel.  Same return values as forward()."""
+        if self.training:
+            raise RuntimeError("forward_images is an inference entry point (model.eval())")
+        if not images_u8.is_cuda:
+            raise RuntimeError("input must be a CUDA tensor (no CPU fallback)")
+        out = self.engine().forward_u8(images_u8, mean, std, want_features=self.return_features)
         get = (lambda k: out[k]) if self.static_outputs else (lambda k: out[k].clone())
         feat = get("features") if self.return_features else None
         if self.variant == "softmax":

@@ -20,3 +20,20 @@ def targets(B, J=21, h=64, w=64, seed=2, sigma=2.0):
     mu = xy.round()
     hm = torch.exp(-((xs - mu[..., 0, None, None]) ** 2 + (ys - mu[..., 1, None, None]) ** 2) / (2 * sigma ** 2))
     return hm, xy, vis
+
+
+def cameras(B, V, seed=3, focal=600.0, center=(320.0, 240.0), distance=600.0):
+    """B x V projection matrices K [R | t] of cameras on an arc looking at the origin (MHP-like: 4 views, 640x480)"""
+    g = torch.Generator().manual_seed(seed)
+    P = torch.zeros(B, V, 3, 4)
+    K = torch.tensor([[focal, 0.0, center[0]], [0.0, focal, center[1]], [0.0, 0.0, 1.0]])
+    for b in range(B):
+        for v in range(V):
+            ang = torch.rand(3, generator=g) * 0.6 - 0.3 + torch.tensor([0.0, v * 0.5, 0.0])
+            (cx, cy, cz), (sx, sy, sz) = torch.cos(ang), torch.sin(ang)
+            Rx = torch.tensor([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+            Ry = torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+            Rz = torch.tensor([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]])
+            t = torch.tensor([0.0, 0.0, distance]) + torch.randn(3, generator=g) * 30
+            P[b, v] = K @ torch.cat([Rz @ Ry @ Rx, t.view(3, 1)], 1)
+    return P

@@ -44,8 +44,9 @@ def _phase_view(ph, i):
 
 
 class TrainPlan:
-    def __init__(self, eng, B, H, W):
+    def __init__(self, eng, B, H, W, feat_grad=False):
         self.eng, self.B, self.H, self.W = eng, B, H, W
+        self.feat_grad = feat_grad      # the backward pass also takes a gradient w.r.t. the returned feature tensor
         self.dev = eng.device
         self.fwd, self.loss_steps, self.bwd = [], [], []      # fwd / bwd: (kind, sid, fn | other stream, name)
         self._ctx, self._sid = "", 0
@@ -526,6 +527,25 @@ class TrainPlan:
                                                                    feat_src.H, feat_src.W, self.feat.data_ptr(),
                                                                    _lib.stream_ptr()))
 
+        # gradient w.r.t. the feature output (inter_feat): the second return value of the reference's forward is an
+        # autograd-connected tensor (pose_hrnet_softmax.py:528 the 480-channel concat, pose_hrnet.py:568 stage-3 branch 0) and
+        # wrappers train through it (pose_hrnet_volumetric.py:620-634).  It is injected FIRST in the backward pass as the
+        # initial content of that activation's gradient buffer; every later contribution then accumulates.
+        self.d_feat = None
+        if self.feat_grad:
+            ft = cat if e.variant == "softmax" else stage3_b0
+            self.d_feat = torch.zeros((B, feat_src.C, feat_src.H, feat_src.W), dtype=torch.float32, device=self.dev)
+            d_feat = self.d_feat
+
+            def back_feat():
+                self.on(0)
+                self._ctx = "inter_feat"
+                g, mode = self._gw(ft)
+                assert mode == 1
+                self._b(lambda: _lib.check(lib.hrnb_nchw_f32_to_pf8(d_feat.data_ptr(), B, g.C, g.H, g.W, g.ptr, g.ps,
+                                                                    _lib.stream_ptr())), "nchw_to_pf8:inter_feat")
+            self.tape.append(back_feat)
+
         # backward launch list from the tape
         self.on(0)
         if self.softmax_back is not None:
@@ -618,12 +638,13 @@ class TrainEngine:
         self.use_graph = use_graph and os.environ.get("HRNB_NO_GRAPH", "0") != "1"
         # Default: branches of a HighResolutionModule on parallel streams, plain stream-ordered launches.
         # HRNB_TRAIN_STREAMS=0: single-stream plan with the BatchNorm kernels of a module's branches batched horizontally.
-        # HRNB_TRAIN_PDL=1: programmatic dependent launch (PDL) on every kernel of the step: 23.0 vs 25.0 ms/step at batch 64.
-        # PDL is still opt-in: before the producer fix in conv_tc.cu (the prefetched weight stage must not wait on empty_b)
-        # about one PDL bench run in eight ended in a device-side mbarrier time-out; after it 5 of 5 runs passed, which is
-        # not yet the soak a default needs (profiles/r1_hang_records_wgrad_streams.txt).
+        # Programmatic dependent launch (PDL) on every kernel of the step is the default since round 2: 22.98 vs 24.83 ms/step at
+        # batch 64.  Round 1 kept it opt-in because about one PDL run in eight ended in a device-side mbarrier time-out; the
+        # cause (conv_tc.cu producer: the prefetched weight stage must not wait on empty_b) was fixed then, and the soak a default
+        # needs was done in round 2: 8 of 8 bench runs + the whole GPU suite under PDL (profiles/r2_pdl_soak.txt).
+        # HRNB_TRAIN_PDL=0 turns it off.
         self.multi_stream = os.environ.get("HRNB_TRAIN_STREAMS", "1") != "0" if multi_stream is None else bool(multi_stream)
-        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "0") == "1"
+        self.pdl = os.environ.get("HRNB_TRAIN_PDL", "1") != "0"
         # BatchNorm batch statistics reduced in the epilogue of the producing conv where the tile shape allows it (cout = BN
         # in {16, 32, 64}: the high-resolution layers); HRNB_FUSE_STATS=0: always the separate bn_stats pass
         self.fuse_stats = os.environ.get("HRNB_FUSE_STATS", "1") != "0"
@@ -641,7 +662,7 @@ class TrainEngine:
 
     def _setup(self, lr, betas, eps, weight_decay):
         model, dev = self.model, self.device
-        named = list(model.named_parameters())
+        named = model.engine_parameters() if hasattr(model, "engine_parameters") else list(model.named_parameters())
         index = {n: i for i, (n, _) in enumerate(named)}
         self.param_names = [n for n, _ in named]
         specs = A.layer_specs(self.arch)
@@ -715,12 +736,12 @@ class TrainEngine:
             self._s2_cache[ck] = layers
         return self._s2_cache[ck]
 
-    def plan(self, B, H, W):
-        key = (B, H, W)
+    def plan(self, B, H, W, feat_grad=False):
+        key = (B, H, W) if not feat_grad else (B, H, W, True)
         if key not in self.plans:
             with torch.cuda.device(self.device):
                 self._prepare_s2(H, W)     # stride-2 units: per-resolution data-gradient layers
-                p = TrainPlan(self, B, H, W)
+                p = TrainPlan(self, B, H, W, feat_grad=feat_grad)
                 self.repacker.run()
                 torch.cuda.synchronize(self.device)
                 self.plans[key] = p
@@ -753,9 +774,9 @@ class TrainEngine:
     def repack(self):
         self.repacker.run()
 
-    def forward(self, x, want_features=False):
+    def forward(self, x, want_features=False, feat_grad=False):
         B, _, H, W = x.shape
-        p = self.plan(B, H, W)
+        p = self.plan(B, H, W, feat_grad=feat_grad)
         p.generation += 1
         self._touch_model()
         p.x.copy_(x, non_blocking=True)

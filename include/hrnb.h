@@ -353,6 +353,38 @@ int hrnb_grad_to_natural(const float* grads, float* out, const hrnb_param_seg* s
  * out [B][J][3] euclidean 3-D joints; all fp32 device pointers. V >= 2, iterations >= 1 (reference: 2). */
 int hrnb_triangulate_dlt(const float* points, const float* proj, const float* bk0, int32_t B, int32_t V, int32_t J,
                          int32_t iterations, float* out, void* stream);
+/* Adjoint of hrnb_triangulate_dlt w.r.t. the 2-D points (the reference's DLT_sii_pytorch is a differentiable torch graph;
+ * lib/core/function.py train3D back-propagates the 3-D joint loss through it into the backbone).  d_out [B][J][3] ->
+ * d_points [B][V][J][2] (written).  The projection matrices are data (no gradient).  iterations <= 4. */
+int hrnb_triangulate_dlt_bwd(const float* points, const float* proj, const float* bk0, const float* d_out, int32_t B,
+                             int32_t V, int32_t J, int32_t iterations, float* d_points, void* stream);
+
+/* ---- loop glue on the device: SURVEY §8 rows (f1) confidence head, (f3) targets + normalisation, (f4) flip test ------ */
+/* Ground-truth heat maps, replaces HeatmapGenerator.__call__ (lib/dataset/target_generators/target_generators.py:28-53) run per
+ * sample in the data-loader workers: joints [BJ][joint_stride] fp32 rows (u, v[, visible]) in heat-map pixels, out [BJ][h][w]
+ * fp32.  x = int(u), y = int(v); joints with visible <= 0 or outside the map give an all-zero map; otherwise the
+ * (6 sigma + 3)^2 patch around (x, y) holds exp(-d^2 / (2 sigma^2)) evaluated in float64 (as numpy) and the rest is zero. */
+int hrnb_gen_heatmaps(const float* joints, int32_t joint_stride, int32_t BJ, int32_t h, int32_t w, float sigma, float* out,
+                      void* stream);
+/* uint8 NHWC image [N][in_H][in_W][3] (device) -> the stem's im2col slab (as hrnb_stem_im2col) with torchvision's ToTensor
+ * (/255) and Normalize(mean, std) applied on the fly (lib/dataset/transforms/build.py:82-85): the fp32 NCHW image tensor
+ * the reference uploads (4x the bytes) never exists.  mean3_host / std3_host: 3 floats each in HOST memory. */
+int hrnb_stem_im2col_u8(const uint8_t* img_nhwc, const float* mean3_host, const float* std3_host, void* out, int64_t out_ps,
+                        int32_t N, int32_t in_H, int32_t in_W, void* stream);
+/* Flip test merge, replaces flip_back (lib/utils/transforms.py:16-30: reverse x, swap the matched joint pairs) + the
+ * SHIFT_HEATMAP one-pixel shift + the average of lib/core/function.py:681-701, which the reference does through a
+ * device->host->device round trip in numpy.  out = 0.5 * (hm + shift(flip_back(hm_flipped))), or shift(flip_back(hm_flipped))
+ * alone when hm is NULL; perm_dev [J] int32 = the joint permutation of the pair swaps; all maps [B][J][h][w] fp32. */
+int hrnb_flip_merge(const float* hm, const float* hm_flipped, const int32_t* perm_dev, int32_t B, int32_t J, int32_t h, int32_t w,
+                    int32_t shift, float* out, void* stream);
+/* GlobalAveragePoolingHead (lib/models/pose_hrnet_volumetric.py:22-56): nn.MaxPool2d(2) + ReLU on PF8 (the conv + BatchNorm
+ * in front of it is an hrnb_conv launch), and mean over positions + Linear/ReLU + Linear/ReLU + Linear/Sigmoid -> out [N][NC].
+ * Linear weights row-major [out][in] fp32 as nn.Linear stores them. */
+int hrnb_maxpool2_relu(const void* src, int64_t src_ps, int32_t N, int32_t C, int32_t H, int32_t W, void* dst, int64_t dst_ps,
+                       void* stream);
+int hrnb_gap_mlp(const void* x, int64_t x_ps, int32_t N, int32_t C, int32_t H, int32_t W, const float* w1, const float* b1,
+                 int32_t H1, const float* w2, const float* b2, int32_t H2, const float* w3, const float* b3, int32_t NC,
+                 float* out, void* stream);
 
 /* ---- misc --------------------------------------------------------------------------------------- */
 const char* hrnb_last_error(void);

@@ -365,11 +365,101 @@ def triangulation_fixture():
         assert err < 2e-5, (name, err)
         svd = torch.stack([M.triangulate_from_multiple_views_svd(P.clone(), uv[:, :, k].clone()) for k in range(J)], dim=1)
         assert np.abs(T.svd_triangulation(uv[:, :, 0].numpy(), P.numpy()) - svd[:, 0].numpy()).max() < 1e-2
+        # the reference's own autograd through DLT_sii_pytorch (train3D trains the backbone through it): d loss / d points
+        gw = torch.randn(B, J, 3, generator=torch.Generator().manual_seed(seed + 500))
+        uvg = uv.clone().requires_grad_(True)
+        torch.manual_seed(seed)
+        refg = torch.cat([M.DLT_sii_pytorch(uvg[:, :, k], P.clone()).unsqueeze(1) for k in range(J)], dim=1)
+        (refg * gw).sum().backward()
+        d_uv = uvg.grad.numpy()
+        mine = np.stack([T.dlt_sii_backward(uv[:, :, k].numpy(), P.numpy(), bk0[k], gw[:, k].numpy()) for k in range(J)], axis=2)
+        gerr = np.abs(mine - d_uv).max() / np.abs(d_uv).max()
+        assert gerr < 2e-3, (name, gerr)       # fp32 autograd of the reference vs the float64 adjoint
+        rec.update({name + "/d_out": gw.numpy(), name + "/d_points": d_uv})
+        print("triangulation", name, "backward: oracle adjoint == reference autograd (rel %.1e)" % gerr)
         rec.update({name + "/proj": P.numpy(), name + "/points": uv.numpy(), name + "/bk0": bk0, name + "/seed": np.int64(seed),
                     name + "/ref": ref.numpy(), name + "/svd": svd.numpy(), name + "/gt": X.numpy()})
         print("triangulation", name, "oracle == reference (rel %.1e); |sii - svd| max %.2e; |sii - gt| max %.2f"
               % (err, np.abs(ref.numpy() - svd.numpy()).max(), np.abs(ref.numpy() - X.numpy()).max()))
     np.savez_compressed(os.path.join(GOLD, "triangulation.npz"), **rec)
+
+
+def glue_fixture():
+    """the UNMODIFIED reference's HeatmapGenerator, flip_back (+ the flip-test merge of
+    core/function.py:681-701), ToTensor + Normalize and GlobalAveragePoolingHead -> tests/golden/glue.npz; the oracle
+    restatements (oracle/glue_oracle.py) are asserted equal."""
+    import importlib.util
+    from oracle import glue_oracle as G
+    ref_shim.install()
+    spec = importlib.util.spec_from_file_location(
+        "ref_target_generators", os.path.join(ref_shim.REF_ROOT, "lib/dataset/target_generators/target_generators.py"))
+    tg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tg)
+    import utils.transforms as RT
+    rec = {}
+    g = torch.Generator().manual_seed(21)
+    # ---- heat maps: 64 x 64, sigma 2 (RHD / MHP configs), 21 joints, 6 samples incl. edge cases ----
+    J, res, sigma = 21, 64, 2
+    joints = torch.rand(6, J, 3, generator=g) * torch.tensor([res + 8.0, res + 8.0, 1.0]) - torch.tensor([4.0, 4.0, 0.0])
+    joints[..., 2] = (torch.rand(6, J, generator=g) < 0.85).float()
+    joints[0, 0] = torch.tensor([0.0, 0.0, 1.0]); joints[0, 1] = torch.tensor([63.9, 63.9, 1.0])
+    joints[0, 2] = torch.tensor([-0.5, 10.0, 1.0]); joints[0, 3] = torch.tensor([64.0, 10.0, 1.0])      # int(-0.5) = 0: inside; 64: outside
+    joints[0, 4] = torch.tensor([3.2, 60.7, 1.0]); joints[0, 5] = torch.tensor([30.0, 30.0, 0.0])      # invisible
+    gen = tg.HeatmapGenerator(res, J, sigma)
+    hms = np.stack([gen(joints[b].numpy()) for b in range(6)])
+    mine = np.stack([G.heatmap_generator(joints[b].numpy(), (res, res), sigma) for b in range(6)])
+    assert np.array_equal(hms, mine)
+    rec.update(hm_joints=joints.numpy(), hm_out=hms, hm_sigma=np.array(sigma), hm_res=np.array(res))
+    # ---- flip_back + flip-test merge (RHD flip pairs: none are defined for hands in most configs; use a synthetic pairing) ----
+    pairs = [[1, 2], [3, 4], [5, 8], [17, 20]]
+    a = torch.randn(3, J, 16, 24, generator=g).numpy()
+    bflip = torch.randn(3, J, 16, 24, generator=g).numpy()
+    fb = RT.flip_back(bflip.copy(), pairs)
+    assert np.array_equal(fb, G.flip_back(bflip, pairs))
+    merged = {}
+    for shift in (0, 1):
+        t = torch.from_numpy(fb.copy())
+        if shift:
+            t[:, :, :, 1:] = t.clone()[:, :, :, 0:-1]                     # core/function.py:697-699
+        merged[shift] = ((torch.from_numpy(a) + t) * 0.5).numpy()         # :701
+        assert np.array_equal(merged[shift], G.flip_test_merge(a, bflip, pairs, bool(shift)))
+    rec.update(flip_pairs=np.array(pairs), flip_a=a, flip_b=bflip, flip_back=fb, flip_merge0=merged[0], flip_merge1=merged[1])
+    # ---- ToTensor + Normalize (the reference's own transform classes over torchvision) ----
+    spec = importlib.util.spec_from_file_location(
+        "ref_transforms", os.path.join(ref_shim.REF_ROOT, "lib/dataset/transforms/transforms.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    img = (torch.rand(2, 32, 48, 3, generator=g) * 256).clamp(0, 255).to(torch.uint8).numpy()
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    norm = []
+    for b in range(2):
+        t, _ = tr.ToTensor()(img[b], None)
+        t, _ = tr.Normalize(mean=mean, std=std)(t, None)
+        norm.append(t.numpy())
+        assert np.allclose(G.normalize_u8(img[b], mean, std), norm[-1], rtol=0, atol=1e-6)
+    rec.update(norm_img=img, norm_out=np.stack(norm), norm_mean=np.array(mean, np.float32), norm_std=np.array(std, np.float32))
+    # ---- GlobalAveragePoolingHead (seeded default init; only outputs + checksums are stored) ----
+    from models.pose_hrnet_volumetric import GlobalAveragePoolingHead
+    torch.manual_seed(5)
+    head = GlobalAveragePoolingHead(64, 32).eval()
+    sd = head.state_dict()
+    for k in sorted(sd):
+        if k.endswith("running_mean"):
+            sd[k].copy_(torch.randn(sd[k].shape, generator=g) * 0.1)
+        elif k.endswith("running_var"):
+            sd[k].copy_(torch.rand(sd[k].shape, generator=g) + 0.5)
+    head.load_state_dict(sd)
+    x = torch.randn(3, 64, 16, 16, generator=g)
+    with torch.no_grad():
+        out = head(x)
+    mine = G.gap_head({"h." + k: v for k, v in head.state_dict().items()}, "h", x)
+    assert torch.allclose(out, mine, rtol=1e-5, atol=1e-7)
+    rec.update(gap_x=x.numpy(), gap_out=out.numpy(), gap_wsum=np.array(float(sum(v.double().abs().sum() for v in sd.values()))))
+    for k in sorted(sd):
+        if k.endswith(("running_mean", "running_var")):
+            rec["gap_stat/" + k] = sd[k].numpy()
+    np.savez_compressed(os.path.join(GOLD, "glue.npz"), **rec)
+    print("glue ok; oracle == reference (heat maps, flip_back / merge, normalisation, confidence head)")
 
 
 def conditioned_fixtures():
@@ -384,6 +474,9 @@ def conditioned_fixtures():
 if __name__ == "__main__":
     if "--triangulation-only" in sys.argv:
         triangulation_fixture()
+        sys.exit(0)
+    if "--glue-only" in sys.argv:
+        glue_fixture()
         sys.exit(0)
     if "--conditioned-only" in sys.argv:
         conditioned_fixtures()
@@ -407,4 +500,5 @@ if __name__ == "__main__":
     train_fixture("train_w32_softmax", Y, "softmax", trainable_temp=True)
     train_fixture("train_w32_raw", YR, "raw")
     conditioned_fixtures()
+    glue_fixture()
     triangulation_fixture()

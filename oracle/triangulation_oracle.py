@@ -45,6 +45,36 @@ def dlt_sii(points, proj, bk0, iterations=2):
     return h[:, :3] / h[:, 3:4]
 
 
+def dlt_sii_backward(points, proj, bk0, d_out, iterations=2):
+    """adjoint of dlt_sii w.r.t. the points (float64 numpy): the chain the CUDA kernel triangulate_dlt_bwd_kernel follows.
+    The reference needs no such function - DLT_sii_pytorch is a torch autograd graph (misc.py:64-97); make_golden.py
+    stores the gradients that graph produces and tests/test_oracle_golden.py pins this restatement to them.
+    points [B, V, 2], proj [B, V, 3, 4], bk0 [B, 4], d_out [B, 3] -> d_points [B, V, 2]"""
+    points, proj = np.asarray(points, np.float64), np.asarray(proj, np.float64)
+    A = proj[:, :, 2:3, :] * points[:, :, :, None] - proj[:, :, :2, :]            # [B, V, 2, 4]
+    Af = A.reshape(A.shape[0], -1, 4)
+    Bm = np.einsum("bri,brj->bij", Af, Af) + 0.001 * np.eye(4)[None]
+    bk = np.asarray(bk0, np.float64)
+    ys, bs, invn = [], [], []
+    for _ in range(iterations):
+        y = np.linalg.solve(Bm, bk[:, :, None])[:, :, 0]
+        n = 1.0 / np.sqrt((y * y).sum(1, keepdims=True))
+        bk = y * n
+        ys.append(y); bs.append(bk); invn.append(n)
+    g = np.asarray(d_out, np.float64)
+    w = bk[:, 3:4]
+    db = np.concatenate([g / w, -(g * bk[:, :3]).sum(1, keepdims=True) / (w * w)], axis=1)
+    dB = np.zeros_like(Bm)
+    for it in reversed(range(iterations)):
+        dy = (db - bs[it] * (bs[it] * db).sum(1, keepdims=True)) * invn[it]
+        lam = np.linalg.solve(Bm, dy[:, :, None])[:, :, 0]          # B symmetric: B^-T = B^-1
+        dB -= lam[:, :, None] * ys[it][:, None, :]
+        db = lam
+    S = dB + dB.transpose(0, 2, 1)
+    dA = np.einsum("bij,bvkj->bvki", S, A)                          # d a = (dB + dB^T) a per row
+    return np.einsum("bvki,bvi->bvk", dA, proj[:, :, 2, :]).astype(np.float32)
+
+
 def triangulate_joints(points, proj, bk0, iterations=2):
     """the per-joint loop of AlgebraicTriangulationNet.forward (triangulation.py:258-261):
     points [B, V, J, 2], proj [B, V, 3, 4], bk0 [J, B, 4] -> [B, J, 3]"""

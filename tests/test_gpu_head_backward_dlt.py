@@ -76,3 +76,21 @@ def test_dlt_triangulation_matches_reference_golden(case):
     torch.manual_seed(int(g[case + "/seed"]))
     one = misc.DLT_sii_pytorch(uv[:, :, 0], P)
     assert (one - ref[:, 0]).abs().max().item() < 1e-4 * scale
+
+
+@pytest.mark.parametrize("case", ["mhp4", "two_views", "eight_views_j20"])
+def test_dlt_triangulation_backward_matches_reference_autograd(case):
+    """gradients w.r.t. the 2-D points through hrnb_triangulate_dlt_bwd against the gradients the UNMODIFIED reference's
+    autograd produced through DLT_sii_pytorch (tests/golden/triangulation.npz: d_out, d_points)"""
+    import os
+    import numpy as np
+    from hrnet_b200.utils import misc
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "triangulation.npz"))
+    P, uv, bk0, d_out, ref = (torch.from_numpy(g[case + "/" + k]).cuda() for k in ("proj", "points", "bk0", "d_out", "d_points"))
+    uv = uv.clone().requires_grad_(True)
+    out = misc.triangulate_joints(uv, P, start_vectors=bk0)
+    (out * d_out).sum().backward()
+    scale = ref.abs().max().item()
+    assert (uv.grad - ref).abs().max().item() < 2e-3 * scale
+    with pytest.raises(NotImplementedError):
+        misc.triangulate_joints(uv.detach(), P.clone().requires_grad_(True), start_vectors=bk0)

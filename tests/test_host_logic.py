@@ -166,3 +166,48 @@ def test_grad_allreduce_bucket_bounds_and_cpu_form():
     assert not ar.overlap and ar.mean_scale == 1.0
     t = torch.arange(1000, dtype=torch.float32)
     assert torch.equal(ar(t.clone()), t)          # world 1: identity
+
+
+def test_volumetric_backbone_mirrors_the_reference_module_tree():
+    """row f1: pose_hrnet_volumetric.get_pose_net - same state_dict keys, parameter order and seeded init as the reference
+    (VOL_CONFIDENCES head created between stage4 and last_layer)"""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref_shim.install()
+    from models import pose_hrnet_volumetric as RV
+    from hrnet_b200.models import pose_hrnet_volumetric as OV
+    cfg = ref_shim.load_cfg()
+    cfg.MODEL["ALG_CONFIDENCES"], cfg.MODEL["VOL_CONFIDENCES"], cfg.MODEL["TRAINABLE_SOFTMAX"] = False, True, True
+    torch.manual_seed(0)
+    ref = RV.get_pose_net(cfg, is_train=False)
+    torch.manual_seed(0)
+    ours = OV.get_pose_net(cfg, is_train=False)
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
+    for (k, a), (_, b) in zip(ours.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert all(not n.startswith("vol_confidences") for n, _ in ours.engine_parameters())
+    assert len(ours.engine_parameters()) == len(list(ours.named_parameters())) - len(list(ours.vol_confidences.parameters()))
+    # the reference cannot even construct with ALG_CONFIDENCES: true (NameError at pose_hrnet_volumetric.py:375)
+    cfg.MODEL["ALG_CONFIDENCES"] = True
+    with pytest.raises(NameError):
+        RV.get_pose_net(cfg, is_train=False)
+
+
+def test_algebraic_triangulation_net_host_logic():
+    from hrnet_b200.models.triangulation import AlgebraicTriangulationNet
+    from hrnet_b200.config import make_cfg
+    cfg = make_cfg(32, trainable_softmax=True)
+    cfg.MODEL["BACKBONE_NAME"], cfg.MODEL["ALG_CONFIDENCES"], cfg.MODEL["BACKBONE_MODEL_PATH"] = "pose_hrnet_volumetric", False, ""
+    net = AlgebraicTriangulationNet(cfg)
+    free = {n.split(".")[0] for n, p in net.backbone.named_parameters() if p.requires_grad}
+    assert free == {"stage4", "last_layer"}                  # lib/models/triangulation.py:205-215
+    cfg.MODEL["ALG_CONFIDENCES"] = True
+    net2 = AlgebraicTriangulationNet(cfg)
+    assert hasattr(net2.backbone, "alg_confidences")
+    with pytest.raises(RuntimeError, match="ALG_CONFIDENCES"):
+        net2(torch.zeros(1, 4, 3, 64, 64), torch.zeros(1, 4, 3, 4))
+    cfg.MODEL["BACKBONE_NAME"] = "pose_resnet"
+    with pytest.raises(ValueError, match="BACKBONE_NAME"):
+        AlgebraicTriangulationNet(cfg)

@@ -222,3 +222,48 @@ def test_warm_golden_records_the_reference_trajectory(golden_dir):
     o = train_oracle.train_step(sd, *warm_batch(0, B, H, W), hrnet_oracle.Arch.from_cfg(cfg), "softmax", trainable_temp=True)
     assert np.allclose(o["losses"], g["trajectory"][0], rtol=1e-4)
     assert o["opt_state"] is not None and int(o["state"]["bn1.num_batches_tracked"]) == 1
+
+
+def test_triangulation_adjoint_matches_reference_autograd(golden_dir):
+    """oracle/triangulation_oracle.dlt_sii_backward (the chain the CUDA adjoint kernel follows) against the gradients the
+    unmodified reference's autograd produced through DLT_sii_pytorch"""
+    from oracle import triangulation_oracle as T
+    g = np.load(os.path.join(golden_dir, "triangulation.npz"))
+    for case in ("mhp4", "two_views", "eight_views_j20"):
+        P, uv, bk0, d_out, ref = (g[case + "/" + k] for k in ("proj", "points", "bk0", "d_out", "d_points"))
+        mine = np.stack([T.dlt_sii_backward(uv[:, :, k], P, bk0[k], d_out[:, k]) for k in range(uv.shape[2])], axis=2)
+        assert np.abs(mine - ref).max() < 2e-3 * np.abs(ref).max(), case
+
+
+def test_glue_oracle_matches_reference_golden(golden_dir):
+    """oracle/glue_oracle.py against the outputs of the unmodified reference's HeatmapGenerator, flip_back (+ flip-test merge)
+    and ToTensor + Normalize stored in tests/golden/glue.npz"""
+    from oracle import glue_oracle as G
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    res, sigma = int(g["hm_res"]), int(g["hm_sigma"])
+    for b in range(g["hm_joints"].shape[0]):
+        assert np.array_equal(G.heatmap_generator(g["hm_joints"][b], (res, res), sigma), g["hm_out"][b])
+    assert g["hm_out"][0, 2].max() == 1.0 and g["hm_out"][0, 3].max() == 0.0 and g["hm_out"][0, 5].max() == 0.0   # edge semantics
+    pairs = g["flip_pairs"].tolist()
+    assert np.array_equal(G.flip_back(g["flip_b"], pairs), g["flip_back"])
+    assert np.array_equal(G.flip_test_merge(g["flip_a"], g["flip_b"], pairs, False), g["flip_merge0"])
+    assert np.array_equal(G.flip_test_merge(g["flip_a"], g["flip_b"], pairs, True), g["flip_merge1"])
+    for b in range(2):
+        assert np.allclose(G.normalize_u8(g["norm_img"][b], g["norm_mean"], g["norm_std"]), g["norm_out"][b], atol=1e-6)
+
+
+def test_confidence_head_seeded_init_matches_reference(golden_dir):
+    """the GlobalAveragePoolingHead mirror draws the reference's seeded weights (same construction order) and the oracle
+    restatement reproduces the reference's output from them"""
+    from oracle import glue_oracle as G
+    from hrnet_b200.models.pose_hrnet_volumetric import GlobalAveragePoolingHead
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    torch.manual_seed(5)
+    head = GlobalAveragePoolingHead(64, 32)
+    sd = head.state_dict()
+    for k in sd:
+        if k.endswith(("running_mean", "running_var")):
+            sd[k].copy_(torch.from_numpy(g["gap_stat/" + k]))
+    assert np.isclose(float(sum(v.double().abs().sum() for v in sd.values())), float(g["gap_wsum"]), rtol=1e-9)
+    out = G.gap_head({"h." + k: v for k, v in sd.items()}, "h", torch.from_numpy(g["gap_x"]))
+    assert np.allclose(out.numpy(), g["gap_out"], rtol=1e-5, atol=1e-7)
