@@ -67,7 +67,13 @@ struct ConvK {
   int tap_off[9];         // flat-shift path: row offset of tap t inside an A stage (source * KC * halo + lead + dpos)
   float* stats_sums;      // STATS variant: per-channel (sum, sum of squares) of the conv output over the real positions
   float* stats_ws;        // STATS variant: ticket counter + per-CTA partial sums (hrnb_conv_stats_ws_floats)
+  // LEAN epilogue: exact division by multiplication for n < 2^31, d >= 2: n / d == __umulhi(n, m) >> s (see fast_magic)
+  unsigned mWp, sWp, mHp, sHp, mNt, sNt;
 };
+
+// floor(n / d) for n < 2^31 and the divisor behind (m, s): m = ceil(2^(31 + c) / d), s = c - 1, c = ceil(log2 d) >= 1.
+// Exact: n * m / 2^(31+c) = n/d + n*e/(d * 2^(31+c)) with e = m*d - 2^(31+c) < d <= 2^c, and n*e < 2^(31+c).
+__device__ __forceinline__ unsigned fast_div(unsigned n, unsigned m, unsigned s) { return __umulhi(n, m) >> s; }
 
 // debug timeline: slot = role*64 + 2*tile_iter + {0,1}; written by one lane of CTA 0 only when tracing is on
 #define HRNB_TRACE(role, iter, ev)                                                                   \
@@ -102,7 +108,15 @@ constexpr int kThreadsGather = kThreadsFS + 128;   // + gather producers
 // and every summation order are static, so the statistics are bit-reproducible run to run.
 constexpr int kStatsSlot = 128;   // floats per CTA partial: [column group (<= 4)][sum x16 | sumsq x16]
 constexpr int kStatsMaxCtas = 320;
-template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false>
+// LEAN (flat-shift path, PF8 output, no phase-split output copy - i.e. almost every launch of the network): a specialised
+// epilogue.  The general one below spends ~1,470 instructions per warp and tile on the thin layers (SASS: 8 runtime integer
+// divisions per tile for the row geometry, phase-offset arithmetic and three store variants per 16-column group, cursor
+// bookkeeping of the residual ring); with 16 epilogue warps on 4 schedulers that is ~5,900 issue cycles per tile against
+// ~2,900 tensor-pipe cycles, and conv_bench's debug masks showed the 32-channel 64x64 layers bound by exactly that - not by
+// HBM (no operand loads at all: 62 vs 66 us) and not by TMEM reads.  The lean form: row geometry by multiply-high (fast_div),
+// per-warp item table (TMEM column, output / residual / bias offsets) hoisted out of the persistent loop, at most four items
+// per warp and tile fully unrolled with all residual loads issued before the accumulator wait, packed fp32x2 adds.
+template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false, bool LEAN = false>
 __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ? 1 : kCtasPerSm) conv_tc_kernel(const ConvK k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
@@ -329,6 +343,107 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     for (int i = 0; i < (STATS ? 16 : 1); ++i) st2[i] = 0ull;
     const int E = k.MB * groups;   // groups per tile; this warp takes e = cs, cs + CS, ...
     int it = 0;
+    if constexpr (LEAN) {
+      // ---- per-warp item table: item u = (M block, 16-column group) number cs + u*CS of a tile; MB*BN <= 256 => <= 4 items
+      constexpr int MAXI = 4;
+      uint32_t tcol[MAXI];          // TMEM column of the item inside an accumulator stage
+      long long ooff[MAXI], roff[MAXI];   // element offsets of the item's first plane from the tile's base pointers
+      int boff[MAXI], imb[MAXI];
+      const long long out_g = 2 * k.out_ps * 8, res_g = 2 * k.res_ps * 8;   // two planes per 16-channel group
+#pragma unroll
+      for (int u = 0; u < MAXI; ++u) {
+        const int e = cs + u * CS;
+        int mb = 0, g = e;
+        while (g >= groups) { g -= groups; ++mb; }
+        imb[u] = mb;
+        tcol[u] = (uint32_t)(mb * k.BN + g * 16);
+        ooff[u] = (long long)g * out_g + (long long)mb * 1024;
+        roff[u] = (long long)g * res_g + (long long)mb * 1024;
+        boff[u] = g * 16;
+      }
+      __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(k.out);
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1, aph = (it >> 1) & 1;
+        const unsigned mg = k.n_tiles == 1 ? (unsigned)tile : fast_div((unsigned)tile, k.mNt, k.sNt);
+        const int ntile = tile - (int)mg * k.n_tiles;
+        const unsigned p0 = mg * (unsigned)(k.MB * 128) + (unsigned)(q * 32 + lane);
+        unsigned validm = 0, realm = 0;
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          if (mb < k.MB) {
+            const unsigned p = p0 + (unsigned)(mb * 128);
+            const unsigned rowi = fast_div(p, k.mWp, k.sWp);
+            const unsigned px = p - rowi * (unsigned)k.Wp;
+            const unsigned py = rowi - fast_div(rowi, k.mHp, k.sHp) * (unsigned)k.Hp;
+            if (p < (unsigned)k.P) {
+              validm |= 1u << mb;
+              if (px != 0u && py != 0u) realm |= 1u << mb;
+            }
+          }
+        }
+        const int plane0 = ntile * (k.BN / 8);
+        __nv_bfloat16* const obase = outp + ((long long)plane0 * k.out_ps + p0) * 8;
+        const __nv_bfloat16* const rbase = k.res + ((long long)plane0 * k.res_ps + p0) * 8;
+        const float* const bias_t = bias_s + ntile * k.BN;
+        // residuals of all items of this warp: requested before the accumulator is waited for
+        uint4 rb[MAXI][2];
+#pragma unroll
+        for (int u = 0; u < MAXI; ++u) {
+          rb[u][0] = rb[u][1] = make_uint4(0u, 0u, 0u, 0u);
+          if (has_res && cs + u * CS < E && ((realm >> imb[u]) & 1u)) {
+            rb[u][0] = ldg_nc_v4(rbase + roff[u]);
+            rb[u][1] = ldg_nc_v4(rbase + roff[u] + k.res_ps * 8);
+          }
+        }
+        mbar_wait(&tmem_full[as], aph);
+        tc_fence_after_sync();
+        const uint32_t t_base = lane_base + (uint32_t)(as * acc_cols);
+#pragma unroll
+        for (int u = 0; u < MAXI; ++u) {
+          if (cs + u * CS < E) {
+            uint32_t v[16];
+            tmem_ld16(t_base + tcol[u], v);
+            tmem_ld_wait();
+            const bool valid = (validm >> imb[u]) & 1u, real = (realm >> imb[u]) & 1u;
+            unsigned long long x2[8];      // 8 packed column pairs
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&bias_t[boff[u] + 4 * i]);
+              x2[2 * i] = add_f32x2(pack_f32x2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), pack_f32x2(b4.x, b4.y));
+              x2[2 * i + 1] = add_f32x2(pack_f32x2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), pack_f32x2(b4.z, b4.w));
+            }
+            if constexpr (STATS) {
+              if (real) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  st2[j] = add_f32x2(st2[j], x2[j]);
+                  st2[8 + j] = fma_f32x2(x2[j], x2[j], st2[8 + j]);
+                }
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 r = rb[u][h];
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float lo, hi;
+                unpack_f32x2(add_f32x2(x2[h * 4 + j], pack_f32x2(bf16_lo(rw[j]), bf16_hi(rw[j]))), lo, hi);
+                ow[j] = relu ? pack_bf16x2_relu(lo, hi) : pack_bf16x2(lo, hi);
+              }
+              uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              if (!real) o = make_uint4(0u, 0u, 0u, 0u);      // keep the shared zero padding intact
+              if (valid) *reinterpret_cast<uint4*>(obase + ooff[u] + (long long)h * k.out_ps * 8) = o;
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      }
+    } else
     for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1, aph = (it >> 1) & 1;
       const int mg = tile / k.n_tiles, ntile = tile - mg * k.n_tiles;
@@ -618,6 +733,15 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
 int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 long long* g_trace = nullptr;
 
+// (m, s) of fast_div for divisor d >= 2
+static void fast_magic(unsigned d, unsigned* m, unsigned* s) {
+  unsigned c = 1;
+  while ((1ull << c) < d) ++c;
+  const unsigned long long num = 1ull << (31 + c);
+  *m = (unsigned)((num + d - 1) / d);
+  *s = c - 1;
+}
+
 static int next_pow2_cols(int c) {
   int r = 32;
   while (r < c) r <<= 1;
@@ -698,6 +822,10 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   k->oWp2 = p->W / 2 + 1;
   k->stats_sums = p->stats_sums;
   k->stats_ws = p->stats_ws;
+  fast_magic((unsigned)k->Wp, &k->mWp, &k->sWp);
+  fast_magic((unsigned)k->Hp, &k->mHp, &k->sHp);
+  k->mNt = 0; k->sNt = 0;
+  if (k->n_tiles > 1) fast_magic((unsigned)k->n_tiles, &k->mNt, &k->sNt);
   if (p->stats_sums != nullptr) {
     const int groups = p->BN / 16;
     if (!p->stats_ws || gather || nchw || k->n_tiles != 1 || (groups != 1 && groups != 2 && groups != 4) || p->res != nullptr ||
@@ -795,7 +923,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // per-device launch state: written once per (device, variant), read on every launch, possibly from one host thread per
   // GPU (nn.DataParallel calls forward that way, tools/train.py:254) -> atomics; cudaFuncSetAttribute itself is idempotent
-  static std::atomic<unsigned char> attr_set[64][28] = {};
+  static std::atomic<unsigned char> attr_set[64][56] = {};
   static std::atomic<int> sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -806,18 +934,22 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   const int ks = p->KC / 2;
   int ksi = -1;
   const void* fn = nullptr;
+  // the lean epilogue covers the flat-shift path with a plain PF8 output (no phase-split form or copy)
+  const bool lean = !gather && !nchw_out && k.out_phase_stride == 0 && k.out2 == nullptr && g_debug[3] == 0 && g_debug[0] == 0;
 #define HRNB_PICK(KS, IDX)                                                                                   \
   if (ks == KS) {                                                                                            \
     ksi = IDX;                                                                                               \
     fn = gather ? (const void*)conv_tc_kernel<true, false, KS>                                               \
                 : (nchw_out ? (const void*)conv_tc_kernel<false, true, KS>                                   \
-                            : (stats ? (const void*)conv_tc_kernel<false, false, KS, true>                   \
-                                     : (const void*)conv_tc_kernel<false, false, KS>));                      \
+                            : (lean ? (stats ? (const void*)conv_tc_kernel<false, false, KS, true, true>     \
+                                             : (const void*)conv_tc_kernel<false, false, KS, false, true>)   \
+                                    : (stats ? (const void*)conv_tc_kernel<false, false, KS, true>           \
+                                             : (const void*)conv_tc_kernel<false, false, KS>)));             \
   }
   HRNB_PICK(1, 0) HRNB_PICK(2, 1) HRNB_PICK(3, 2) HRNB_PICK(4, 3) HRNB_PICK(6, 4) HRNB_PICK(8, 5) HRNB_PICK(16, 6)
 #undef HRNB_PICK
   if (!fn) return fail(HRNB_EINVAL, "conv: KC must be one of 2, 4, 6, 8, 12, 16, 32");
-  const int variant = ksi * 4 + (gather ? 2 : (nchw_out ? 1 : (stats ? 3 : 0)));
+  const int variant = ksi * 8 + (gather ? 2 : (nchw_out ? 1 : (stats ? 3 : 0) + (lean ? 4 : 0)));
   if (!attr_set[dev][variant].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "conv: cudaFuncSetAttribute");

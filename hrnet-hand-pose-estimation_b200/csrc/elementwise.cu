@@ -57,10 +57,8 @@ __global__ void __launch_bounds__(256) stem_conv1_kernel(const float* __restrict
   const int plane = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.P) return;
-  const int px = (int)(p % g.Wp);
-  const long long rowi = p / g.Wp;
-  const int py = (int)(rowi % g.Hp);
-  const int n = (int)(rowi / g.Hp);
+  const Pos q_ = decode_pos(g, p);      // 32-bit divisions whenever P fits (geo.cuh)
+  const int px = q_.px, py = q_.py, n = q_.n;
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (px > 0 && py > 0) {
     float acc[8];
@@ -103,10 +101,8 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
                                                          long long out_ps, Geo g, int inH, int inW) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.P) return;
-  const int px = (int)(p % g.Wp);
-  const long long rowi = p / g.Wp;
-  const int py = (int)(rowi % g.Hp);
-  const int n = (int)(rowi / g.Hp);
+  const Pos q_ = decode_pos(g, p);      // 32-bit divisions whenever P fits (geo.cuh)
+  const int px = q_.px, py = q_.py, n = q_.n;
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -145,10 +141,8 @@ __global__ void __launch_bounds__(256) phase_split_kernel(const __nv_bfloat16* _
   const int plane = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.P) return;
-  const int px = (int)(p % g.Wp);
-  const long long rowi = p / g.Wp;
-  const int py = (int)(rowi % g.Hp);
-  const int n = (int)(rowi / g.Hp);
+  const Pos q_ = decode_pos(g, p);      // 32-bit divisions whenever P fits (geo.cuh)
+  const int px = q_.px, py = q_.py, n = q_.n;
   if (px == 0 || py == 0) return;
   const int y = py - 1, x = px - 1;
   const uint4 v = *reinterpret_cast<const uint4*>(src + ((long long)plane * src_ps + p) * 8);
@@ -181,10 +175,8 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseK k) {
   const int plane = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= k.g.P) return;
-  const int px = (int)(p % k.g.Wp);
-  const long long rowi = p / k.g.Wp;
-  const int py = (int)(rowi % k.g.Hp);
-  const int n = (int)(rowi / k.g.Hp);
+  const Pos q_ = decode_pos(k.g, p);      // 32-bit divisions whenever P fits (geo.cuh)
+  const int px = q_.px, py = q_.py, n = q_.n;
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (px > 0 && py > 0) {
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -209,41 +201,49 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseK k) {
 // ------------------------------------------------------------------------------------------------
 // bilinear up-sample (PyTorch upsample_bilinear2d index rules, fp32 index math) PF8 -> PF8
 // ------------------------------------------------------------------------------------------------
+constexpr int kBilPlanes = 4;   // channel planes per thread: the index / weight math of a position is shared by all of them
 __global__ void __launch_bounds__(256) bilinear_kernel(const __nv_bfloat16* __restrict__ src, long long src_ps, Geo sg,
                                                       __nv_bfloat16* __restrict__ dst, long long dst_ps, Geo dg,
-                                                      int align) {
-  const int plane = blockIdx.y;
+                                                      int align, int planes) {
+  const int plane0 = blockIdx.y * kBilPlanes;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= dg.P) return;
-  const int px = (int)(p % dg.Wp);
-  const long long rowi = p / dg.Wp;
-  const int py = (int)(rowi % dg.Hp);
-  const int n = (int)(rowi / dg.Hp);
-  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-  if (px > 0 && py > 0) {
-    int y0, y1, x0, x1;
-    float ly, lx;
+  const Pos q_ = decode_pos(dg, p);
+  const int px = q_.px, py = q_.py, n = q_.n;
+  const bool real = px > 0 && py > 0;
+  int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+  float ly = 0.f, lx = 0.f;
+  if (real) {
     bil_index(py - 1, sg.H, dg.H, align != 0, y0, y1, ly);
     bil_index(px - 1, sg.W, dg.W, align != 0, x0, x1, lx);
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const __nv_bfloat16* base = src + (long long)plane * src_ps * 8;
-    const long long r0 = ((long long)n * sg.Hp + y0 + 1) * sg.Wp, r1 = ((long long)n * sg.Hp + y1 + 1) * sg.Wp;
-    const uint4 v00 = *reinterpret_cast<const uint4*>(base + (r0 + x0 + 1) * 8);
-    const uint4 v01 = *reinterpret_cast<const uint4*>(base + (r0 + x1 + 1) * 8);
-    const uint4 v10 = *reinterpret_cast<const uint4*>(base + (r1 + x0 + 1) * 8);
-    const uint4 v11 = *reinterpret_cast<const uint4*>(base + (r1 + x1 + 1) * 8);
-    const uint32_t* a = &v00.x; const uint32_t* b = &v01.x; const uint32_t* c = &v10.x; const uint32_t* d = &v11.x;
-    uint32_t ow[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      // same association as ATen: hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11)
-      const float lo = hy * (hx * bf16_lo(a[i]) + lx * bf16_lo(b[i])) + ly * (hx * bf16_lo(c[i]) + lx * bf16_lo(d[i]));
-      const float hi = hy * (hx * bf16_hi(a[i]) + lx * bf16_hi(b[i])) + ly * (hx * bf16_hi(c[i]) + lx * bf16_hi(d[i]));
-      ow[i] = pack_bf16x2(lo, hi);
-    }
-    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
-  *reinterpret_cast<uint4*>(dst + ((long long)plane * dst_ps + p) * 8) = o;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const long long r0 = ((long long)n * sg.Hp + y0 + 1) * sg.Wp, r1 = ((long long)n * sg.Hp + y1 + 1) * sg.Wp;
+  const long long o00 = (r0 + x0 + 1) * 8, o01 = (r0 + x1 + 1) * 8, o10 = (r1 + x0 + 1) * 8, o11 = (r1 + x1 + 1) * 8;
+#pragma unroll
+  for (int j = 0; j < kBilPlanes; ++j) {
+    const int plane = plane0 + j;
+    if (plane >= planes) break;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (real) {
+      const __nv_bfloat16* base = src + (long long)plane * src_ps * 8;
+      const uint4 v00 = *reinterpret_cast<const uint4*>(base + o00);
+      const uint4 v01 = *reinterpret_cast<const uint4*>(base + o01);
+      const uint4 v10 = *reinterpret_cast<const uint4*>(base + o10);
+      const uint4 v11 = *reinterpret_cast<const uint4*>(base + o11);
+      const uint32_t* a = &v00.x; const uint32_t* b = &v01.x; const uint32_t* c = &v10.x; const uint32_t* d = &v11.x;
+      uint32_t ow[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // same association as ATen: hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11)
+        const float lo = hy * (hx * bf16_lo(a[i]) + lx * bf16_lo(b[i])) + ly * (hx * bf16_lo(c[i]) + lx * bf16_lo(d[i]));
+        const float hi = hy * (hx * bf16_hi(a[i]) + lx * bf16_hi(b[i])) + ly * (hx * bf16_hi(c[i]) + lx * bf16_hi(d[i]));
+        ow[i] = pack_bf16x2(lo, hi);
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    *reinterpret_cast<uint4*>(dst + ((long long)plane * dst_ps + p) * 8) = o;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,10 +271,8 @@ __global__ void __launch_bounds__(256) nchw_to_pf8_kernel(const float* __restric
   const int plane = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.P) return;
-  const int px = (int)(p % g.Wp);
-  const long long rowi = p / g.Wp;
-  const int py = (int)(rowi % g.Hp);
-  const int n = (int)(rowi / g.Hp);
+  const Pos q_ = decode_pos(g, p);      // 32-bit divisions whenever P fits (geo.cuh)
+  const int px = q_.px, py = q_.py, n = q_.n;
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (px > 0 && py > 0) {
     float v[8];
@@ -371,9 +369,9 @@ extern "C" int hrnb_bilinear_up(const void* src, int64_t src_ps, int32_t N, int3
                                 int64_t dst_ps, int32_t dH, int32_t dW, int32_t align_corners, void* stream) {
   if (!src || !dst || C % 8) return fail(HRNB_EINVAL, "bilinear: bad params");
   const Geo sg = make_geo(N, sH, sW), dg = make_geo(N, dH, dW);
-  dim3 grid((unsigned)((dg.P + 255) / 256), C / 8);
+  dim3 grid((unsigned)((dg.P + 255) / 256), (C / 8 + kBilPlanes - 1) / kBilPlanes);
   bilinear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ps, sg, (__nv_bfloat16*)dst,
-                                                           dst_ps, dg, align_corners);
+                                                           dst_ps, dg, align_corners, C / 8);
   count_launch();
   return check_launch("bilinear_kernel");
 }

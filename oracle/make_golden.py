@@ -333,6 +333,11 @@ def train_conditioned_fixture(name, yaml_rel, variant, B=8, H=128, W=128, warm_s
     for k in TRAIN_KEYS:
         rec["grad/" + k] = fixtures.sample(grads[k]).numpy()
         rec["weight/" + k] = fixtures.sample(cur[k]).numpy()
+        if warm_steps:
+            # fp32 floor of "the weights end up where the reference's did": cosine between the 60-step weight UPDATES of the
+            # reference and of the oracle port (a second fp32 run of the same trajectory)
+            da, db = (osd[k] - sd0[k]).double().reshape(-1), (cur[k] - sd0[k]).double().reshape(-1)
+            rec["update_cos_floor/" + k] = np.array(float((da * db).sum() / (da.norm() * db.norm() + 1e-30)))
     names = sorted(grads)
     rec["all_keys"] = np.array(names)
     rec["gnorm_all"] = np.array([float(grads[k].double().norm()) for k in names])

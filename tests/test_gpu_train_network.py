@@ -395,13 +395,16 @@ def test_loss_trajectory_against_reference(golden_dir):
     # the pose2d term alone (10 % of the total): two fp32 runs of the UNMODIFIED reference (8 vs 3 host threads) already
     # differ by 1.5 % after 16 steps (profiles/r2_reference_self_chaos.txt)
     assert rel[:, 2].max() < 0.15, rel[:, 2].max()
-    # the weights after 60 steps: Adam's first steps move every element by ~lr regardless of the gradient's size, so
-    # compare the UPDATE direction (w_60 - w_0) with the reference's
+    # the weights after 60 steps: Adam's first steps move every element by ~lr whatever the gradient's size, so the UPDATE
+    # direction (w_60 - w_0) is compared, and against the floor two fp32 runs set: the golden stores the cosine between the
+    # reference's update and the oracle port's (a second fp32 run of the same 60 steps): 0.55 (stem) ... 0.71 (last_layer.3) ...
+    # 0.98 (stage 4).  The bf16 path must reach 60 % of that floor on every sampled tensor.
     cur = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-    for k in ("last_layer.3.weight", "last_layer.0.weight", "stage4.2.fuse_layers.0.3.0.weight", "stage2.0.branches.0.0.conv1.weight",
-              "conv2.weight"):
+    for k in ("last_layer.3.weight", "last_layer.0.weight", "stage4.2.fuse_layers.0.3.0.weight", "stage4.0.branches.3.0.conv1.weight",
+              "stage2.0.branches.0.0.conv1.weight", "conv2.weight"):
         d_ref = torch.from_numpy(g["weight/" + k]) - fixtures.sample(sd[k])
         d_got = fixtures.sample(cur[k]) - fixtures.sample(sd[k])
         l2, cos = _cmp(d_got, d_ref)
-        _report("trajectory_update:" + k, rel_l2=l2, cos=cos)
-        assert cos > 0.8, (k, l2, cos)
+        floor = float(g["update_cos_floor/" + k])
+        _report("trajectory_update:" + k, rel_l2=l2, cos=cos, fp32_floor=floor)
+        assert cos > 0.6 * floor, (k, l2, cos, floor)
