@@ -42,6 +42,8 @@ class ConvParams(C.Structure):
         ("out2", C.c_void_p), ("out2_ps", C.c_int64), ("out2_phase_stride", C.c_int64),
         ("ntap_custom", C.c_int32), ("tap_src", C.c_int32 * 9), ("tap_dpos", C.c_int32 * 9),
         ("stats_sums", C.c_void_p), ("stats_ws", C.c_void_p),
+        ("nfuse", C.c_int32), ("fuse_shift", C.c_int32 * 3), ("fuse_src", C.c_void_p * 3), ("fuse_ps", C.c_int64 * 3),
+        ("in_up_shift", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -144,6 +146,7 @@ _SIGS = {
     "hrnb_flip_merge": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "hrnb_maxpool2_relu": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "hrnb_gap_mlp": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "hrnb_axpby": (C.c_int, [C.c_float, _vp, C.c_float, _vp, _vp, _i64, _vp]),
     "hrnb_last_error": (C.c_char_p, []),
     "hrnb_abi_version": (C.c_int, []),
     "hrnb_launch_count": (_i64, []),
@@ -176,7 +179,7 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if h.hrnb_abi_version() != 3:
+        if h.hrnb_abi_version() != 4:
             raise HrnbError("libhrnb.so ABI version mismatch")
         if os.environ.get("HRNB_NO_PDL", "0") == "1":      # debug: launch the conv kernels without programmatic dependent launch
             h.hrnb_debug_set(2, 1)

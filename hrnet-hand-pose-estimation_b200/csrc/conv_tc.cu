@@ -69,6 +69,12 @@ struct ConvK {
   float* stats_ws;        // STATS variant: ticket counter + per-CTA partial sums (hrnb_conv_stats_ws_floats)
   // LEAN epilogue: exact division by multiplication for n < 2^31, d >= 2: n / d == __umulhi(n, m) >> s (see fast_magic)
   unsigned mWp, sWp, mHp, sHp, mNt, sNt;
+  // fuse-layer sum in the epilogue: extra PF8 sources read with nearest up-sampling (include/hrnb.h: nfuse)
+  int nfuse;
+  int fuse_shift[3];
+  const __nv_bfloat16* fuse_src[3];
+  long long fuse_ps[3];
+  int in_up_shift;        // gather 1x1: input read at (y >> s, x >> s)
 };
 
 // floor(n / d) for n < 2^31 and the divisor behind (m, s): m = ceil(2^(31 + c) / d), s = c - 1, c = ceil(log2 d) >= 1.
@@ -422,6 +428,25 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
                 }
               }
             }
+            if (k.nfuse != 0 && real) {
+              // fuse-layer sum: the other branches' contributions, nearest up-sampled on the fly (tiny, L2-resident sources)
+              const unsigned p = p0 + (unsigned)(imb[u] * 128);
+              const unsigned rowi = fast_div(p, k.mWp, k.sWp);
+              const unsigned n = fast_div(rowi, k.mHp, k.sHp);
+              const int x = (int)(p - rowi * (unsigned)k.Wp) - 1, y = (int)(rowi - n * (unsigned)k.Hp) - 1;
+              for (int f = 0; f < k.nfuse; ++f) {
+                const int sh = k.fuse_shift[f];
+                const long long sp = ((long long)n * ((k.H >> sh) + 1) + (y >> sh) + 1) * ((k.W >> sh) + 1) + (x >> sh) + 1;
+                const __nv_bfloat16* fs = k.fuse_src[f] + ((long long)(plane0 + 2 * (boff[u] >> 4)) * k.fuse_ps[f] + sp) * 8;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint4 r = ldg_nc_v4(fs + (long long)h * k.fuse_ps[f] * 8);
+                  const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) x2[h * 4 + j] = add_f32x2(x2[h * 4 + j], pack_f32x2(bf16_lo(rw[j]), bf16_hi(rw[j])));
+                }
+              }
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint4 r = rb[u][h];
@@ -644,6 +669,9 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           pin[mb] = real ? ((long long)n * k.in_Hp + (long long)(py - 1) * k.stride) * k.in_Wp +
                                (long long)(px - 1) * k.stride
                          : -1;
+          // 1x1 conv on a nearest-up-sampled input (in_up_shift): output pixel (y, x) reads input pixel (y >> s, x >> s)
+          if (k.in_up_shift != 0 && real)
+            pin[mb] = ((long long)n * k.in_Hp + ((py - 1) >> k.in_up_shift)) * k.in_Wp + ((px - 1) >> k.in_up_shift);
         }
         for (int c = 0; c < k.nchunks; ++c) {
           for (int t = 0; t < k.taps; ++t, ++it) {
@@ -774,7 +802,12 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   if (p->MB != 1 && p->MB != 2 && p->MB != 4) return fail(HRNB_EINVAL, "conv: MB must be 1, 2 or 4");
   if (p->MB * p->BN > 256) return fail(HRNB_EINVAL, "conv: MB*BN exceeds 256 (two accumulator stages in 512 TMEM columns)");
   if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->cout <= 0) return fail(HRNB_EINVAL, "conv: bad geometry");
-  if (p->in_H != p->H * p->stride || p->in_W != p->W * p->stride) return fail(HRNB_EINVAL, "conv: in_H/in_W must equal H*stride/W*stride");
+  if (p->in_up_shift != 0) {
+    if (!gather || p->taps != 1 || p->stride != 1 || p->in_up_shift < 0 || p->in_up_shift > 3 ||
+        p->in_H != (p->H >> p->in_up_shift) || p->in_W != (p->W >> p->in_up_shift) || (p->H & ((1 << p->in_up_shift) - 1)) ||
+        (p->W & ((1 << p->in_up_shift) - 1)))
+      return fail(HRNB_EINVAL, "conv: in_up_shift needs a gathered 1x1 stride-1 conv with in_H/in_W == H/W >> in_up_shift");
+  } else if (p->in_H != p->H * p->stride || p->in_W != p->W * p->stride) return fail(HRNB_EINVAL, "conv: in_H/in_W must equal H*stride/W*stride");
   const bool nchw = (p->flags & HRNB_CONV_OUT_NCHW) != 0;
   if (!nchw && (p->cout % p->BN)) return fail(HRNB_EINVAL, "conv: PF8 output needs cout % BN == 0");
   k->in = (const __nv_bfloat16*)p->in;
@@ -822,6 +855,21 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   k->oWp2 = p->W / 2 + 1;
   k->stats_sums = p->stats_sums;
   k->stats_ws = p->stats_ws;
+  k->nfuse = p->nfuse;
+  k->in_up_shift = p->in_up_shift;
+  if (p->nfuse < 0 || p->nfuse > 3) return fail(HRNB_EINVAL, "conv: nfuse must be 0..3");
+  for (int f = 0; f < 3; ++f) {
+    k->fuse_src[f] = f < p->nfuse ? (const __nv_bfloat16*)p->fuse_src[f] : nullptr;
+    k->fuse_ps[f] = p->fuse_ps[f];
+    k->fuse_shift[f] = p->fuse_shift[f];
+    if (f < p->nfuse) {
+      const int sh = p->fuse_shift[f];
+      if (!p->fuse_src[f] || sh < 0 || sh > 3 || (p->H & ((1 << sh) - 1)) || (p->W & ((1 << sh) - 1)))
+        return fail(HRNB_EINVAL, "conv: bad fuse source (NULL, or shift not in 0..3 / not dividing H and W)");
+    }
+  }
+  if (p->nfuse > 0 && ((p->flags & (HRNB_CONV_OUT_NCHW | HRNB_CONV_OUT_PHASES)) || p->out2 || p->stats_sums))
+    return fail(HRNB_EINVAL, "conv: fuse sources need a plain PF8 output without fused statistics");
   fast_magic((unsigned)k->Wp, &k->mWp, &k->sWp);
   fast_magic((unsigned)k->Hp, &k->mHp, &k->sHp);
   k->mNt = 0; k->sNt = 0;
@@ -935,11 +983,14 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   int ksi = -1;
   const void* fn = nullptr;
   // the lean epilogue covers the flat-shift path with a plain PF8 output (no phase-split form or copy)
-  const bool lean = !gather && !nchw_out && k.out_phase_stride == 0 && k.out2 == nullptr && g_debug[3] == 0 && g_debug[0] == 0;
+  const bool lean_ok = !nchw_out && k.out_phase_stride == 0 && k.out2 == nullptr;
+  if (k.nfuse > 0 && !lean_ok) return fail(HRNB_EINVAL, "conv: fuse sources need the lean epilogue (plain PF8 output)");
+  const bool lean = lean_ok && ((g_debug[3] == 0 && g_debug[0] == 0) || k.nfuse > 0);
 #define HRNB_PICK(KS, IDX)                                                                                   \
   if (ks == KS) {                                                                                            \
     ksi = IDX;                                                                                               \
-    fn = gather ? (const void*)conv_tc_kernel<true, false, KS>                                               \
+    fn = gather ? (lean ? (const void*)conv_tc_kernel<true, false, KS, false, true>                          \
+                        : (const void*)conv_tc_kernel<true, false, KS>)                                      \
                 : (nchw_out ? (const void*)conv_tc_kernel<false, true, KS>                                   \
                             : (lean ? (stats ? (const void*)conv_tc_kernel<false, false, KS, true, true>     \
                                              : (const void*)conv_tc_kernel<false, false, KS, false, true>)   \
@@ -949,7 +1000,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   HRNB_PICK(1, 0) HRNB_PICK(2, 1) HRNB_PICK(3, 2) HRNB_PICK(4, 3) HRNB_PICK(6, 4) HRNB_PICK(8, 5) HRNB_PICK(16, 6)
 #undef HRNB_PICK
   if (!fn) return fail(HRNB_EINVAL, "conv: KC must be one of 2, 4, 6, 8, 12, 16, 32");
-  const int variant = ksi * 8 + (gather ? 2 : (nchw_out ? 1 : (stats ? 3 : 0) + (lean ? 4 : 0)));
+  const int variant = ksi * 8 + (gather ? (lean ? 6 : 2) : (nchw_out ? 1 : (stats ? 3 : 0) + (lean ? 4 : 0)));
   if (!attr_set[dev][variant].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "conv: cudaFuncSetAttribute");

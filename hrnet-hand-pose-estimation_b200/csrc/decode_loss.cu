@@ -58,14 +58,23 @@ __device__ __forceinline__ void block_argmax(const float* __restrict__ m, int hw
   int bi = 0x7fffffff;
   const int nvec = hw >> 2;
   const float4* m4 = reinterpret_cast<const float4*>(m);
-  for (int i = threadIdx.x; i < nvec; i += kThreads) {
-    const float4 v = __ldg(m4 + i);
-    const int b = i << 2;
-    // strictly-greater keeps the first occurrence inside a thread (indices visited in increasing order)
-    if (v.x > bv) { bv = v.x; bi = b; }
-    if (v.y > bv) { bv = v.y; bi = b + 1; }
-    if (v.z > bv) { bv = v.z; bi = b + 2; }
-    if (v.w > bv) { bv = v.w; bi = b + 3; }
+  // four independent 16-byte loads in flight per thread before the first comparison (a 64 x 64 map is exactly one round)
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * kThreads) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * kThreads;
+      v[j] = i < nvec ? __ldg(m4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = (i0 + j * kThreads) << 2;
+      // strictly-greater keeps the first occurrence inside a thread (indices visited in increasing order)
+      if (v[j].x > bv) { bv = v[j].x; bi = b; }
+      if (v[j].y > bv) { bv = v[j].y; bi = b + 1; }
+      if (v[j].z > bv) { bv = v[j].z; bi = b + 2; }
+      if (v[j].w > bv) { bv = v[j].w; bi = b + 3; }
+    }
   }
   for (int i = (nvec << 2) + threadIdx.x; i < hw; i += kThreads) {
     const float v = __ldg(m + i);
@@ -187,6 +196,64 @@ __global__ void __launch_bounds__(kThreads) softmax_softargmax_kernel(const floa
   }
 }
 
+// Register form of the kernel above for maps of up to NV * 1024 elements with w % 4 == 0 (64 x 64: NV = 4, 96 x 72: NV = 7): every
+// thread keeps its NV float4 in registers across the three phases (max, exp + sum, normalise + expectation), so the map is read
+// from HBM once, written once and never staged in shared memory; exp through ex2.approx (__expf, 2 ulp), one reciprocal per map.
+template <int NV>
+__global__ void __launch_bounds__(kThreads) softmax_softargmax_reg_kernel(const float* __restrict__ logits,
+                                                                         const float* __restrict__ temp_dev, int h, int w,
+                                                                         float* __restrict__ heat_out,
+                                                                         float* __restrict__ coords) {
+  __shared__ float red[kWarps];
+  const int hw = h * w, nvec = hw >> 2;
+  const int map = blockIdx.x;
+  const float temp = temp_dev ? __ldg(temp_dev) : 1.f;
+  const float4* src = reinterpret_cast<const float4*>(logits + (long long)map * hw);
+  float4 v[NV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + j * kThreads;
+    if (i < nvec) {
+      float4 t = __ldg(src + i);
+      t.x *= temp; t.y *= temp; t.z *= temp; t.w *= temp;
+      v[j] = t;
+      mx = fmaxf(fmaxf(mx, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+    } else {
+      v[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+  }
+  mx = block_max(mx, red);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j].x = __expf(v[j].x - mx); v[j].y = __expf(v[j].y - mx); v[j].z = __expf(v[j].z - mx); v[j].w = __expf(v[j].w - mx);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  s = block_sum(s, red);
+  const float inv = 1.f / s;
+  float sx = 0.f, sy = 0.f;
+  float4* dst = heat_out ? reinterpret_cast<float4*>(heat_out + (long long)map * hw) : nullptr;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = threadIdx.x + j * kThreads;
+    if (i < nvec) {
+      const float4 p = make_float4(v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
+      if (dst) dst[i] = p;
+      const int e = i << 2;
+      const int y = e / w, x = e - y * w;          // w % 4 == 0: the four elements share a row
+      const float fx = (float)x;
+      sx += (p.x * fx + p.y * (fx + 1.f)) + (p.z * (fx + 2.f) + p.w * (fx + 3.f));
+      sy = fmaf((p.x + p.y) + (p.z + p.w), (float)y, sy);
+    }
+  }
+  if (coords) {
+    sx = block_sum(sx, red);
+    sy = block_sum(sy, red);
+    if (threadIdx.x == 0) { coords[2 * map] = sx; coords[2 * map + 1] = sy; }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) softargmax_kernel(const float* __restrict__ hm, int h, int w,
                                                              float* __restrict__ coords) {
   __shared__ float red[kWarps];
@@ -194,11 +261,33 @@ __global__ void __launch_bounds__(kThreads) softargmax_kernel(const float* __res
   const int map = blockIdx.x;
   const float* src = hm + (long long)map * hw;
   float sx = 0.f, sy = 0.f;
-  for (int i = threadIdx.x; i < hw; i += kThreads) {
-    const float p = __ldg(src + i);
-    const int y = i / w, x = i - y * w;
-    sx = fmaf(p, (float)x, sx);
-    sy = fmaf(p, (float)y, sy);
+  if ((w & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // 16-byte loads, four in flight per thread; one row/column split per float4 (its elements share a row)
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    const int nvec = hw >> 2;
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * kThreads) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * kThreads;
+        v[j] = i < nvec ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = (i0 + j * kThreads) << 2;
+        const int y = e / w, x = e - y * w;
+        const float fx = (float)x;
+        sx += (v[j].x * fx + v[j].y * (fx + 1.f)) + (v[j].z * (fx + 2.f) + v[j].w * (fx + 3.f));
+        sy = fmaf((v[j].x + v[j].y) + (v[j].z + v[j].w), (float)y, sy);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < hw; i += kThreads) {
+      const float p = __ldg(src + i);
+      const int y = i / w, x = i - y * w;
+      sx = fmaf(p, (float)x, sx);
+      sy = fmaf(p, (float)y, sy);
+    }
   }
   sx = block_sum(sx, red);
   sy = block_sum(sy, red);
@@ -252,18 +341,31 @@ __global__ void __launch_bounds__(kThreads) heatmap_loss_partial_kernel(const fl
   const float gs = (grad_scale_dev ? __ldg(grad_scale_dev) : 1.f) * inv_bj;
   float acc = 0.f;
   const long long nvec = n >> 2;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(pred) + i);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(gt) + i);
-    const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
-    if (mode == 0) {
-      acc += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-      if (d_pred) reinterpret_cast<float4*>(d_pred)[i] = make_float4(2.f * d0 * gs, 2.f * d1 * gs, 2.f * d2 * gs, 2.f * d3 * gs);
-    } else {
-      acc += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
-      if (d_pred) {
-        auto sg = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
-        reinterpret_cast<float4*>(d_pred)[i] = make_float4(sg(d0) * gs, sg(d1) * gs, sg(d2) * gs, sg(d3) * gs);
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x; i0 < nvec; i0 += 2 * stride) {
+    // two independent (pred, gt) pairs in flight per thread
+    float4 a[2], b[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const long long i = i0 + j * stride;
+      const bool in = i < nvec;
+      a[j] = in ? __ldg(reinterpret_cast<const float4*>(pred) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      b[j] = in ? __ldg(reinterpret_cast<const float4*>(gt) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const long long i = i0 + j * stride;
+      if (i >= nvec) break;
+      const float d0 = a[j].x - b[j].x, d1 = a[j].y - b[j].y, d2 = a[j].z - b[j].z, d3 = a[j].w - b[j].w;
+      if (mode == 0) {
+        acc += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        if (d_pred) reinterpret_cast<float4*>(d_pred)[i] = make_float4(2.f * d0 * gs, 2.f * d1 * gs, 2.f * d2 * gs, 2.f * d3 * gs);
+      } else {
+        acc += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+        if (d_pred) {
+          auto sg = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+          reinterpret_cast<float4*>(d_pred)[i] = make_float4(sg(d0) * gs, sg(d1) * gs, sg(d2) * gs, sg(d3) * gs);
+        }
       }
     }
   }
@@ -360,6 +462,17 @@ extern "C" int hrnb_softmax_softargmax(const float* logits, const float* temp_de
   const size_t smem = (size_t)h * w * sizeof(float);
   if (smem > 200 * 1024) return fail(HRNB_EINVAL, "softmax_softargmax: map too large for shared memory");
   if ((reinterpret_cast<uintptr_t>(logits) & 15) || ((h * w) & 3)) return fail(HRNB_EINVAL, "softmax_softargmax: maps must be 16-byte aligned with h*w % 4 == 0");
+  const int nvec = (h * w) >> 2;
+  if ((w & 3) == 0 && nvec <= 8 * kThreads && (heat_out == nullptr || (reinterpret_cast<uintptr_t>(heat_out) & 15) == 0)) {
+    // register-resident form: 64 x 64 maps (4 float4 per thread), 96 x 72 (7), up to 8192 elements (8)
+    const int nv = (nvec + kThreads - 1) / kThreads;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nv <= 4) softmax_softargmax_reg_kernel<4><<<BJ, kThreads, 0, st>>>(logits, temp_dev, h, w, heat_out, coords);
+    else if (nv <= 7) softmax_softargmax_reg_kernel<7><<<BJ, kThreads, 0, st>>>(logits, temp_dev, h, w, heat_out, coords);
+    else softmax_softargmax_reg_kernel<8><<<BJ, kThreads, 0, st>>>(logits, temp_dev, h, w, heat_out, coords);
+    count_launch();
+    return check_launch("softmax_softargmax_reg_kernel");
+  }
   int rc = set_smem((const void*)softmax_softargmax_kernel, smem);
   if (rc) return rc;
   softmax_softargmax_kernel<<<BJ, kThreads, smem, (cudaStream_t)stream>>>(logits, temp_dev, h, w, heat_out, coords);

@@ -181,9 +181,34 @@ __global__ void __launch_bounds__(256) gap_mlp_kernel(const GapMlpK k) {
   }
 }
 
+// out = a * x + b * y over n floats (float4 main loop): the weighted view fusion of Aggregation.fuse_with_weights
+__global__ void __launch_bounds__(256) axpby_kernel(float a, const float* __restrict__ x, float b, const float* __restrict__ y,
+                                                   float* __restrict__ out, long long n) {
+  const long long nvec = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(x) + i), v = __ldg(reinterpret_cast<const float4*>(y) + i);
+    reinterpret_cast<float4*>(out)[i] = make_float4(a * u.x + b * v.x, a * u.y + b * v.y, a * u.z + b * v.z, a * u.w + b * v.w);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (nvec << 2) + threadIdx.x; i < n; i += blockDim.x) out[i] = a * x[i] + b * y[i];
+}
+
 }  // namespace hrnb
 
 using namespace hrnb;
+
+extern "C" int hrnb_axpby(float a, const float* x, float b, const float* y, float* out, int64_t n, void* stream) {
+  if (!x || !y || !out || n < 0) return fail(HRNB_EINVAL, "axpby: bad params");
+  if (n == 0) return HRNB_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail(HRNB_EINVAL, "axpby: buffers must be 16-byte aligned");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  axpby_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, x, b, y, out, (long long)n);
+  count_launch();
+  return check_launch("axpby_kernel");
+}
 
 extern "C" int hrnb_gen_heatmaps(const float* joints, int32_t joint_stride, int32_t BJ, int32_t h, int32_t w, float sigma,
                                  float* out, void* stream) {

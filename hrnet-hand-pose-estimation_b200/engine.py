@@ -91,9 +91,9 @@ class Plan:
         self._op(sid, fn, name)
         return dst
 
-    def _conv(self, sid, layer, x, out, res=None, name="", out2=None):
+    def _conv(self, sid, layer, x, out, res=None, name="", out2=None, fuse=None, relu=None, up_shift=0):
         layer.no_pdl = not self.engine.pdl
-        p = layer.params(x, out, res, out2=out2)
+        p = layer.params(x, out, res, out2=out2, fuse=fuse, relu=relu, up_shift=up_shift)
         self.keep.append(p)
         lib = _lib.lib()
         ref = C.byref(p)
@@ -118,6 +118,40 @@ class Plan:
             _lib.check(lib.hrnb_fuse_sum(ref, _lib.stream_ptr()))
         self._op(sid, fn, name)
         return out
+
+    def _down_chain(self, pre, i, j, t, ch, res_hw, last_kw=None):
+        """fuse_layers.i.j for j < i: (i - j) stride-2 3x3 convs from branch j's phase-split output `t`; intermediate outputs
+        are written as phases by the conv epilogue itself.  last_kw: extra arguments of the LAST conv (fuse-sum host)"""
+        L, e = self.engine.layers, self.engine
+        for k in range(i - j):
+            fp = "%s.fuse_layers.%d.%d.%d.0" % (pre, i, j, k)
+            last = k == i - j - 1
+            co = ch[i] if last else ch[j]
+            if last and last_kw is not None:
+                return self._conv(i, L[fp], t, name=fp, **last_kw)
+            dst = self._buf(co, *res_hw[j + k + 1]) if last else self._phases(co, *res_hw[j + k + 1])
+            t = self._conv(i, L[fp], t, dst, name=fp)
+        return t
+
+    def _fuse_in_epilogue(self, pre, i, nb, xs, split, dst, ch, res_hw):
+        """Fuse output i = ReLU(sum_j f_ij(x_j)) (lib/models/pose_hrnet.py:199-207,257-266) WITHOUT a separate sum pass: one
+        of the output's own convolutions is the host of the sum - its epilogue adds the identity branch (residual input) and
+        the other contributions (nearest up-sampled on the fly) and applies the ReLU.  Host: the single-step stride-2 conv
+        from branch i-1 (i >= 1); for i = 0, which has no stride-2 chain, the 1x1 conv from branch 1 evaluated on the 64x64
+        grid with its input up-sampled (1x1 conv and nearest up-sampling commute)."""
+        L = self.engine.layers
+        fuse = []
+        for j in range(nb):
+            if j > i and not (i == 0 and j == 1):
+                fp = "%s.fuse_layers.%d.%d.0" % (pre, i, j)
+                fuse.append((self._conv(i, L[fp], xs[j], self._buf(ch[i], *res_hw[j]), name=fp), j - i))
+            elif j < i - 1:
+                fuse.append((self._down_chain(pre, i, j, split[j], ch, res_hw), 0))
+        if i == 0:
+            fp = "%s.fuse_layers.0.1.0" % pre
+            return self._conv(0, L[fp], xs[1], dst, res=xs[0], name=fp + "+fuse", fuse=fuse, relu=True, up_shift=1)
+        return self._down_chain(pre, i, i - 1, split[i - 1], ch, res_hw,
+                                last_kw=dict(out=dst, res=xs[i], fuse=fuse, relu=True))
 
     # ---- the network -------------------------------------------------------------------------------
     def _build(self):
@@ -193,6 +227,14 @@ class Plan:
                         self._wait(i, j)
                 outs = []
                 for i in range(nb):
+                    if last_module and i == 0:
+                        cat = self._buf(arch.head_channels, *res_hw[0])
+                        dst = cat.view_planes(0, ch[0] // 8)
+                    else:
+                        dst = self._buf(ch[i], *res_hw[i])
+                    if e.fuse_epilogue:
+                        outs.append(self._fuse_in_epilogue(pre, i, nb, xs, split, dst, ch, res_hw))
+                        continue
                     srcs, shifts = [], []
                     for j in range(nb):
                         if j == i:
@@ -202,20 +244,7 @@ class Plan:
                             z = self._conv(i, L[fp], xs[j], self._buf(ch[i], *res_hw[j]), name=fp)
                             srcs.append(z); shifts.append(j - i)
                         else:
-                            t = split[j]
-                            for k in range(i - j):
-                                fp = "%s.fuse_layers.%d.%d.%d.0" % (pre, i, j, k)
-                                last = k == i - j - 1
-                                co = ch[i] if last else ch[j]
-                                # intermediate chain outputs are written as phases by the conv epilogue itself
-                                dst = self._buf(co, *res_hw[j + k + 1]) if last else self._phases(co, *res_hw[j + k + 1])
-                                t = self._conv(i, L[fp], t, dst, name=fp)
-                            srcs.append(t); shifts.append(0)
-                    if last_module and i == 0:
-                        cat = self._buf(arch.head_channels, *res_hw[0])
-                        dst = cat.view_planes(0, ch[0] // 8)
-                    else:
-                        dst = self._buf(ch[i], *res_hw[i])
+                            srcs.append(self._down_chain(pre, i, j, split[j], ch, res_hw)); shifts.append(0)
                     outs.append(self._fuse(i, srcs, shifts, dst, name="%s.fuse.%d" % (pre, i)))
                 # the next module's branch j reads outs[j], produced on stream j: no extra sync needed;
                 # the fuse kernels of other streams still read the old xs, which are distinct buffers.
@@ -326,6 +355,9 @@ class HRNetEngine:
         # programmatic dependent launch of the conv kernels: default on since the round-2 soak (train.py); neutral for the
         # graph-replayed inference plan (13.12 vs 13.13 ms at batch 256), kept on so both engines run one launch mode.  HRNB_PDL=0: off
         self.pdl = os.environ.get("HRNB_PDL", "1") != "0"
+        # fuse-layer sums inside the epilogue of one of the output's own convs (no separate fuse_sum pass, no second trip of the
+        # summed tensor through HBM); HRNB_FUSE_EPILOGUE=0 restores the stand-alone sum kernel
+        self.fuse_epilogue = os.environ.get("HRNB_FUSE_EPILOGUE", "1") != "0"
         with torch.cuda.device(self.device):
             _lib.hang_init()
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]

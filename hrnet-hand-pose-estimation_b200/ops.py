@@ -278,13 +278,15 @@ class ConvLayer:
             custom = (max(0, max(dps)) - min(0, min(dps)), max(s_ for s_, _ in self.custom_taps) + 1)
         return H, W, P, mode, custom
 
-    def params(self, x, out, res=None, mb=None, bn=None, kc=None, out2=None):
+    def params(self, x, out, res=None, mb=None, bn=None, kc=None, out2=None, fuse=None, relu=None, up_shift=0):
         """launch parameters; the tile shape (BN, MB, KC) comes from the caller, else from the autotuner (measured on the
         device the first time a shape is seen, like the reference's cudnn.benchmark = True, tools/train.py:128), else from
         the cycle model"""
+        if up_shift:
+            return self._fuse_host_up(x, out, res, fuse, relu, up_shift)
         H, W, P, mode, custom = self._geometry(x)
         forced = mb is not None or bn is not None or kc is not None or self.fixed_bn is not None
-        if not forced and autotune_enabled():
+        if not forced and autotune_enabled() and not fuse:
             tile = autotune_conv(self, x, out, res, out2)
             if tile is not None:
                 return self._build_params(x, out, res, out2, *tile)
@@ -300,7 +302,46 @@ class ConvLayer:
                 if _smem_bytes(W, self.taps, mode, bn, mb, cand, custom) <= 200 * 1024:
                     kc = cand
                     break
-        return self._build_params(x, out, res, out2, bn, mb, kc)
+        p = self._build_params(x, out, res, out2, bn, mb, kc)
+        return self._attach_fuse(p, fuse, relu)
+
+    @staticmethod
+    def _attach_fuse(p, fuse, relu):
+        """fuse: [(PF8 source, shift)] added in the epilogue with nearest up-sampling (include/hrnb.h: nfuse); relu: override
+        of the layer's ReLU flag (the fuse-layer host conv applies the ReLU of the sum, pose_hrnet.py:266)"""
+        if fuse:
+            assert len(fuse) <= 3
+            p.nfuse = len(fuse)
+            for i, (src, sh) in enumerate(fuse):
+                assert src.C == p.cout and src.H == p.H >> sh and src.W == p.W >> sh, (src.C, src.H, src.W, sh)
+                p.fuse_src[i], p.fuse_ps[i], p.fuse_shift[i] = src.ptr, src.ps, sh
+            p._keep_fuse = [s_ for s_, _ in fuse]
+        if relu is not None:
+            p.flags = (p.flags | HRNB_CONV_RELU) if relu else (p.flags & ~HRNB_CONV_RELU)
+        return p
+
+    def _fuse_host_up(self, x, out, res, fuse, relu, up_shift):
+        """1x1 conv evaluated on the grid of `out` with its input read through nearest up-sampling by 2^up_shift (gather
+        path): the host convolution of the highest-resolution fuse output (include/hrnb.h: in_up_shift)"""
+        assert self.taps == 1 and self.stride == 1 and x.H == out.H >> up_shift and x.W == out.W >> up_shift
+        H, W = out.H, out.W
+        P = x.N * (H + 1) * (W + 1)
+        bn, mb, kc = pick_tile(P, W, self.cin, self.cout, 1, 2, res is not None, self.fixed_kc)
+        wpk, bias = self.pack(bn, kc)
+        p = ConvParams()
+        p.inp, p.in_ps = x.ptr, x.ps
+        p.wpk, p.bias = wpk.data_ptr(), bias.data_ptr()
+        p.res, p.res_ps = (res.ptr, res.ps) if res is not None else (None, 0)
+        p.out, p.out_ps = out.ptr, out.ps
+        p.N, p.H, p.W, p.in_H, p.in_W = x.N, H, W, x.H, x.W
+        p.cin, p.cout, p.taps, p.stride = self.cin, self.cout, 1, 1
+        p.KC, p.BN, p.MB = kc, bn, mb
+        p.flags = self.flags | HRNB_CONV_GATHER | (_lib.HRNB_CONV_NO_PDL if self.no_pdl else 0)
+        p.in_up_shift = up_shift
+        p._keep = (wpk, bias)
+        while p.MB > 1 and _lib.lib().hrnb_conv_smem_bytes(C.byref(p)) < 0:
+            p.MB //= 2
+        return self._attach_fuse(p, fuse, relu)
 
     def _build_params(self, x, out, res, out2, bn, mb, kc, temporary=False):
         in_ph, out_ph = isinstance(x, PhasePF8), isinstance(out, PhasePF8)
@@ -341,11 +382,11 @@ class ConvLayer:
             p.MB //= 2          # tile does not fit in shared memory at this MB
         return p
 
-    def __call__(self, x, out, res=None, mb=None, bn=None, out2=None, stats=None):
+    def __call__(self, x, out, res=None, mb=None, bn=None, out2=None, stats=None, fuse=None, relu=None, up_shift=0):
         """stats: fp32 [cout, 2] tensor -> the launch also writes the BatchNorm batch statistics (sum, sum of squares per
         channel) of `out`; raises when the launch is not eligible (see attach_stats)"""
         assert x.C == self.cin, (x.C, self.cin)
-        p = self.params(x, out, res, mb, bn, out2=out2)
+        p = self.params(x, out, res, mb, bn, out2=out2, fuse=fuse, relu=relu, up_shift=up_shift)
         if stats is not None and not attach_stats(p, stats):
             raise ValueError("conv launch not eligible for fused BatchNorm statistics (BN=%d cout=%d flags=%d)" % (p.BN, p.cout, p.flags))
         _lib.check(_lib.lib().hrnb_conv(C.byref(p), _lib.stream_ptr()))

@@ -29,7 +29,7 @@ extern "C" {
 #define HRNB_EINVAL (-1)  /* bad argument / unsupported shape */
 #define HRNB_ECUDA (-2)   /* CUDA runtime error (message in hrnb_last_error) */
 
-#define HRNB_ABI_VERSION 3
+#define HRNB_ABI_VERSION 4
 
 /* guard bands (in positions) a PF8 plane must carry around [0, P) */
 #define HRNB_GUARD_LEAD(Wp) ((((Wp) + 2) + 7) / 8 * 8)
@@ -95,6 +95,21 @@ typedef struct hrnb_conv_params {
    * once, not shared between launches that may run concurrently. */
   float* stats_sums;
   float* stats_ws;
+  /* Fuse-layer sum inside the epilogue (inference; replaces the summation loop + nn.Upsample(nearest) + ReLU of
+   * HighResolutionModule.forward, lib/models/pose_hrnet.py:199-207,257-266): after bias and `res`, the epilogue adds nfuse
+   * (0..3) further PF8 tensors, source f given on the grid [N, H >> fuse_shift[f], W >> fuse_shift[f]] and read with nearest
+   * up-sampling (fuse_shift 0: same grid, e.g. the output of another stride-2 chain).  Flat-shift or gather path with a
+   * plain PF8 output; no fused statistics. */
+  int32_t nfuse;
+  int32_t fuse_shift[3];
+  const void* fuse_src[3];
+  int64_t fuse_ps[3];
+  /* HRNB_CONV_GATHER 1x1 convs only: the input tensor lives on the grid [N, H >> in_up_shift, W >> in_up_shift] and is read
+   * with nearest up-sampling, i.e. the conv runs on the up-sampled grid (1x1 conv and nearest up-sampling commute).  This is
+   * how the fuse sum of the highest-resolution branch, which has no stride-2 chain of its own, gets a host convolution.
+   * in_H / in_W are then H >> in_up_shift / W >> in_up_shift. */
+  int32_t in_up_shift;
+  int32_t pad_;
 } hrnb_conv_params;
 
 int hrnb_conv(const hrnb_conv_params* p, void* stream);
@@ -385,6 +400,11 @@ int hrnb_maxpool2_relu(const void* src, int64_t src_ps, int32_t N, int32_t C, in
 int hrnb_gap_mlp(const void* x, int64_t x_ps, int32_t N, int32_t C, int32_t H, int32_t W, const float* w1, const float* b1,
                  int32_t H1, const float* w2, const float* b2, int32_t H2, const float* w3, const float* b3, int32_t NC,
                  float* out, void* stream);
+
+/* Cross-view fusion: out = a * x + b * y over n fp32 values - Aggregation.fuse_with_weights
+ * (lib/models/multiview_pose_hrnet.py:51-55) after the ChannelWiseFC GEMMs (:15-29), which run as hrnb_conv launches with
+ * the flattened heat map as the channel axis. */
+int hrnb_axpby(float a, const float* x, float b, const float* y, float* out, int64_t n, void* stream);
 
 /* ---- misc --------------------------------------------------------------------------------------- */
 const char* hrnb_last_error(void);

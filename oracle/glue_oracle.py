@@ -76,3 +76,22 @@ def gap_head(sd, prefix, x):
     x = F.relu(F.linear(x, sd[p + "head.0.weight"], sd[p + "head.0.bias"]))
     x = F.relu(F.linear(x, sd[p + "head.2.weight"], sd[p + "head.2.bias"]))
     return torch.sigmoid(F.linear(x, sd[p + "head.4.weight"], sd[p + "head.4.bias"]))
+
+
+def aggregation(fc_weights, inputs, weights=(0.4, 0.2, 0.2, 0.2)):
+    """lib/models/multiview_pose_hrnet.py:32-71 - fc_weights: the 12 (= V*(V-1)) [size, size] nn.Linear weights in module order,
+    inputs: V tensors [N, C, H, W]; -> V fused tensors (target first, then the other views in order, FC index running)"""
+    outs, index = [], 0
+    V = len(inputs)
+    for i in range(V):
+        views = [inputs[i]] + [inputs[j] for j in range(V) if j != i]
+        warped = [views[0]]
+        for j in range(1, V):
+            N, C, H, W = views[j].shape
+            warped.append(F.linear(views[j].reshape(N * C, H * W), fc_weights[index]).reshape(N, C, H, W))
+            index += 1
+        t = torch.zeros_like(views[0])
+        for v, w in zip(warped, weights):
+            t = t + v * w
+        outs.append(t)
+    return outs

@@ -463,6 +463,19 @@ def glue_fixture():
     for k in sorted(sd):
         if k.endswith(("running_mean", "running_var")):
             rec["gap_stat/" + k] = sd[k].numpy()
+    # ---- cross-view fusion (row f2): the reference's Aggregation on 8 x 8 heat maps (12 FC layers of 64 x 64) ----
+    from models.multiview_pose_hrnet import Aggregation
+    torch.manual_seed(9)
+    ag = Aggregation(ref_shim.to_attr({"MODEL": {"HEATMAP_SIZE": [8, 8]}})).eval()
+    views = [torch.rand(2, 5, 8, 8, generator=g) for _ in range(4)]
+    with torch.no_grad():
+        fused = ag(views)
+    mine = G.aggregation([m_.weight.weight.detach() for m_ in ag.aggre], views)
+    for a_, b_ in zip(fused, mine):
+        assert torch.allclose(a_, b_, rtol=1e-5, atol=1e-6)
+    rec.update(agg_views=np.stack([v.numpy() for v in views]), agg_out=np.stack([f.numpy() for f in fused]),
+               agg_wsum=np.array(float(sum(m_.weight.weight.double().abs().sum() for m_ in ag.aggre))),
+               agg_keys=np.array(list(ag.state_dict().keys())))
     np.savez_compressed(os.path.join(GOLD, "glue.npz"), **rec)
     print("glue ok; oracle == reference (heat maps, flip_back / merge, normalisation, confidence head)")
 

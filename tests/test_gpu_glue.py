@@ -134,3 +134,23 @@ def test_algebraic_triangulation_net_forward_and_backward():
     assert gl is not None and torch.isfinite(gl).all() and float(gl.abs().max()) > 0
     assert net.backbone.stage4[0].branches[0][0].conv1.weight.grad is not None
     assert net.backbone.conv1.weight.grad is None
+
+
+@pytest.mark.parametrize("size,B", [(16, 3), (64, 2)])
+def test_cross_view_aggregation_matches_oracle(size, B):
+    """row f2: Aggregation (12 ChannelWiseFC GEMMs + weighted fusion) on the tcgen05 GEMM path against the fp32 oracle
+    (pinned to the reference's Aggregation by make_golden); 64 x 64 heat maps = the 4096 x 4096 layers of the MHP configs"""
+    from oracle import glue_oracle as G
+    from hrnet_b200.models.multiview_pose_hrnet import Aggregation
+    torch.manual_seed(3)
+    ag = Aggregation({"MODEL": {"HEATMAP_SIZE": [size, size]}}).cuda().eval()
+    gen_ = torch.Generator().manual_seed(4)
+    views = [torch.softmax(torch.randn(B, 21, size * size, generator=gen_) * 3, -1).view(B, 21, size, size) for _ in range(4)]
+    ref = G.aggregation([m.weight.weight.detach().cpu() for m in ag.aggre], views)
+    with torch.no_grad():
+        out = ag([v.cuda() for v in views])
+    for a, b in zip(out, ref):
+        assert a.shape == b.shape
+        assert (a.cpu() - b).abs().max().item() <= 2e-2 * b.abs().max().item()
+    with pytest.raises(NotImplementedError):
+        ag.train()([v.cuda() for v in views])

@@ -317,3 +317,89 @@ def test_stem_im2col_then_1x1_equals_conv1():
     ConvLayer(w32, None, b, relu=True)(cols, out)
     ref = F.relu(F.conv2d(_bf16(x), _bf16(w), b, stride=2, padding=1))
     assert (out.to_nchw() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,stride,shifts", [
+    (2, 32, 32, 32, 64, 3, 2, (1, 2)),          # stage-4 output 1: host = stride-2 conv from branch 0, + up-sampled branches 2, 3
+    (2, 16, 16, 64, 128, 3, 2, (0, 1)),         # output 2: + another chain's output (same grid) + up-sampled branch 3
+    (3, 8, 8, 128, 256, 3, 2, (0, 0)),          # output 3: + two other chains
+    (2, 16, 24, 64, 64, 3, 1, (0, 1, 3)),       # three sources on a stride-1 host, non-square
+])
+def test_conv_with_fuse_sources_in_the_epilogue(N, H, W, cin, cout, k, stride, shifts):
+    """include/hrnb.h nfuse: out = ReLU(conv(x) + bias + res + sum_f nearest_up(src_f)) in one launch - the fuse-layer sum of
+    HighResolutionModule.forward (lib/models/pose_hrnet.py:257-266) inside the epilogue of the output's own stride-2 conv"""
+    from hrnet_b200.ops import ConvLayer, PF8, PhasePF8, phase_split
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(N, cin, H * stride, W * stride, device="cuda", generator=g)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5
+    scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(cout, device="cuda", generator=g) * 0.1
+    res = torch.randn(N, cout, H, W, device="cuda", generator=g)
+    srcs = [torch.randn(N, cout, H >> s, W >> s, device="cuda", generator=g) for s in shifts]
+    layer = ConvLayer(w, scale, shift, stride=stride, relu=False)
+    xp = PF8.from_nchw(x)
+    if stride == 2:
+        ph = PhasePF8(N, cin, H * 2, W * 2)
+        phase_split(xp, ph)
+        xp = ph
+    out = PF8(N, cout, H, W)
+    out.buf.fill_(7.0); out.buf[:, :out.lead] = 0; out.buf[:, out.lead + out.P:] = 0
+    layer(xp, out, PF8.from_nchw(res), fuse=[(PF8.from_nchw(t), s) for t, s in zip(srcs, shifts)], relu=True)
+    ref = F.conv2d(_bf16(x), _bf16(w * scale.view(-1, 1, 1, 1)), None, stride=stride, padding=k // 2) + shift.view(1, -1, 1, 1)
+    ref = ref + _bf16(res)
+    for t, s in zip(srcs, shifts):
+        ref = ref + F.interpolate(_bf16(t), scale_factor=2 ** s, mode="nearest") if s else ref + _bf16(t)
+    ref = F.relu(ref)
+    torch.cuda.synchronize()
+    assert out.padding_is_zero()
+    assert (out.to_nchw() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,up,shifts", [(2, 64, 64, 64, 32, 1, (2, 3)), (2, 32, 32, 128, 64, 1, ()), (1, 32, 48, 96, 48, 2, (1,))])
+def test_1x1_conv_on_upsampled_input_hosts_the_fuse_sum(N, H, W, cin, cout, up, shifts):
+    """include/hrnb.h in_up_shift: the fuse output of the highest-resolution branch - the 1x1 conv from the next branch
+    evaluated on the fine grid (input read through nearest up-sampling), identity as residual, other up paths as fuse sources"""
+    from hrnet_b200.ops import ConvLayer, PF8
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(N, cin, H >> up, W >> up, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 1, 1, device="cuda", generator=g) / cin ** 0.5
+    scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(cout, device="cuda", generator=g) * 0.1
+    res = torch.randn(N, cout, H, W, device="cuda", generator=g)
+    srcs = [torch.randn(N, cout, H >> s, W >> s, device="cuda", generator=g) for s in shifts]
+    layer = ConvLayer(w, scale, shift, relu=False)
+    out = PF8(N, cout, H, W)
+    out.buf.fill_(7.0); out.buf[:, :out.lead] = 0; out.buf[:, out.lead + out.P:] = 0
+    layer(PF8.from_nchw(x), out, PF8.from_nchw(res), fuse=[(PF8.from_nchw(t), s) for t, s in zip(srcs, shifts)], relu=True,
+          up_shift=up)
+    z = F.conv2d(_bf16(x), _bf16(w * scale.view(-1, 1, 1, 1))) + shift.view(1, -1, 1, 1)
+    ref = F.interpolate(z, scale_factor=2 ** up, mode="nearest") + _bf16(res)
+    for t, s in zip(srcs, shifts):
+        ref = ref + F.interpolate(_bf16(t), scale_factor=2 ** s, mode="nearest")
+    ref = F.relu(ref)
+    torch.cuda.synchronize()
+    assert out.padding_is_zero()
+    assert (out.to_nchw() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_fuse_in_epilogue_plan_equals_stand_alone_sum_plan():
+    """whole network: the inference plan with the fuse sums inside conv epilogues against the plan with fuse_sum kernels"""
+    import os
+    from oracle import fixtures
+    from hrnet_b200.config import make_cfg
+    from hrnet_b200.models import pose_hrnet_softmax
+    outs = []
+    for flag in ("1", "0"):
+        os.environ["HRNB_FUSE_EPILOGUE"] = flag
+        try:
+            torch.manual_seed(0)
+            m = pose_hrnet_softmax.get_pose_net(make_cfg(32), is_train=False)
+            sd = m.state_dict(); fixtures.perturb_state_dict(sd); m.load_state_dict(sd)
+            m = m.cuda().eval()
+            h, f, _ = m(fixtures.images(2, 128, 128).cuda())
+            outs.append((h.clone(), f.clone(), m.engine().plan(2, 128, 128).launches(False)))
+        finally:
+            os.environ.pop("HRNB_FUSE_EPILOGUE", None)
+    assert outs[0][2] < outs[1][2]                                  # 26 fuse_sum launches gone
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 4e-2 * outs[1][1].abs().max().item()
+    assert (outs[0][0] - outs[1][0]).abs().max().item() <= 2e-2 * outs[1][0].abs().max().item()

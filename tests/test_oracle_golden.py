@@ -267,3 +267,19 @@ def test_confidence_head_seeded_init_matches_reference(golden_dir):
     assert np.isclose(float(sum(v.double().abs().sum() for v in sd.values())), float(g["gap_wsum"]), rtol=1e-9)
     out = G.gap_head({"h." + k: v for k, v in sd.items()}, "h", torch.from_numpy(g["gap_x"]))
     assert np.allclose(out.numpy(), g["gap_out"], rtol=1e-5, atol=1e-7)
+
+
+def test_cross_view_aggregation_oracle_and_seeded_init_match_reference(golden_dir):
+    """row f2: the Aggregation mirror has the reference's state-dict keys and seeded weights; the oracle restatement reproduces
+    the reference's fused views from them"""
+    from oracle import glue_oracle as G
+    from hrnet_b200.models.multiview_pose_hrnet import Aggregation
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    torch.manual_seed(9)
+    ag = Aggregation({"MODEL": {"HEATMAP_SIZE": [8, 8]}})
+    assert list(ag.state_dict().keys()) == [str(k) for k in g["agg_keys"]]
+    assert np.isclose(float(sum(m.weight.weight.double().abs().sum() for m in ag.aggre)), float(g["agg_wsum"]), rtol=1e-9)
+    views = [torch.from_numpy(v) for v in g["agg_views"]]
+    outs = G.aggregation([m.weight.weight.detach() for m in ag.aggre], views)
+    for a, b in zip(outs, g["agg_out"]):
+        assert np.allclose(a.numpy(), b, rtol=1e-5, atol=1e-6)
