@@ -151,7 +151,9 @@ struct BnK {
 };
 
 // y = [relu]( gamma*(c-mean)*invstd + beta [+ res] ), zeros at padding; block (0, plane) also updates the running stats
-__device__ __forceinline__ void bn_apply_body(const BnK& k, int plane, unsigned bx) {
+constexpr int kApplyPos = 4;     // positions per thread of bn_apply
+constexpr int kBwdApplyPos = 1;  // positions per thread of bn_bwd_apply
+__device__ __forceinline__ void bn_apply_body(const BnK& k, int plane, unsigned nb, unsigned bx) {
   __shared__ float sa[8], sb[8];
   if (threadIdx.x < 8) {
     const int ch = plane * 8 + threadIdx.x;
@@ -168,33 +170,45 @@ __device__ __forceinline__ void bn_apply_body(const BnK& k, int plane, unsigned 
     }
   }
   __syncthreads();
-  const long long p = (long long)bx * blockDim.x + threadIdx.x;
-  if (p >= k.g.P) return;
-  const Pos q = decode_pos(k.g, p);
-  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-  if (q.px > 0 && q.py > 0) {
-    float x[8];
-    unpack8(ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8), x);
+  // kApplyPos positions per thread, one block-stride apart (lanes stay on consecutive positions): all loads of a thread are
+  // issued before the first use, and a plane needs 4x fewer blocks - at batch 64 these kernels are latency-, not bandwidth-bound
+  uint4 rc[kApplyPos], rr[kApplyPos];
+  const long long stride = (long long)nb * blockDim.x;
+  const long long p0 = (long long)bx * blockDim.x + threadIdx.x;
+  const __nv_bfloat16* cb = k.c + (long long)plane * k.c_ps * 8;
+  const __nv_bfloat16* rbase = k.res != nullptr ? k.res + (long long)plane * k.res_ps * 8 : nullptr;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], sa[i], sb[i]);
-    if (k.res != nullptr) {
-      float r[8];
-      unpack8(ldg_nc_v4(k.res + ((long long)plane * k.res_ps + p) * 8), r);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] += r[i];
-    }
-    if (k.relu) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
-    }
-    o = pack8(x);
+  for (int u = 0; u < kApplyPos; ++u) {
+    const long long p = p0 + u * stride;
+    const bool in = p < k.g.P;
+    rc[u] = in ? ldg_nc_v4(cb + p * 8) : make_uint4(0u, 0u, 0u, 0u);
+    rr[u] = (in && rbase != nullptr) ? ldg_nc_v4(rbase + p * 8) : make_uint4(0u, 0u, 0u, 0u);
   }
-  *reinterpret_cast<uint4*>(k.out + ((long long)plane * k.out_ps + p) * 8) = o;
+#pragma unroll
+  for (int u = 0; u < kApplyPos; ++u) {
+    const long long p = p0 + u * stride;
+    if (p >= k.g.P) break;
+    const Pos q = decode_pos(k.g, p);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (q.px > 0 && q.py > 0) {
+      float x[8], r[8];
+      unpack8(rc[u], x);
+      unpack8(rr[u], r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], sa[i], sb[i]) + r[i];
+      if (k.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+      }
+      o = pack8(x);
+    }
+    *reinterpret_cast<uint4*>(k.out + ((long long)plane * k.out_ps + p) * 8) = o;
+  }
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnK k) {
   pdl_enter();
-  bn_apply_body(k, (int)blockIdx.y, blockIdx.x);
+  bn_apply_body(k, (int)blockIdx.y, gridDim.x, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdK k) {
 }
 
 // dc = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dres (+)= g; block (0, plane) writes dgamma / dbeta
-__device__ __forceinline__ void bn_bwd_apply_body(const BnBwdK& k, int plane, unsigned bx) {
+__device__ __forceinline__ void bn_bwd_apply_body(const BnBwdK& k, int plane, unsigned nb, unsigned bx) {
   __shared__ float sm[8], si[8], sa[8], s0[8], s1[8];
   if (threadIdx.x < 8) {
     const int ch = plane * 8 + threadIdx.x;
@@ -291,38 +305,55 @@ __device__ __forceinline__ void bn_bwd_apply_body(const BnBwdK& k, int plane, un
     }
   }
   __syncthreads();
-  const long long p = (long long)bx * blockDim.x + threadIdx.x;
-  if (p >= k.g.P) return;
-  const Pos q = decode_pos(k.g, p);
-  const bool real = q.px > 0 && q.py > 0;
-  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-  uint4 gres = make_uint4(0u, 0u, 0u, 0u);
-  if (real) {
-    float g[8], x[8];
-    unpack8(*reinterpret_cast<const uint4*>(k.dy + ((long long)plane * k.dy_ps + p) * 8), g);
-    unpack8(ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8), x);
-    if (k.relu) relu_mask8(g, ldg_nc_v4(k.y + ((long long)plane * k.y_ps + p) * 8));
-    if (k.dres_mode == 2) {
-      float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8), r);
+  // kBwdApplyPos positions per thread; up to four independent 16-byte loads per position [4 positions measured SLOWER than 1 on
+  // B200: 64 registers of loads in flight cost more occupancy than they hide latency: 12.4 % -> 13.9 % of the serial step]
+  const long long stride = (long long)nb * blockDim.x;
+  const long long p0 = (long long)bx * blockDim.x + threadIdx.x;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 rg[kBwdApplyPos], rx[kBwdApplyPos], ry[kBwdApplyPos], rd[kBwdApplyPos];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] += g[i];
-      gres = pack8(r);
-    } else if (k.dres_mode == 1) {
-      gres = pack8(g);
-    }
-    float d[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = sa[i] * (g[i] - s0[i] - (x[i] - sm[i]) * si[i] * s1[i]);
-    o = pack8(d);
+  for (int u = 0; u < kBwdApplyPos; ++u) {
+    const long long p = p0 + u * stride;
+    const bool in = p < k.g.P;
+    rg[u] = in ? *reinterpret_cast<const uint4*>(k.dy + ((long long)plane * k.dy_ps + p) * 8) : z4;
+    rx[u] = in ? ldg_nc_v4(k.c + ((long long)plane * k.c_ps + p) * 8) : z4;
+    ry[u] = (in && k.relu) ? ldg_nc_v4(k.y + ((long long)plane * k.y_ps + p) * 8) : z4;
+    rd[u] = (in && k.dres_mode == 2) ? *reinterpret_cast<const uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8) : z4;
   }
-  *reinterpret_cast<uint4*>(k.dc + ((long long)plane * k.dc_ps + p) * 8) = o;
-  if (k.dres_mode != 0) *reinterpret_cast<uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8) = gres;
+#pragma unroll
+  for (int u = 0; u < kBwdApplyPos; ++u) {
+    const long long p = p0 + u * stride;
+    if (p >= k.g.P) break;
+    const Pos q = decode_pos(k.g, p);
+    const bool real = q.px > 0 && q.py > 0;
+    uint4 o = z4, gres = z4;
+    if (real) {
+      float g[8], x[8];
+      unpack8(rg[u], g);
+      unpack8(rx[u], x);
+      if (k.relu) relu_mask8(g, ry[u]);
+      if (k.dres_mode == 2) {
+        float r[8];
+        unpack8(rd[u], r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] += g[i];
+        gres = pack8(r);
+      } else if (k.dres_mode == 1) {
+        gres = pack8(g);
+      }
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = sa[i] * (g[i] - s0[i] - (x[i] - sm[i]) * si[i] * s1[i]);
+      o = pack8(d);
+    }
+    *reinterpret_cast<uint4*>(k.dc + ((long long)plane * k.dc_ps + p) * 8) = o;
+    if (k.dres_mode != 0) *reinterpret_cast<uint4*>(k.dres + ((long long)plane * k.dres_ps + p) * 8) = gres;
+  }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdK k) {
   pdl_enter();
-  bn_bwd_apply_body(k, (int)blockIdx.y, blockIdx.x);
+  bn_bwd_apply_body(k, (int)blockIdx.y, gridDim.x, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -372,7 +403,7 @@ __global__ void __launch_bounds__(256) bn_apply_batch_kernel(const BnBatchK b) {
   int j, plane;
   unsigned bx;
   batch_locate(b.blk0_app, b.nb_app, b.n, j, plane, bx);
-  bn_apply_body(b.k[j], plane, bx);
+  bn_apply_body(b.k[j], plane, b.nb_app[j], bx);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_batch_kernel(const BnBwdBatchK b) {
@@ -388,7 +419,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_batch_kernel(const BnBwdBatc
   int j, plane;
   unsigned bx;
   batch_locate(b.blk0_app, b.nb_app, b.n, j, plane, bx);
-  bn_bwd_apply_body(b.k[j], plane, bx);
+  bn_bwd_apply_body(b.k[j], plane, b.nb_app[j], bx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -710,6 +741,8 @@ __global__ void __launch_bounds__(256) grad_to_natural_kernel(const float* __res
 
 using namespace hrnb;
 
+static unsigned apply_blocks_host(long long P) { return (unsigned)((P + 256 * kApplyPos - 1) / (256 * kApplyPos)); }
+static unsigned bwd_apply_blocks_host(long long P) { return (unsigned)((P + 256 * kBwdApplyPos - 1) / (256 * kBwdApplyPos)); }
 static unsigned reduce_blocks(long long P) {
   long long b = (P + 256 * 2 - 1) / (256 * 2);   // ~2 positions per thread (the kernels are latency bound on small maps)
   if (b < 1) b = 1;
@@ -761,7 +794,7 @@ extern "C" int hrnb_bn_apply(const hrnb_bn_params* p, void* stream) {
   k.g = make_geo(p->N, p->H, p->W);
   k.relu = p->relu; k.eps = p->eps; k.momentum = p->momentum;
   k.count = (float)((long long)p->N * p->H * p->W);
-  dim3 grid((unsigned)((k.g.P + 255) / 256), p->C / 8);
+  dim3 grid(apply_blocks_host(k.g.P), p->C / 8);
   launch_pdl(bn_apply_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("bn_apply_kernel");
@@ -799,7 +832,7 @@ extern "C" int hrnb_bn_bwd_apply(const hrnb_bn_bwd_params* p, void* stream) {
   const int rc = make_bwd(p, &k);
   if (rc) return rc;
   if (!p->dc) return fail(HRNB_EINVAL, "bn_bwd_apply: dc missing");
-  dim3 grid((unsigned)((k.g.P + 255) / 256), p->C / 8);
+  dim3 grid(bwd_apply_blocks_host(k.g.P), p->C / 8);
   launch_pdl(bn_bwd_apply_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
   return check_launch("bn_bwd_apply_kernel");
@@ -833,7 +866,7 @@ extern "C" int hrnb_bn_forward_batch(const hrnb_bn_params* p, int32_t n, float* 
     b.sums_out[j] = const_cast<float*>(p[j].sums);
     b.plane0[j + 1] = b.plane0[j] + p[j].C / 8;
     b.nb_red[j] = reduce_blocks(b.k[j].g.P);
-    b.nb_app[j] = (unsigned)((b.k[j].g.P + 255) / 256);
+    b.nb_app[j] = apply_blocks_host(b.k[j].g.P);
     b.blk0_red[j + 1] = b.blk0_red[j] + b.nb_red[j] * (unsigned)(p[j].C / 8);
     b.blk0_app[j + 1] = b.blk0_app[j] + b.nb_app[j] * (unsigned)(p[j].C / 8);
     if (!((have_stats_mask >> j) & 1)) {
@@ -872,7 +905,7 @@ extern "C" int hrnb_bn_backward_batch(const hrnb_bn_bwd_params* p, int32_t n, vo
     if (p[j].ws != p[0].ws) return fail(HRNB_EINVAL, "bn_backward_batch: one reduction workspace per launch");
     b.plane0[j + 1] = b.plane0[j] + p[j].C / 8;
     b.nb_red[j] = reduce_blocks(b.k[j].g.P);
-    b.nb_app[j] = (unsigned)((b.k[j].g.P + 255) / 256);
+    b.nb_app[j] = bwd_apply_blocks_host(b.k[j].g.P);
     b.blk0_red[j + 1] = b.blk0_red[j] + b.nb_red[j] * (unsigned)(p[j].C / 8);
     b.blk0_app[j + 1] = b.blk0_app[j] + b.nb_app[j] * (unsigned)(p[j].C / 8);
   }

@@ -338,7 +338,8 @@ class Plan:
             self._run_steps(want_features, u8)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: nn.DataParallel threads capture / launch on other devices at the same time
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._run_steps(want_features, u8)
             self.graph[key] = g
         self.graph[key].replay()

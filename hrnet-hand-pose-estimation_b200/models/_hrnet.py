@@ -128,6 +128,10 @@ class PoseHighResolutionNet(nn.Module):
         self._tensors = None
         self._train_engine = None
         self._train_key = None
+        # nn.DataParallel (the reference's default wrapper, tools/train.py:250-254) replicates the module on every forward and
+        # calls the replicas from one thread per GPU: replicas share this dict by reference (replicate() copies __dict__
+        # shallowly), so every device keeps ONE engine across calls, keyed by the ORIGINAL module's parameter versions
+        self._shared = {"orig": self, "engines": {}}
         self._train_epoch = 0         # bumped by the training engine on every train-mode forward / step (stale-fold guard)
         self.return_features = True   # set False to skip materialising the NCHW fp32 feature output
         self.feat_requires_grad = False   # True: loss.backward() may flow through the returned feature tensor (train mode)
@@ -158,6 +162,7 @@ class PoseHighResolutionNet(nn.Module):
 
     def invalidate(self):
         """Drop the packed weights (call after mutating parameters in place)."""
+        self._shared["engines"].clear()
         self._engine = None
         self._engine_key = None
         self._tensors = None
@@ -187,6 +192,8 @@ class PoseHighResolutionNet(nn.Module):
 
     def engine(self):
         from ..engine import HRNetEngine
+        if getattr(self, "_is_replica", False):
+            return self._replica_engine()
         key = self._param_versions()
         if self._engine is None or self._engine_key != key:
             dev = next(self.parameters()).device
@@ -196,6 +203,31 @@ class PoseHighResolutionNet(nn.Module):
             self._engine = HRNetEngine(sd, self.arch, self.variant, dev)
             self._engine_key = key
         return self._engine
+
+    def _replica_engine(self):
+        """engine of a DataParallel replica: cached per device on the original module (self._shared), rebuilt when the
+        original's parameters changed; built from THIS replica's (broadcast) tensors, on this replica's device"""
+        from ..engine import HRNetEngine
+        orig = self._shared["orig"]
+        key = orig._param_versions() if orig is not None else None
+        # replicas hold their (broadcast, non-leaf) parameters in _former_parameters; .parameters() / state_dict() are empty
+        sd = {}
+        for mod_name, mod in self.named_modules():
+            prefix = mod_name + "." if mod_name else ""
+            for k, v in getattr(mod, "_former_parameters", {}).items():
+                sd[prefix + k] = v.detach()
+            for k, v in mod._parameters.items():
+                if v is not None:
+                    sd[prefix + k] = v.detach()
+            for k, v in mod._buffers.items():
+                if v is not None:
+                    sd[prefix + k] = v
+        dev = sd["conv1.weight"].device
+        entry = self._shared["engines"].get(dev)
+        if entry is None or entry[0] != key or key is None:
+            entry = (key, HRNetEngine(sd, self.arch, self.variant, dev))
+            self._shared["engines"][dev] = entry
+        return entry[1]
 
     def train_engine(self, **kw):
         """the CUDA training engine of this module (created on first use; parameters become views of its flat fp32
@@ -217,6 +249,10 @@ class PoseHighResolutionNet(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("input must be a CUDA tensor (no CPU fallback)")
         if self.training:
+            if getattr(self, "_is_replica", False):
+                raise RuntimeError("training under nn.DataParallel is not supported by the B200 engine (it owns flat parameter / "
+                                   "optimizer buffers per process): launch one process per GPU (torchrun), as bench.py does; "
+                                   "model.eval() forward under nn.DataParallel is supported")
             params = [p for _, p in self.engine_parameters()]
             out, feat = _TrainForward.apply(self, x, *params)
             feat = feat if self.return_features else None

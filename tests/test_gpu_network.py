@@ -157,3 +157,31 @@ def test_streaming_predictor_matches_direct_calls():
     assert len(outs) == 5
     for a, b in zip(outs, direct):
         assert torch.equal(a, b)
+
+
+def test_data_parallel_replicas_share_one_engine_per_device():
+    """nn.DataParallel (the reference's default wrapper, tools/train.py:250-254) replicates the module on every forward; the
+    replicas must find the per-device engine of the ORIGINAL module instead of re-packing the weights on every call, must
+    read their (non-leaf, broadcast) parameters, and must refuse to train.  (Replica logic on one device, called in turn;
+    the concurrent one-thread-per-GPU form runs in tests/test_gpu_multi.py on two devices.)"""
+    from torch.nn.parallel import replicate
+    from oracle import fixtures
+    m, _, _ = _model(32, "softmax")
+    m = m.cuda()
+    x = fixtures.images(2, 128, 128).cuda()
+    ref = m(x)[0].clone()
+    built = []
+    for _ in range(2):
+        reps = replicate(m, [0, 0])
+        for r in reps:
+            assert len(list(r.parameters())) == 0            # what torch does to replicas: the engine must not rely on it
+            assert torch.equal(r(x)[0], ref)
+        built.append(id(m._shared["engines"][torch.device("cuda", 0)][1]))
+    assert built[0] == built[1]
+    with torch.no_grad():
+        m.last_layer[3].bias.add_(1.0)                       # parameter change on the original -> replicas re-pack
+    reps = replicate(m, [0])
+    assert not torch.equal(reps[0](x)[0], ref)
+    assert id(m._shared["engines"][torch.device("cuda", 0)][1]) != built[0]
+    with pytest.raises(RuntimeError, match="DataParallel"):
+        replicate(m.train(), [0])[0](x)
