@@ -555,7 +555,8 @@ def run_b200_train(args):
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert float(lo) == float(hi), "ranks start from different weights"
-        allreduce = GradAllReduce(eng.flat.grads.numel(), device=dev)
+        # HRNB_AR_OVERLAP=0: one collective over the whole buffer after the backward graph (the round-1 form), for A/B runs
+        allreduce = GradAllReduce(eng.flat.grads.numel(), device=dev if os.environ.get("HRNB_AR_OVERLAP", "1") != "0" else None)
         eng.flat.set_grad_scale(allreduce.mean_scale)
     plan = eng.plan(B, H, W)
     pool = []
