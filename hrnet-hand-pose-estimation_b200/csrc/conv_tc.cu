@@ -186,6 +186,10 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       const size_t b_elems = k.b_stage_bytes / 2;
       bool b_prefetched = false;
+      // RESIDENT WEIGHTS: a layer whose whole weight tensor is one stage (one K chunk, one N tile - the 32- and 64-channel
+      // 3x3 layers) loads it once per CTA instead of once per tile: -30 % shared-memory fill traffic on the thinnest layers
+      // and one ring stage instead of three, which is what lets two CTAs share an SM there (hrnb_conv: per_sm)
+      const bool wres = k.nchunks == 1 && k.n_tiles == 1;
       if ((int)blockIdx.x < k.num_tiles && !(k.dbg & 16)) {   // first weight stage of the first tile, ahead of the wait
         const int nt0 = (int)blockIdx.x % k.n_tiles;
         if (elect_one_sync()) {
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
             // time-out of round 1 (programmatic dependent launch / extra streams; profiles/r1_hang_records_*.txt: only
             // producer warps of 1-tile conv CTAs stuck on empty_b[0], parity 1).
             b_prefetched = false;
-          } else {
+          } else if (!wres || tile == (int)blockIdx.x) {
             mbar_wait(&empty_b[b_stage], b_phase ^ 1);
             if (k.dbg & 16) {
               if (elect_one_sync()) mbar_arrive(&full_b[b_stage]);
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           }
           __syncwarp();
           wsrc += b_elems;
-          if (++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
+          if (!wres && ++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
           if (c == k.nchunks - 1) HRNB_TRACE(0, pit, 1);
         }
       }
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       const uint32_t b_tap16 = (uint32_t)(k.KC * k.BN);                 // one tap's weight tile in 16-byte units
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       int it = 0;
+      const bool wres = k.nchunks == 1 && k.n_tiles == 1;   // resident weights (see the producer)
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1, aph = (it >> 1) & 1;
         HRNB_TRACE(1, it, 0);
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           // one wait per chunk for the A halo (flat-shift) and for the weights of all taps: every wait / commit
           // stalls the tensor pipe (~100-140 cycles each, measured), so hand-offs are per chunk, not per tap
           if (!GATHER) mbar_wait(&full_a[a_stage], a_phase);
-          mbar_wait(&full_b[b_stage], b_phase);
+          if (!wres || it == 0) mbar_wait(&full_b[b_stage], b_phase);
           tc_fence_after_sync();
           if (c == 0) HRNB_TRACE(2, it, 1);
           uint32_t b_lo_tap = b_lo_ring + (uint32_t)b_stage * b_stage16;
@@ -316,10 +321,10 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           }
           __syncwarp();
           if (elect_one_sync()) {
-            umma_commit(&empty_b[b_stage]);
+            if (!wres) umma_commit(&empty_b[b_stage]);
             if (!GATHER) umma_commit(&empty_a[a_stage]);
           }
-          if (++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
+          if (!wres && ++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
           if (!GATHER) {
             if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
           }
@@ -392,30 +397,56 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
         __nv_bfloat16* const obase = outp + ((long long)plane0 * k.out_ps + p0) * 8;
         const __nv_bfloat16* const rbase = k.res + ((long long)plane0 * k.res_ps + p0) * 8;
         const float* const bias_t = bias_s + ntile * k.BN;
+        // With 16 epilogue warps a warp owns <= 4 items of a tile (ROUNDS == 1); with 8 warps (two CTAs per SM) up to 8: a second
+        // round over items 4..7, whose table entries are recomputed instead of being held in registers.
+        constexpr int ROUNDS = (16 + MAXI * CS - 1) / (MAXI * CS);
+        const uint32_t t_base = lane_base + (uint32_t)(as * acc_cols);
+#pragma unroll
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+        if (rd > 0 && cs + rd * MAXI * CS >= E) break;
+        uint32_t tcol_r[MAXI];
+        long long ooff_r[MAXI], roff_r[MAXI];
+        int boff_r[MAXI], imb_r[MAXI];
+#pragma unroll
+        for (int u = 0; u < MAXI; ++u) {
+          if (rd == 0) {
+            tcol_r[u] = tcol[u]; ooff_r[u] = ooff[u]; roff_r[u] = roff[u]; boff_r[u] = boff[u]; imb_r[u] = imb[u];
+          } else {
+            const int e = cs + (u + rd * MAXI) * CS;
+            int mb = 0, g = e;
+            while (g >= groups) { g -= groups; ++mb; }
+            imb_r[u] = mb;
+            tcol_r[u] = (uint32_t)(mb * k.BN + g * 16);
+            ooff_r[u] = (long long)g * out_g + (long long)mb * 1024;
+            roff_r[u] = (long long)g * res_g + (long long)mb * 1024;
+            boff_r[u] = g * 16;
+          }
+        }
         // residuals of all items of this warp: requested before the accumulator is waited for
         uint4 rb[MAXI][2];
 #pragma unroll
         for (int u = 0; u < MAXI; ++u) {
           rb[u][0] = rb[u][1] = make_uint4(0u, 0u, 0u, 0u);
-          if (has_res && cs + u * CS < E && ((realm >> imb[u]) & 1u)) {
-            rb[u][0] = ldg_nc_v4(rbase + roff[u]);
-            rb[u][1] = ldg_nc_v4(rbase + roff[u] + k.res_ps * 8);
+          if (has_res && cs + (u + rd * MAXI) * CS < E && ((realm >> imb_r[u]) & 1u)) {
+            rb[u][0] = ldg_nc_v4(rbase + roff_r[u]);
+            rb[u][1] = ldg_nc_v4(rbase + roff_r[u] + k.res_ps * 8);
           }
         }
-        mbar_wait(&tmem_full[as], aph);
-        tc_fence_after_sync();
-        const uint32_t t_base = lane_base + (uint32_t)(as * acc_cols);
+        if (rd == 0) {
+          mbar_wait(&tmem_full[as], aph);
+          tc_fence_after_sync();
+        }
 #pragma unroll
         for (int u = 0; u < MAXI; ++u) {
-          if (cs + u * CS < E) {
+          if (cs + (u + rd * MAXI) * CS < E) {
             uint32_t v[16];
-            tmem_ld16(t_base + tcol[u], v);
+            tmem_ld16(t_base + tcol_r[u], v);
             tmem_ld_wait();
-            const bool valid = (validm >> imb[u]) & 1u, real = (realm >> imb[u]) & 1u;
+            const bool valid = (validm >> imb_r[u]) & 1u, real = (realm >> imb_r[u]) & 1u;
             unsigned long long x2[8];      // 8 packed column pairs
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b4 = *reinterpret_cast<const float4*>(&bias_t[boff[u] + 4 * i]);
+              const float4 b4 = *reinterpret_cast<const float4*>(&bias_t[boff_r[u] + 4 * i]);
               x2[2 * i] = add_f32x2(pack_f32x2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), pack_f32x2(b4.x, b4.y));
               x2[2 * i + 1] = add_f32x2(pack_f32x2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), pack_f32x2(b4.z, b4.w));
             }
@@ -430,14 +461,14 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
             }
             if (k.nfuse != 0 && real) {
               // fuse-layer sum: the other branches' contributions, nearest up-sampled on the fly (tiny, L2-resident sources)
-              const unsigned p = p0 + (unsigned)(imb[u] * 128);
+              const unsigned p = p0 + (unsigned)(imb_r[u] * 128);
               const unsigned rowi = fast_div(p, k.mWp, k.sWp);
               const unsigned n = fast_div(rowi, k.mHp, k.sHp);
               const int x = (int)(p - rowi * (unsigned)k.Wp) - 1, y = (int)(rowi - n * (unsigned)k.Hp) - 1;
               for (int f = 0; f < k.nfuse; ++f) {
                 const int sh = k.fuse_shift[f];
                 const long long sp = ((long long)n * ((k.H >> sh) + 1) + (y >> sh) + 1) * ((k.W >> sh) + 1) + (x >> sh) + 1;
-                const __nv_bfloat16* fs = k.fuse_src[f] + ((long long)(plane0 + 2 * (boff[u] >> 4)) * k.fuse_ps[f] + sp) * 8;
+                const __nv_bfloat16* fs = k.fuse_src[f] + ((long long)(plane0 + 2 * (boff_r[u] >> 4)) * k.fuse_ps[f] + sp) * 8;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   const uint4 r = ldg_nc_v4(fs + (long long)h * k.fuse_ps[f] * 8);
@@ -460,9 +491,10 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
               }
               uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
               if (!real) o = make_uint4(0u, 0u, 0u, 0u);      // keep the shared zero padding intact
-              if (valid) *reinterpret_cast<uint4*>(obase + ooff[u] + (long long)h * k.out_ps * 8) = o;
+              if (valid) *reinterpret_cast<uint4*>(obase + ooff_r[u] + (long long)h * k.out_ps * 8) = o;
             }
           }
+        }
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -923,7 +955,7 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }
   const long long limit = 200 * 1024;
-  int SB = 3;
+  int SB = (k->nchunks == 1 && k->n_tiles == 1) ? 1 : 3;   // resident weights: one stage
   auto total = [&](int sa, int sb) { return kSmemHeader + (long long)sa * k->a_stage_bytes + (long long)sb * k->b_stage_bytes; };
   while (SB > 2 && total(k->SA, SB) > limit) --SB;
   while (gather && k->SA > 3 && total(k->SA, SB) > limit) --k->SA;
@@ -1016,11 +1048,13 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (g_debug[1] > 0) per_sm = g_debug[1] == 1 ? 1 : per_sm;   // debug: force one CTA per SM
   int grid = nsm * per_sm;
   if (grid > k.num_tiles) grid = k.num_tiles;
+  if (stats && k.BN / 16 > kEpiWarps / 4 && k.BN / 16 != 1)
+    return fail(HRNB_EINVAL, "conv: fused statistics need one fixed column group per epilogue warp (BN/16 <= epilogue warps / 4)");
   if (stats && grid > kStatsMaxCtas) return fail(HRNB_EINVAL, "conv: fused statistics support at most 320 CTAs");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(gather ? (unsigned)kThreadsGather : (unsigned)kThreadsFS);
-  cfg.dynamicSmemBytes = (size_t)(smem < kTmemExclusiveSmem && g_debug[6] == 0 ? kTmemExclusiveSmem : smem);
+  cfg.dynamicSmemBytes = (size_t)(per_sm == 1 && smem < kTmemExclusiveSmem && g_debug[6] == 0 ? kTmemExclusiveSmem : smem);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

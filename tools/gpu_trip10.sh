@@ -3,7 +3,7 @@
 # ncu launch lists (training step, inference pass) and `--set full` captures of the dominant kernels
 mkdir -p gpurun_out; cd "$(dirname "$0")/.."
 O=gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_multi.py > $O/t10_pytest.txt 2>&1; echo "suite rc=$?"; tail -4 $O/t10_pytest.txt
+timeout 1500 python -m pytest tests/test_gpu_train_network.py -m gpu -q > $O/t10_pytest.txt 2>&1; echo "train-network tests rc=$?"; tail -4 $O/t10_pytest.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/t10_smoke.txt 2>&1; echo "smoke rc=$?"; tail -2 $O/t10_smoke.txt
 timeout 900 python bench.py > $O/t10_bench_default.json 2> $O/t10_bench_default.err; echo "bench default rc=$?"; cut -c1-600 $O/t10_bench_default.json
 timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > $O/t10_bench_reference.json 2> $O/t10_bench_reference.err; echo "bench ref rc=$?"; cut -c1-400 $O/t10_bench_reference.json
@@ -15,4 +15,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 # full captures of the dominant kernels in isolation
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc|wgrad_tc|bn_stats" --launch-skip 5 --launch-count 15 -f -o $O/t10_prof_train_kernels python tools/kernel_once.py 64 > $O/t10_ncu_train_kernels.log 2>&1; echo "ncu train full rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc|softmax_softargmax|decode_argmax|softargmax|final_preds|heatmap_loss" --launch-count 30 -f -o $O/t10_prof_infer_kernels python tools/kernel_once_infer.py 256 > $O/t10_ncu_infer_kernels.log 2>&1; echo "ncu infer full rc=$?"
-ls -la $O/*.ncu-rep
+for n in train infer; do ncu -i $O/t10_prof_${n}_kernels.ncu-rep --page raw --csv > $O/t10_prof_${n}_kernels_raw.csv 2>/dev/null; ncu -i $O/t10_prof_${n}_kernels.ncu-rep --page details --csv > $O/t10_prof_${n}_kernels_details.csv 2>/dev/null; done
+ls -la $O/*.ncu-rep; rm -f $O/*.ncu-rep; du -sh $O

@@ -43,9 +43,20 @@ if __name__ == "__main__":
     allrec = {}
     for p in sys.argv[1:]:
         allrec[os.path.basename(p)] = parse(p)
+    # bench.py's `roofline.traffic`: DRAM bytes (read + write) of ONE launch of the dominant tensor-pipe kernel - the first
+    # conv_tc record of the inference / training capture = the 3x3 32->32 conv at 64x64 (21 % of the network's MACs)
+    for name, recs in list(allrec.items()):
+        kind = "conv_tc_kernel_infer" if "infer" in name else ("conv_tc_kernel_train" if "train" in name else None)
+        first = next((r for r in recs if r["kernel"].startswith("conv_tc") and "dram_read_MB" in r), None)
+        if kind and first:
+            allrec[kind] = int((first["dram_read_MB"] + first.get("dram_write_MB", 0.0)) * 1e6)
+            allrec[kind + "_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of one %s launch (%.1f us), 3x3 32->32 conv at 64x64, from %s" % (
+                first["kernel"], first.get("time_us", 0.0), name)
     with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json"), "w") as f:
         json.dump(allrec, f, indent=1)
     for name, recs in allrec.items():
+        if not isinstance(recs, list):
+            continue
         print("#", name)
         for r in recs:
             print("%-46s %8.1f us  read %8.1f MB  write %8.1f MB  %7.0f GB/s  hmma %.3f  regs %s grid %s" % (
