@@ -18,6 +18,7 @@ HRNB_CONV_GATHER = 4
 HRNB_CONV_IN_PHASES = 8
 HRNB_CONV_OUT_PHASES = 16
 HRNB_CONV_NO_PDL = 32
+HRNB_CONV_FUSE_AFTER_RELU = 64
 
 
 def guard_lead(Wp):
@@ -183,6 +184,8 @@ def lib():
             raise HrnbError("libhrnb.so ABI version mismatch")
         if os.environ.get("HRNB_NO_PDL", "0") == "1":      # debug: launch the conv kernels without programmatic dependent launch
             h.hrnb_debug_set(2, 1)
+        if os.environ.get("HRNB_NO_WRES", "0") == "1":     # A/B: re-load the weight stage per tile instead of keeping it resident
+            h.hrnb_debug_set(5, 1)
         if os.environ.get("HRNB_TMEM_SHARE", "0") == "1":  # debug: let TMEM-holding CTAs of different kernels share an SM (can deadlock)
             h.hrnb_debug_set(6, 1)
         _lib = h

@@ -75,6 +75,7 @@ struct ConvK {
   const __nv_bfloat16* fuse_src[3];
   long long fuse_ps[3];
   int in_up_shift;        // gather 1x1: input read at (y >> s, x >> s)
+  int wres;               // weights resident in shared memory for the whole CTA (one K chunk, one N tile)
 };
 
 // floor(n / d) for n < 2^31 and the divisor behind (m, s): m = ceil(2^(31 + c) / d), s = c - 1, c = ceil(log2 d) >= 1.
@@ -122,7 +123,9 @@ constexpr int kStatsMaxCtas = 320;
 // HBM (no operand loads at all: 62 vs 66 us) and not by TMEM reads.  The lean form: row geometry by multiply-high (fast_div),
 // per-warp item table (TMEM column, output / residual / bias offsets) hoisted out of the persistent loop, at most four items
 // per warp and tile fully unrolled with all residual loads issued before the accumulator wait, packed fp32x2 adds.
-template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false, bool LEAN = false>
+// PH (lean flat-shift launches whose output also / only exists in the phase-split form a following stride-2 conv reads):
+// kept out of the plain variant - the thin layers are bound by the epilogue's issue slots, every instruction there counts
+template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false, bool LEAN = false, bool PH = false>
 __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ? 1 : kCtasPerSm) conv_tc_kernel(const ConvK k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       // RESIDENT WEIGHTS: a layer whose whole weight tensor is one stage (one K chunk, one N tile - the 32- and 64-channel
       // 3x3 layers) loads it once per CTA instead of once per tile: -30 % shared-memory fill traffic on the thinnest layers
       // and one ring stage instead of three, which is what lets two CTAs share an SM there (hrnb_conv: per_sm)
-      const bool wres = k.nchunks == 1 && k.n_tiles == 1;
+      const bool wres = k.wres != 0;
       if ((int)blockIdx.x < k.num_tiles && !(k.dbg & 16)) {   // first weight stage of the first tile, ahead of the wait
         const int nt0 = (int)blockIdx.x % k.n_tiles;
         if (elect_one_sync()) {
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       const uint32_t b_tap16 = (uint32_t)(k.KC * k.BN);                 // one tap's weight tile in 16-byte units
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
       int it = 0;
-      const bool wres = k.nchunks == 1 && k.n_tiles == 1;   // resident weights (see the producer)
+      const bool wres = k.wres != 0;   // resident weights (see the producer)
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1, aph = (it >> 1) & 1;
         HRNB_TRACE(1, it, 0);
@@ -374,22 +377,37 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       }
       __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(k.out);
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      // phase-split form of the output (input of a following 3x3 stride-2 conv): either the only output (OUT_PHASES) or a
+      // second copy next to the plain PF8 tensor (out2); padding of the phase tensors is never written and stays zero
+      const bool primary = PH ? k.out_phase_stride == 0 : true;
+      __nv_bfloat16* const ph_base = PH ? (primary ? k.out2 : outp) : nullptr;
+      const long long ph_ps = primary ? k.out2_ps : k.out_ps;
+      const unsigned ph_stride16 = (unsigned)((primary ? k.out2_phase_stride : k.out_phase_stride) >> 3);
+      // FUSE_AFTER_RELU: the phase copy receives the unit's own output ReLU(acc + bias + res); the fuse sources are added to
+      // THAT and a second ReLU gives the primary output - the last conv of branch 0 hosting fuse output 0
+      const bool fuse_after = PH && (k.flags & HRNB_CONV_FUSE_AFTER_RELU) != 0;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1, aph = (it >> 1) & 1;
         const unsigned mg = k.n_tiles == 1 ? (unsigned)tile : fast_div((unsigned)tile, k.mNt, k.sNt);
         const int ntile = tile - (int)mg * k.n_tiles;
         const unsigned p0 = mg * (unsigned)(k.MB * 128) + (unsigned)(q * 32 + lane);
         unsigned validm = 0, realm = 0;
+        unsigned phoff[4] = {0u, 0u, 0u, 0u};   // phase-split copy / output: position of the row in 16-byte units, phase offset included
 #pragma unroll
         for (int mb = 0; mb < 4; ++mb) {
           if (mb < k.MB) {
             const unsigned p = p0 + (unsigned)(mb * 128);
             const unsigned rowi = fast_div(p, k.mWp, k.sWp);
             const unsigned px = p - rowi * (unsigned)k.Wp;
-            const unsigned py = rowi - fast_div(rowi, k.mHp, k.sHp) * (unsigned)k.Hp;
+            const unsigned n = fast_div(rowi, k.mHp, k.sHp);
+            const unsigned py = rowi - n * (unsigned)k.Hp;
             if (p < (unsigned)k.P) {
               validm |= 1u << mb;
               if (px != 0u && py != 0u) realm |= 1u << mb;
+            }
+            if constexpr (PH) {
+              const unsigned x = px - 1u, y = py - 1u;   // garbage on padding rows, which are never stored to the phases
+              phoff[mb] = ((y & 1u) * 2u + (x & 1u)) * ph_stride16 + (n * (unsigned)k.oHp2 + (y >> 1) + 1u) * (unsigned)k.oWp2 + (x >> 1) + 1u;
             }
           }
         }
@@ -459,6 +477,25 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
                 }
               }
             }
+            // residual first (the unit's own output), then - before or after its ReLU - the fuse sources
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 r = rb[u][h];
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x2[h * 4 + j] = add_f32x2(x2[h * 4 + j], pack_f32x2(bf16_lo(rw[j]), bf16_hi(rw[j])));
+            }
+            uint32_t own[PH ? 8 : 1];   // FUSE_AFTER_RELU: the unit's own output as bf16 pairs (goes to the phase copy)
+            if constexpr (PH) if (fuse_after) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float lo, hi;
+                unpack_f32x2(x2[j], lo, hi);
+                if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                own[j] = pack_bf16x2(lo, hi);
+                x2[j] = pack_f32x2(lo, hi);
+              }
+            }
             if (k.nfuse != 0 && real) {
               // fuse-layer sum: the other branches' contributions, nearest up-sampled on the fly (tiny, L2-resident sources)
               const unsigned p = p0 + (unsigned)(imb_r[u] * 128);
@@ -480,18 +517,22 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const uint4 r = rb[u][h];
-              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
               uint32_t ow[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float lo, hi;
-                unpack_f32x2(add_f32x2(x2[h * 4 + j], pack_f32x2(bf16_lo(rw[j]), bf16_hi(rw[j]))), lo, hi);
+                unpack_f32x2(x2[h * 4 + j], lo, hi);
                 ow[j] = relu ? pack_bf16x2_relu(lo, hi) : pack_bf16x2(lo, hi);
               }
               uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
               if (!real) o = make_uint4(0u, 0u, 0u, 0u);      // keep the shared zero padding intact
-              if (valid) *reinterpret_cast<uint4*>(obase + ooff_r[u] + (long long)h * k.out_ps * 8) = o;
+              if (primary && valid) *reinterpret_cast<uint4*>(obase + ooff_r[u] + (long long)h * k.out_ps * 8) = o;
+              if constexpr (PH) if (real) {
+                if (fuse_after) o = make_uint4(own[h * 4], own[h * 4 + 1], own[h * 4 + 2], own[h * 4 + 3]);
+                const int im = imb_r[u];   // selected without dynamic indexing (keeps phoff in registers)
+                const unsigned po = im == 0 ? phoff[0] : (im == 1 ? phoff[1] : (im == 2 ? phoff[2] : phoff[3]));
+                *reinterpret_cast<uint4*>(ph_base + ((long long)(plane0 + (boff_r[u] >> 3) + h) * ph_ps + po) * 8) = o;
+              }
             }
           }
         }
@@ -900,8 +941,10 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
         return fail(HRNB_EINVAL, "conv: bad fuse source (NULL, or shift not in 0..3 / not dividing H and W)");
     }
   }
-  if (p->nfuse > 0 && ((p->flags & (HRNB_CONV_OUT_NCHW | HRNB_CONV_OUT_PHASES)) || p->out2 || p->stats_sums))
-    return fail(HRNB_EINVAL, "conv: fuse sources need a plain PF8 output without fused statistics");
+  if (p->nfuse > 0 && ((p->flags & (HRNB_CONV_OUT_NCHW | HRNB_CONV_OUT_PHASES)) || p->stats_sums))
+    return fail(HRNB_EINVAL, "conv: fuse sources need a PF8 primary output without fused statistics");
+  if ((p->flags & HRNB_CONV_FUSE_AFTER_RELU) && (p->nfuse == 0 || (p->flags & HRNB_CONV_GATHER)))
+    return fail(HRNB_EINVAL, "conv: HRNB_CONV_FUSE_AFTER_RELU needs fuse sources on the flat-shift path");
   fast_magic((unsigned)k->Wp, &k->mWp, &k->sWp);
   fast_magic((unsigned)k->Hp, &k->mHp, &k->sHp);
   k->mNt = 0; k->sNt = 0;
@@ -955,7 +998,8 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }
   const long long limit = 200 * 1024;
-  int SB = (k->nchunks == 1 && k->n_tiles == 1) ? 1 : 3;   // resident weights: one stage
+  k->wres = (k->nchunks == 1 && k->n_tiles == 1 && g_debug[5] == 0) ? 1 : 0;   // hrnb_debug_set(5, 1): re-load per tile (A/B)
+  int SB = k->wres ? 1 : 3;   // resident weights: one stage
   auto total = [&](int sa, int sb) { return kSmemHeader + (long long)sa * k->a_stage_bytes + (long long)sb * k->b_stage_bytes; };
   while (SB > 2 && total(k->SA, SB) > limit) --SB;
   while (gather && k->SA > 3 && total(k->SA, SB) > limit) --k->SA;
@@ -1015,7 +1059,11 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   int ksi = -1;
   const void* fn = nullptr;
   // the lean epilogue covers the flat-shift path with a plain PF8 output (no phase-split form or copy)
-  const bool lean_ok = !nchw_out && k.out_phase_stride == 0 && k.out2 == nullptr;
+  const bool phases = k.out_phase_stride != 0 || k.out2 != nullptr;
+  // the lean epilogue: PF8 output; the phase-split form / copy only on the flat-shift path without fused statistics
+  const bool lean_ok = !nchw_out && (!phases || (!gather && !stats));
+  if ((p->flags & HRNB_CONV_FUSE_AFTER_RELU) && (k.out2 == nullptr || !lean_ok))
+    return fail(HRNB_EINVAL, "conv: HRNB_CONV_FUSE_AFTER_RELU needs out2 on the flat-shift path");
   if (k.nfuse > 0 && !lean_ok) return fail(HRNB_EINVAL, "conv: fuse sources need the lean epilogue (plain PF8 output)");
   const bool lean = lean_ok && ((g_debug[3] == 0 && g_debug[0] == 0) || k.nfuse > 0);
 #define HRNB_PICK(KS, IDX)                                                                                   \
@@ -1025,14 +1073,15 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
                         : (const void*)conv_tc_kernel<true, false, KS>)                                      \
                 : (nchw_out ? (const void*)conv_tc_kernel<false, true, KS>                                   \
                             : (lean ? (stats ? (const void*)conv_tc_kernel<false, false, KS, true, true>     \
-                                             : (const void*)conv_tc_kernel<false, false, KS, false, true>)   \
+                                             : (phases ? (const void*)conv_tc_kernel<false, false, KS, false, true, true>   \
+                                                       : (const void*)conv_tc_kernel<false, false, KS, false, true>))   \
                                     : (stats ? (const void*)conv_tc_kernel<false, false, KS, true>           \
                                              : (const void*)conv_tc_kernel<false, false, KS>)));             \
   }
   HRNB_PICK(1, 0) HRNB_PICK(2, 1) HRNB_PICK(3, 2) HRNB_PICK(4, 3) HRNB_PICK(6, 4) HRNB_PICK(8, 5) HRNB_PICK(16, 6)
 #undef HRNB_PICK
   if (!fn) return fail(HRNB_EINVAL, "conv: KC must be one of 2, 4, 6, 8, 12, 16, 32");
-  const int variant = ksi * 8 + (gather ? (lean ? 6 : 2) : (nchw_out ? 1 : (stats ? 3 : 0) + (lean ? 4 : 0)));
+  const int variant = ksi * 8 + (gather ? (lean ? 6 : 2) : (nchw_out ? 1 : (lean && phases ? 5 : (stats ? 3 : 0) + (lean ? 4 : 0))));
   if (!attr_set[dev][variant].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "conv: cudaFuncSetAttribute");

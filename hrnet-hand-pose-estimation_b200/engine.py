@@ -91,9 +91,9 @@ class Plan:
         self._op(sid, fn, name)
         return dst
 
-    def _conv(self, sid, layer, x, out, res=None, name="", out2=None, fuse=None, relu=None, up_shift=0):
+    def _conv(self, sid, layer, x, out, res=None, name="", out2=None, fuse=None, relu=None, up_shift=0, fuse_after=False):
         layer.no_pdl = not self.engine.pdl
-        p = layer.params(x, out, res, out2=out2, fuse=fuse, relu=relu, up_shift=up_shift)
+        p = layer.params(x, out, res, out2=out2, fuse=fuse, relu=relu, up_shift=up_shift, fuse_after=fuse_after)
         self.keep.append(p)
         lib = _lib.lib()
         ref = C.byref(p)
@@ -212,6 +212,7 @@ class Plan:
                 last_module = (s == 4 and m == nmod - 1)
                 # branches: 4 BasicBlocks each, branch i on stream i
                 split = {}   # branch outputs that feed stride-2 chains also exist as phases (written by the last conv)
+                host0 = None  # fuse output 0 hosted by the LAST conv of branch 0 (deferred until the other branches are done)
                 for i in range(nb):
                     for b in range(arch.blocks):
                         bp = "%s.branches.%d.%d" % (pre, i, b)
@@ -219,16 +220,39 @@ class Plan:
                         ph = None
                         if b == arch.blocks - 1 and i < nb - 1:
                             ph = split[i] = self._phases(ch[i], *res_hw[i])
+                        if b == arch.blocks - 1 and i == 0 and e.fuse_epilogue and e.fuse_host0 == "conv2":
+                            host0 = (L[bp + ".conv2"], y, xs[0], ph, bp + ".conv2+fuse")
+                            continue
                         xs[i] = self._conv(i, L[bp + ".conv2"], y, self._buf(ch[i], *res_hw[i]), res=xs[i],
                                            name=bp + ".conv2", out2=ph)
+                if last_module:
+                    cat = self._buf(arch.head_channels, *res_hw[0])
+                out0 = None
+                if host0 is not None:
+                    # Output 0 = ReLU(x0 + sum_j up(f_0j(x_j))) with x0 = ReLU(conv2(...) + residual): the low-resolution 1x1 convs
+                    # f_0j run first (their inputs are ready long before branch 0's eighth conv), then branch 0's last conv adds
+                    # them AFTER its own ReLU (HRNB_CONV_FUSE_AFTER_RELU) - x0 itself only leaves the SM as the phase-split
+                    # copy the stride-2 chains read; the full-resolution sum never makes an extra trip through HBM.
+                    fuse0 = []
+                    for j in range(1, nb):
+                        fp = "%s.fuse_layers.0.%d.0" % (pre, j)
+                        fuse0.append((self._conv(j, L[fp], xs[j], self._buf(ch[0], *res_hw[j]), name=fp), j))
+                    for j in range(1, nb):
+                        self._wait(0, j)
+                    layer, y, res0, ph, name = host0
+                    out0 = cat.view_planes(0, ch[0] // 8) if last_module else self._buf(ch[0], *res_hw[0])
+                    self._conv(0, layer, y, out0, res=res0, name=name, out2=ph, fuse=fuse0, relu=True, fuse_after=True)
+                    xs[0] = None
                 # every fuse output needs every branch
                 for i in range(nb):
                     for j in range(nb):
                         self._wait(i, j)
                 outs = []
                 for i in range(nb):
+                    if i == 0 and out0 is not None:
+                        outs.append(out0)
+                        continue
                     if last_module and i == 0:
-                        cat = self._buf(arch.head_channels, *res_hw[0])
                         dst = cat.view_planes(0, ch[0] // 8)
                     else:
                         dst = self._buf(ch[i], *res_hw[i])
@@ -359,6 +383,9 @@ class HRNetEngine:
         # fuse-layer sums inside the epilogue of one of the output's own convs (no separate fuse_sum pass, no second trip of the
         # summed tensor through HBM); HRNB_FUSE_EPILOGUE=0 restores the stand-alone sum kernel
         self.fuse_epilogue = os.environ.get("HRNB_FUSE_EPILOGUE", "1") != "0"
+        # host of fuse output 0: "conv2" = the last conv of branch 0 (default), "gather" = the 1x1 conv from branch 1 evaluated
+        # on the up-sampled grid (round-2 first form, 88 us instead of ~10 us extra at batch 256)
+        self.fuse_host0 = os.environ.get("HRNB_FUSE_HOST0", "conv2")
         with torch.cuda.device(self.device):
             _lib.hang_init()
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]

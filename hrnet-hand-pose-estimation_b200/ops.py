@@ -278,7 +278,7 @@ class ConvLayer:
             custom = (max(0, max(dps)) - min(0, min(dps)), max(s_ for s_, _ in self.custom_taps) + 1)
         return H, W, P, mode, custom
 
-    def params(self, x, out, res=None, mb=None, bn=None, kc=None, out2=None, fuse=None, relu=None, up_shift=0):
+    def params(self, x, out, res=None, mb=None, bn=None, kc=None, out2=None, fuse=None, relu=None, up_shift=0, fuse_after=False):
         """launch parameters; the tile shape (BN, MB, KC) comes from the caller, else from the autotuner (measured on the
         device the first time a shape is seen, like the reference's cudnn.benchmark = True, tools/train.py:128), else from
         the cycle model"""
@@ -303,12 +303,16 @@ class ConvLayer:
                     kc = cand
                     break
         p = self._build_params(x, out, res, out2, bn, mb, kc)
-        return self._attach_fuse(p, fuse, relu)
+        return self._attach_fuse(p, fuse, relu, fuse_after)
 
     @staticmethod
-    def _attach_fuse(p, fuse, relu):
+    def _attach_fuse(p, fuse, relu, fuse_after=False):
         """fuse: [(PF8 source, shift)] added in the epilogue with nearest up-sampling (include/hrnb.h: nfuse); relu: override
-        of the layer's ReLU flag (the fuse-layer host conv applies the ReLU of the sum, pose_hrnet.py:266)"""
+        of the layer's ReLU flag (the fuse-layer host conv applies the ReLU of the sum, pose_hrnet.py:266); fuse_after: the
+        sources are added AFTER the unit's own ReLU and a second ReLU follows (HRNB_CONV_FUSE_AFTER_RELU)"""
+        if fuse_after:
+            assert fuse
+            p.flags |= _lib.HRNB_CONV_FUSE_AFTER_RELU
         if fuse:
             assert len(fuse) <= 3
             p.nfuse = len(fuse)
@@ -382,11 +386,11 @@ class ConvLayer:
             p.MB //= 2          # tile does not fit in shared memory at this MB
         return p
 
-    def __call__(self, x, out, res=None, mb=None, bn=None, out2=None, stats=None, fuse=None, relu=None, up_shift=0):
+    def __call__(self, x, out, res=None, mb=None, bn=None, out2=None, stats=None, fuse=None, relu=None, up_shift=0, fuse_after=False):
         """stats: fp32 [cout, 2] tensor -> the launch also writes the BatchNorm batch statistics (sum, sum of squares per
         channel) of `out`; raises when the launch is not eligible (see attach_stats)"""
         assert x.C == self.cin, (x.C, self.cin)
-        p = self.params(x, out, res, mb, bn, out2=out2, fuse=fuse, relu=relu, up_shift=up_shift)
+        p = self.params(x, out, res, mb, bn, out2=out2, fuse=fuse, relu=relu, up_shift=up_shift, fuse_after=fuse_after)
         if stats is not None and not attach_stats(p, stats):
             raise ValueError("conv launch not eligible for fused BatchNorm statistics (BN=%d cout=%d flags=%d)" % (p.BN, p.cout, p.flags))
         _lib.check(_lib.lib().hrnb_conv(C.byref(p), _lib.stream_ptr()))

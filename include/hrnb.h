@@ -43,7 +43,9 @@ enum {
   HRNB_CONV_GATHER = 4,     /* per-tap gathered A operand (any stride); otherwise flat-shift      */
   HRNB_CONV_IN_PHASES = 8,  /* 3x3 stride-2 conv whose input is given as 4 phase tensors (see below) */
   HRNB_CONV_OUT_PHASES = 16, /* write the PF8 output as 4 phase tensors for a following stride-2 conv */
-  HRNB_CONV_NO_PDL = 32     /* launch without programmatic dependent launch (plain stream order)      */
+  HRNB_CONV_NO_PDL = 32,    /* launch without programmatic dependent launch (plain stream order)      */
+  HRNB_CONV_FUSE_AFTER_RELU = 64 /* with nfuse > 0: out2 (phase copy) = ReLU(acc + bias + res), the unit's own output;
+                                    out = ReLU(that + fuse sources) - the last conv of a branch hosting its fuse output */
 };
 
 /* One conv + folded-BN bias (+ residual) (+ ReLU) launch.

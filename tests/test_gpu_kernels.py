@@ -382,15 +382,58 @@ def test_1x1_conv_on_upsampled_input_hosts_the_fuse_sum(N, H, W, cin, cout, up, 
     assert (out.to_nchw() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("N,H,W,C,shifts", [(2, 64, 64, 32, (1, 2, 3)), (3, 32, 48, 64, (1,)), (2, 16, 16, 128, (1, 2))])
+def test_last_branch_conv_hosts_fuse_output_0(N, H, W, C, shifts):
+    """HRNB_CONV_FUSE_AFTER_RELU + out2: the last 3x3 conv of branch 0 writes its own output x0 = ReLU(conv + bias + res) as the
+    phase-split copy the stride-2 chains read, and ReLU(x0 + sum_j nearest_up(z_j)) - fuse output 0 of
+    HighResolutionModule.forward (lib/models/pose_hrnet.py:257-266) - as the primary output, in one launch"""
+    from hrnet_b200.ops import ConvLayer, PF8, PhasePF8
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(N, C, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5
+    scale = torch.rand(C, device="cuda", generator=g) + 0.5
+    shift = torch.randn(C, device="cuda", generator=g) * 0.1
+    res = torch.randn(N, C, H, W, device="cuda", generator=g)
+    srcs = [torch.randn(N, C, H >> s, W >> s, device="cuda", generator=g) for s in shifts]
+    out, ph = PF8(N, C, H, W), PhasePF8(N, C, H, W)
+    out.buf.fill_(7.0); out.buf[:, :out.lead] = 0; out.buf[:, out.lead + out.P:] = 0
+    ConvLayer(w, scale, shift, relu=True)(PF8.from_nchw(x), out, PF8.from_nchw(res), out2=ph,
+                                          fuse=[(PF8.from_nchw(t), s) for t, s in zip(srcs, shifts)], fuse_after=True)
+    x0 = F.relu(F.conv2d(_bf16(x), _bf16(w * scale.view(-1, 1, 1, 1)), None, padding=1) + shift.view(1, -1, 1, 1) + _bf16(res))
+    ref = x0
+    for t, s in zip(srcs, shifts):
+        ref = ref + F.interpolate(_bf16(t), scale_factor=2 ** s, mode="nearest")
+    ref = F.relu(ref)
+    torch.cuda.synchronize()
+    assert out.padding_is_zero() and ph.padding_is_zero()
+    assert (ph.to_nchw() - x0).abs().max().item() <= 2e-2 * max(1.0, x0.abs().max().item())
+    assert (out.to_nchw() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_lean_epilogue_phase_copy_equals_plain_output():
+    """out2 on the lean epilogue: the phase-split copy holds exactly the bf16 values of the plain PF8 output"""
+    from hrnet_b200.ops import ConvLayer, PF8, PhasePF8
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for N, C, H, W in ((2, 32, 64, 64), (3, 64, 32, 16), (1, 256, 16, 16)):
+        x = torch.randn(N, C, H, W, device="cuda", generator=g)
+        w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5
+        res = torch.randn(N, C, H, W, device="cuda", generator=g)
+        out, ph = PF8(N, C, H, W), PhasePF8(N, C, H, W)
+        ConvLayer(w, relu=True)(PF8.from_nchw(x), out, PF8.from_nchw(res), out2=ph)
+        torch.cuda.synchronize()
+        assert torch.equal(ph.to_nchw(), out.to_nchw()) and ph.padding_is_zero() and out.padding_is_zero()
+
+
 def test_fuse_in_epilogue_plan_equals_stand_alone_sum_plan():
-    """whole network: the inference plan with the fuse sums inside conv epilogues against the plan with fuse_sum kernels"""
+    """whole network: the inference plans with the fuse sums inside conv epilogues (output 0 hosted by branch 0's last conv, or
+    by the gathered 1x1 conv) against the plan with fuse_sum kernels"""
     import os
     from oracle import fixtures
     from hrnet_b200.config import make_cfg
     from hrnet_b200.models import pose_hrnet_softmax
     outs = []
-    for flag in ("1", "0"):
-        os.environ["HRNB_FUSE_EPILOGUE"] = flag
+    for flag, host0 in (("1", "conv2"), ("1", "gather"), ("0", "conv2")):
+        os.environ["HRNB_FUSE_EPILOGUE"], os.environ["HRNB_FUSE_HOST0"] = flag, host0
         try:
             torch.manual_seed(0)
             m = pose_hrnet_softmax.get_pose_net(make_cfg(32), is_train=False)
@@ -400,6 +443,8 @@ def test_fuse_in_epilogue_plan_equals_stand_alone_sum_plan():
             outs.append((h.clone(), f.clone(), m.engine().plan(2, 128, 128).launches(False)))
         finally:
             os.environ.pop("HRNB_FUSE_EPILOGUE", None)
-    assert outs[0][2] < outs[1][2]                                  # 26 fuse_sum launches gone
-    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 4e-2 * outs[1][1].abs().max().item()
-    assert (outs[0][0] - outs[1][0]).abs().max().item() <= 2e-2 * outs[1][0].abs().max().item()
+            os.environ.pop("HRNB_FUSE_HOST0", None)
+    assert outs[0][2] < outs[2][2] and outs[1][2] < outs[2][2]      # the fuse_sum launches are gone
+    for a in outs[:2]:
+        assert (a[1] - outs[2][1]).abs().max().item() <= 4e-2 * outs[2][1].abs().max().item()
+        assert (a[0] - outs[2][0]).abs().max().item() <= 2e-2 * outs[2][0].abs().max().item()
