@@ -184,8 +184,6 @@ def lib():
             raise HrnbError("libhrnb.so ABI version mismatch")
         if os.environ.get("HRNB_NO_PDL", "0") == "1":      # debug: launch the conv kernels without programmatic dependent launch
             h.hrnb_debug_set(2, 1)
-        if os.environ.get("HRNB_NO_WRES", "0") == "1":     # A/B: re-load the weight stage per tile instead of keeping it resident
-            h.hrnb_debug_set(5, 1)
         if os.environ.get("HRNB_TMEM_SHARE", "0") == "1":  # debug: let TMEM-holding CTAs of different kernels share an SM (can deadlock)
             h.hrnb_debug_set(6, 1)
         _lib = h

@@ -998,7 +998,7 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }
   const long long limit = 200 * 1024;
-  k->wres = (k->nchunks == 1 && k->n_tiles == 1 && g_debug[5] == 0) ? 1 : 0;   // hrnb_debug_set(5, 1): re-load per tile (A/B)
+  k->wres = (k->nchunks == 1 && k->n_tiles == 1) ? 1 : 0;   // measured in-trip against per-tile re-loads: +0.5 ... 1 % (inference)
   int SB = k->wres ? 1 : 3;   // resident weights: one stage
   auto total = [&](int sa, int sb) { return kSmemHeader + (long long)sa * k->a_stage_bytes + (long long)sb * k->b_stage_bytes; };
   while (SB > 2 && total(k->SA, SB) > limit) --SB;
