@@ -184,6 +184,8 @@ def lib():
             raise HrnbError("libhrnb.so ABI version mismatch")
         if os.environ.get("HRNB_NO_PDL", "0") == "1":      # debug: launch the conv kernels without programmatic dependent launch
             h.hrnb_debug_set(2, 1)
+        if os.environ.get("HRNB_NO_DUAL", "0") == "1":     # A/B: one MMA-issuing warp per CTA everywhere
+            h.hrnb_debug_set(8, 1)
         if os.environ.get("HRNB_TMEM_SHARE", "0") == "1":  # debug: let TMEM-holding CTAs of different kernels share an SM (can deadlock)
             h.hrnb_debug_set(6, 1)
         _lib = h
@@ -218,7 +220,7 @@ def hang_report():
         if w0 == 0 and w1 == 0:
             continue
         threads = w0 >> 48
-        out.append({"kernel": {576: "conv_tc", 704: "conv_tc<gather>", 192: "wgrad_tc"}.get(threads, "threads=%d" % threads),
+        out.append({"kernel": {608: "conv_tc", 736: "conv_tc<gather>", 192: "wgrad_tc"}.get(threads, "threads=%d" % threads),
                     "grid": (w0 >> 32) & 0xffff, "cta": (w0 >> 8) & 0xffffff, "warp": w0 & 0xff,
                     "barrier_smem": w1 >> 8, "parity": w1 & 0xff})
     return out

@@ -20,7 +20,7 @@ int bind_hang_buffer_wgrad();
 // ms/step]; it did NOT cure the round-1 mbarrier time-out (that was the producer's prefetch wait, conv_tc.cu).
 // hrnb_debug_set(6, 1) / HRNB_TMEM_SHARE=1 turns the padding off.
 constexpr long long kTmemExclusiveSmem = 116 * 1024;
-extern int g_debug[8];                               // hrnb_debug_set knobs (conv_tc.cu); [4] != 0: PDL for the elementwise / wgrad kernels
+extern int g_debug[16];                               // hrnb_debug_set knobs (conv_tc.cu); [4] != 0: PDL for the elementwise / wgrad kernels
 
 // kernel launch with the programmatic-dependent-launch attribute when knob 4 is set (the kernel must call pdl_enter())
 template <typename... KArgs, typename... Args>

@@ -76,6 +76,7 @@ struct ConvK {
   long long fuse_ps[3];
   int in_up_shift;        // gather 1x1: input read at (y >> s, x >> s)
   int wres;               // weights resident in shared memory for the whole CTA (one K chunk, one N tile)
+  int dual;               // two MMA-issuing warps on alternate tiles (resident-weight flat-shift launches, SA >= 3)
 };
 
 // floor(n / d) for n < 2^31 and the divisor behind (m, s): m = ceil(2^(31 + c) / d), s = c - 1, c = ceil(log2 d) >= 1.
@@ -99,7 +100,7 @@ constexpr int kMaxSA = 8, kMaxSB = 4;
 #endif
 constexpr int kEpiWarps = HRNB_EPI_WARPS;          // warps per CTA draining TMEM (a multiple of 4: k per TMEM lane quarter)
 constexpr int kCtasPerSm = kEpiWarps <= 8 ? 2 : 1;  // 8 epilogue warps leave registers for two co-resident CTAs
-constexpr int kThreadsFS = 64 + 32 * kEpiWarps;    // producer + MMA + epilogue
+constexpr int kThreadsFS = 96 + 32 * kEpiWarps;    // producer + MMA + epilogue + second MMA issuer (dual-issue launches)
 constexpr int kThreadsGather = kThreadsFS + 128;   // + gather producers
 
 // KSTEPS = KC/2 (K=16 MMA steps per tap and chunk) is a template parameter so that the MMA issue loop is straight-line code:
@@ -256,12 +257,21 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
+  } else if (warp == 1 || (!GATHER && warp == 2 + kEpiWarps)) {
+    // =============================== MMA issuer(s) ===============================
     // Executed by the whole warp so that descriptors stay in uniform registers; one elected lane issues.
     // Per-MMA scalar work is two 32-bit adds: the 64-bit descriptors are (constant hi word, running lo word)
     // [measured: with descriptors rebuilt from scratch per MMA the issue loop, not the tensor pipe, set the pace].
-    {
+    //
+    // DUAL ISSUE (k.dual: resident-weight layers, i.e. the thin 32-/64-channel convs): a second warp issues the MMAs of every
+    // other tile into the other accumulator stage.  One issuing thread runs only about one MMA ahead of the tensor pipe and
+    // stalls ~400 cycles per tile on the barrier hand-offs; with two independent issue streams the pipe stays fed while one
+    // of them waits (the effect two co-resident CTAs have - measured -16 % on the 32-channel layers - without a second copy
+    // of the weights and the halo ring in shared memory).  tcgen05.commit tracks the executing thread's own MMAs, so each
+    // issuer releases exactly the stages it consumed.
+    const int mw = warp == 1 ? 0 : 1;
+    const int nmw = k.dual ? 2 : 1;
+    if (mw < nmw) {
       const uint32_t idesc = make_idesc_bf16_m128((uint32_t)k.BN);
       const uint32_t a_lbo16 = (uint32_t)rowsA;            // LBO in 16-byte units (rows * 16 B)
       const uint32_t b_lbo16 = (uint32_t)k.BN;
@@ -271,10 +281,9 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       const uint32_t a_stage16 = k.a_stage_bytes >> 4, b_stage16 = k.b_stage_bytes >> 4;
       const uint32_t a_jstep = 2u * a_lbo16, b_jstep = 2u * b_lbo16;   // K advance of 16 elements = two planes
       const uint32_t b_tap16 = (uint32_t)(k.KC * k.BN);                 // one tap's weight tile in 16-byte units
-      int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
-      int it = 0;
+      int a_stage = mw, a_phase = 0, b_stage = 0, b_phase = 0;   // dual: one A stage per tile (nchunks == 1), issuer mw starts at stage mw
       const bool wres = k.wres != 0;   // resident weights (see the producer)
-      for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
+      for (int it = mw, tile = blockIdx.x + mw * gridDim.x; tile < k.num_tiles; tile += nmw * gridDim.x, it += nmw) {
         const int as = it & 1, aph = (it >> 1) & 1;
         HRNB_TRACE(1, it, 0);
         mbar_wait(&tmem_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           // one wait per chunk for the A halo (flat-shift) and for the weights of all taps: every wait / commit
           // stalls the tensor pipe (~100-140 cycles each, measured), so hand-offs are per chunk, not per tap
           if (!GATHER) mbar_wait(&full_a[a_stage], a_phase);
-          if (!wres || it == 0) mbar_wait(&full_b[b_stage], b_phase);
+          if (!wres || it == mw) mbar_wait(&full_b[b_stage], b_phase);
           tc_fence_after_sync();
           if (c == 0) HRNB_TRACE(2, it, 1);
           uint32_t b_lo_tap = b_lo_ring + (uint32_t)b_stage * b_stage16;
@@ -329,7 +338,8 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           }
           if (!wres && ++b_stage == k.SB) { b_stage = 0; b_phase ^= 1; }
           if (!GATHER) {
-            if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
+            a_stage += nmw;
+            if (a_stage >= k.SA) { a_stage -= k.SA; a_phase ^= 1; }
           }
         }
         HRNB_TRACE(1, it, 1);
@@ -713,7 +723,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     }
   } else {
     // =============================== gather producers (GATHER only) ===============================
-    if (GATHER) {
+    if (GATHER && warp >= 3 + kEpiWarps) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       const int g = threadIdx.x - kThreadsFS;  // A row handled by this thread (per M block)
       const int LAG = k.lag;
@@ -831,7 +841,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
   }
 }
 
-int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_debug[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 long long* g_trace = nullptr;
 
 // (m, s) of fast_div for divisor d >= 2
@@ -997,8 +1007,16 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     k->a_stage_bytes = (unsigned)(k->nsrc * p->KC * k->halo * 16);
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }
-  const long long limit = 200 * 1024;
   k->wres = (k->nchunks == 1 && k->n_tiles == 1) ? 1 : 0;   // measured in-trip against per-tile re-loads: +0.5 ... 1 % (inference)
+  // dual issue: two tiles in flight need two A stages, a third one is the prefetch; hrnb_debug_set(8, 1) turns it off (A/B)
+  k->dual = 0;
+  if (k->wres && !gather && g_debug[8] == 0 &&
+      kSmemHeader + 3LL * k->a_stage_bytes + (long long)k->b_stage_bytes <= 200 * 1024) {
+    k->dual = 1;
+    k->SA = 3;
+    if (kSmemHeader + 4LL * k->a_stage_bytes + (long long)k->b_stage_bytes <= 200 * 1024) k->SA = 4;   // deeper halo prefetch
+  }
+  const long long limit = 200 * 1024;
   int SB = k->wres ? 1 : 3;   // resident weights: one stage
   auto total = [&](int sa, int sb) { return kSmemHeader + (long long)sa * k->a_stage_bytes + (long long)sb * k->b_stage_bytes; };
   while (SB > 2 && total(k->SA, SB) > limit) --SB;
@@ -1022,7 +1040,7 @@ int bind_hang_buffer_conv() {
 using namespace hrnb;
 
 extern "C" int hrnb_debug_set(int key, int value) {
-  if (key < 0 || key >= 8) return HRNB_EINVAL;
+  if (key < 0 || key >= 16) return HRNB_EINVAL;
   g_debug[key] = value;
   return HRNB_OK;
 }

@@ -82,7 +82,9 @@ def test_train_step_against_reference_golden(golden_dir, name, variant):
         l2, cos = _cmp(got, ref)
         ratio = float(nat[k].double().norm()) / float(g["gnorm/" + k])
         _report(name + ":" + k, grad_rel_l2=l2, grad_cos=cos, norm_ratio=ratio)
-        if not (0.6 < ratio < 1.6) or (k.startswith("last_layer") and cos < 0.85):
+        # chaotic case (2 images, random init, train-mode BN: DESIGN.md §2): gradient NORMS within a factor 2.5 everywhere, head
+        # directions pinned; the per-tensor direction checks live in the well-conditioned goldens below
+        if not (0.4 < ratio < 2.5) or (k.startswith("last_layer") and cos < 0.85):
             bad.append((k, round(l2, 4), round(cos, 4), round(ratio, 3)))
     assert not bad, bad
     _report(name, loss_total=float(losses[0]), loss_ref=float(g["losses"][0]))
