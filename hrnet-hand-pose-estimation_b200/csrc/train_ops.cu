@@ -631,47 +631,38 @@ __global__ void __launch_bounds__(256) phase_merge_kernel(const __nv_bfloat16* _
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_batch_kernel(const hrnb_pack_job* __restrict__ jobs,
                                                         const int32_t* __restrict__ block_job) {
+  // One thread = one (output channel, input channel) pair of one job, ALL its taps: the taps of a pair are contiguous in the
+  // OIHW source (36 bytes for a 3x3 kernel: every fetched sector is used, where one thread per packed element touched a new
+  // 32-byte sector for every 4 bytes it needed), and for a fixed tap consecutive threads write consecutive bf16 elements.
   const hrnb_pack_job& j = jobs[block_job[blockIdx.x]];
   const long long i = (long long)(blockIdx.x - j.block0) * blockDim.x + threadIdx.x;
   const int ntiles = (j.lcout + j.BN - 1) / j.BN;
-  const long long total = (long long)ntiles * j.BN * j.ntap * j.lcin;
+  const long long pairs = (long long)ntiles * j.BN * j.lcin;
   float* bias = reinterpret_cast<float*>(j.bias_out);
   if (bias != nullptr && i < (long long)ntiles * j.BN) {
     const float* shift = reinterpret_cast<const float*>(j.shift);
     bias[i] = (i < j.lcout && shift) ? shift[i] : 0.f;
   }
-  if (i >= total) return;
-  // i = ((((nt*nch + c)*ntap + t)*KC + jj)*BN + n)*8 + e
+  if (i >= pairs) return;
+  // pair index i = (((nt*nch + c)*KC + jj)*BN + n)*8 + e;  packed element = ((((nt*nch + c)*ntap + t)*KC + jj)*BN + n)*8 + e
   const int nch = (j.lcin / 8) / j.KC;
-  int e, n, jj, t, c, nt;
-  if (total <= 0xffffffffLL) {     // uniform per job: 32-bit unsigned divisions (five 64-bit ones per element were the kernel's cost)
-    unsigned r = (unsigned)i;
-    e = (int)(r & 7u); r >>= 3;
-    unsigned q = r / (unsigned)j.BN; n = (int)(r - q * (unsigned)j.BN); r = q;
-    q = r / (unsigned)j.KC; jj = (int)(r - q * (unsigned)j.KC); r = q;
-    q = r / (unsigned)j.ntap; t = (int)(r - q * (unsigned)j.ntap); r = q;
-    q = r / (unsigned)nch; c = (int)(r - q * (unsigned)nch);
-    nt = (int)q;
-  } else {
-    long long r = i;
-    e = (int)(r % 8); r /= 8;
-    n = (int)(r % j.BN); r /= j.BN;
-    jj = (int)(r % j.KC); r /= j.KC;
-    t = (int)(r % j.ntap); r /= j.ntap;
-    c = (int)(r % nch); r /= nch;
-    nt = (int)r;
-  }
+  unsigned r = (unsigned)i;          // pairs < 2^32 for any conv of this network (asserted on the host side by the job sizes)
+  const int e = (int)(r & 7u); r >>= 3;
+  unsigned q = r / (unsigned)j.BN; const int n = (int)(r - q * (unsigned)j.BN); r = q;
+  q = r / (unsigned)j.KC; const int jj = (int)(r - q * (unsigned)j.KC); r = q;
+  q = r / (unsigned)nch; const int c = (int)(r - q * (unsigned)nch);
+  const int nt = (int)q;
   const int lco = nt * j.BN + n;
   const int lci = (c * j.KC + jj) * 8 + e;
   const int co = j.transpose ? lci : lco, ci = j.transpose ? lco : lci;
-  float v = 0.f;
-  if (lco < j.lcout && co < j.cout && ci < j.cin) {
-    const float* w = reinterpret_cast<const float*>(j.w);
-    v = w[((long long)co * j.cin + ci) * j.taps_total + j.tap_ids[t]];
-    const float* scale = reinterpret_cast<const float*>(j.scale);
-    if (scale) v *= scale[co];
-  }
-  reinterpret_cast<__nv_bfloat16*>(j.wpk_out)[i] = __float2bfloat16_rn(v);
+  const bool live = lco < j.lcout && co < j.cout && ci < j.cin;
+  const float* w = reinterpret_cast<const float*>(j.w) + (live ? ((long long)co * j.cin + ci) * j.taps_total : 0);
+  const float* scale = reinterpret_cast<const float*>(j.scale);
+  const float sc = (live && scale) ? scale[co] : 1.f;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(j.wpk_out);
+  const long long tap_stride = (long long)j.KC * j.BN * 8;
+  long long o = ((((long long)(nt * nch + c) * j.ntap) * j.KC + jj) * j.BN + n) * 8 + e;
+  for (int t = 0; t < j.ntap; ++t, o += tap_stride) out[o] = __float2bfloat16_rn(live ? w[j.tap_ids[t]] * sc : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -178,7 +178,8 @@ def autotune_conv(layer, x, out, res, out2, max_candidates=8):
 
 def stats_eligible(p):
     """can this conv launch also produce the BatchNorm batch statistics of its output (include/hrnb.h: stats_sums)?"""
-    return (p.BN == p.cout and p.cout in (16, 32, 64) and not p.res and
+    widths = (16, 32, 64) if int(os.environ.get("HRNB_STATS_MAX", "64")) >= 64 else (16, 32)   # 8-epilogue-warp builds: <= 32
+    return (p.BN == p.cout and p.cout in widths and not p.res and
             not (p.flags & (HRNB_CONV_GATHER | HRNB_CONV_OUT_NCHW | HRNB_CONV_RELU)))
 
 
@@ -426,7 +427,7 @@ class Repacker:
         block_job, b0 = [], 0
         arr = (PackJob * len(self.jobs))()
         for i, (job, n) in enumerate(zip(self.jobs, self.sizes)):
-            nb = (n + 255) // 256
+            nb = (n // job.ntap + 255) // 256       # one thread per (output channel, input channel) pair, all taps
             job.block0 = b0
             C.memmove(C.byref(arr, i * C.sizeof(PackJob)), C.byref(job), C.sizeof(PackJob))
             block_job.append(np.full(nb, i, dtype=np.int32))

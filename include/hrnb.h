@@ -250,7 +250,8 @@ int64_t hrnb_wgrad_smem_bytes(const hrnb_wgrad_params* p);
  * lcout x lcin channels (lcin a multiple of 16, zero padded) and ntap taps, logical tap t = source tap tap_ids[t];
  * transpose != 0 swaps the channel roles (logical cout = source cin): with tap_ids reversed this is the
  * data-gradient conv of a stride-1 3x3 conv.  Output order as hrnb_pack_conv_weights ([ntile][chunk][tap][KC][BN][8]).
- * `jobs` and `block_job` (job index of every 256-thread block; job j owns blocks [block0, block0 + ceil(total/256)))
+ * `jobs` and `block_job` (job index of every 256-thread block; job j owns blocks [block0, block0 + ceil(pairs/256)) with
+ * pairs = ntiles*BN*lcin: one thread packs all ntap taps of one (output channel, input channel) pair)
  * live in DEVICE memory.  All pointers inside a job are device pointers. */
 typedef struct hrnb_pack_job {
   const void* w;
