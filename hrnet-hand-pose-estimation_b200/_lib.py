@@ -44,7 +44,9 @@ class ConvParams(C.Structure):
         ("ntap_custom", C.c_int32), ("tap_src", C.c_int32 * 9), ("tap_dpos", C.c_int32 * 9),
         ("stats_sums", C.c_void_p), ("stats_ws", C.c_void_p),
         ("nfuse", C.c_int32), ("fuse_shift", C.c_int32 * 3), ("fuse_src", C.c_void_p * 3), ("fuse_ps", C.c_int64 * 3),
-        ("in_up_shift", C.c_int32), ("pad_", C.c_int32),
+        ("in_up_shift", C.c_int32), ("ngroup", C.c_int32),
+        ("grp_ntap", C.c_int32 * 4), ("grp_tap_dpos", (C.c_int32 * 4) * 4), ("grp_wpk", C.c_void_p * 4),
+        ("grp_out_stride", C.c_int64), ("grp_res_stride", C.c_int64),
     ]
 
 
@@ -63,6 +65,7 @@ class WgradParams(C.Structure):
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
         ("ntap", C.c_int32), ("tap_dpos", C.c_int32 * 9), ("tap_id", C.c_int32 * 9),
         ("NT", C.c_int32), ("TG", C.c_int32), ("KP", C.c_int32), ("ksplit", C.c_int32),
+        ("tap_src", C.c_int32 * 9), ("pad_", C.c_int32), ("x_src_stride", C.c_int64),
     ]
 
 
@@ -180,7 +183,7 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if h.hrnb_abi_version() != 4:
+        if h.hrnb_abi_version() != 5:
             raise HrnbError("libhrnb.so ABI version mismatch")
         if os.environ.get("HRNB_NO_PDL", "0") == "1":      # debug: launch the conv kernels without programmatic dependent launch
             h.hrnb_debug_set(2, 1)

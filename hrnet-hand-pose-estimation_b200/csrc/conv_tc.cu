@@ -77,6 +77,13 @@ struct ConvK {
   int in_up_shift;        // gather 1x1: input read at (y >> s, x >> s)
   int wres;               // weights resident in shared memory for the whole CTA (one K chunk, one N tile)
   int dual;               // two MMA-issuing warps on alternate tiles (resident-weight flat-shift launches, SA >= 3)
+  // grouped launch (hrnb_conv_params.ngroup): tile -> (M group, conv g, N tile); per conv: taps, tap offsets, weights, output
+  int ngroup, n_tiles_all;
+  int grp_taps[4];
+  int grp_tap_off[4][4];
+  const __nv_bfloat16* grp_wpk[4];
+  unsigned grp_b_bytes[4];
+  long long grp_out_stride, grp_res_stride;
 };
 
 // floor(n / d) for n < 2^31 and the divisor behind (m, s): m = ceil(2^(31 + c) / d), s = c - 1, c = ceil(log2 d) >= 1.
@@ -188,26 +195,33 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     // executed by the whole warp (uniform operands); one elected lane issues the copies
     {
       int a_stage = 0, a_phase = 0, b_stage = 0, b_phase = 0;
-      const size_t b_elems = k.b_stage_bytes / 2;
       bool b_prefetched = false;
       // RESIDENT WEIGHTS: a layer whose whole weight tensor is one stage (one K chunk, one N tile - the 32- and 64-channel
       // 3x3 layers) loads it once per CTA instead of once per tile: -30 % shared-memory fill traffic on the thinnest layers
       // and one ring stage instead of three, which is what lets two CTAs share an SM there (hrnb_conv: per_sm)
       const bool wres = k.wres != 0;
       if ((int)blockIdx.x < k.num_tiles && !(k.dbg & 16)) {   // first weight stage of the first tile, ahead of the wait
-        const int nt0 = (int)blockIdx.x % k.n_tiles;
+        const int na0 = (int)blockIdx.x % k.n_tiles_all;
+        const int g0 = k.ngroup > 1 ? na0 / k.n_tiles : 0;
+        const int nt0 = na0 - g0 * k.n_tiles;
+        const unsigned bytes0 = k.ngroup > 1 ? k.grp_b_bytes[g0] : k.b_stage_bytes;
+        const __nv_bfloat16* w0 = k.ngroup > 1 ? k.grp_wpk[g0] : k.wpk;
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full_b[0], k.b_stage_bytes);
-          bulk_g2s(b_ring, k.wpk + (size_t)nt0 * k.nchunks * b_elems, k.b_stage_bytes, &full_b[0]);
+          mbar_arrive_expect_tx(&full_b[0], bytes0);
+          bulk_g2s(b_ring, w0 + (size_t)nt0 * k.nchunks * (bytes0 / 2), bytes0, &full_b[0]);
         }
         __syncwarp();
         b_prefetched = true;
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x) {
-        const int mg = tile / k.n_tiles, ntile = tile - mg * k.n_tiles;
+        const int mg = tile / k.n_tiles_all, nall = tile - mg * k.n_tiles_all;
+        const int grp = k.ngroup > 1 ? nall / k.n_tiles : 0;
+        const int ntile = nall - grp * k.n_tiles;
         const long long pstart = (long long)mg * k.MB * 128 - k.lead;  // first halo position (may be < 0: guard band)
-        const __nv_bfloat16* wsrc = k.wpk + (size_t)ntile * k.nchunks * b_elems;
+        const unsigned bbytes = k.ngroup > 1 ? k.grp_b_bytes[grp] : k.b_stage_bytes;
+        const size_t b_elems = bbytes / 2;
+        const __nv_bfloat16* wsrc = (k.ngroup > 1 ? k.grp_wpk[grp] : k.wpk) + (size_t)ntile * k.nchunks * b_elems;
         const int pit = (tile - (int)blockIdx.x) / (int)gridDim.x;
         HRNB_TRACE(0, pit, 0);
         for (int c = 0; c < k.nchunks; ++c) {
@@ -246,8 +260,8 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
             if (k.dbg & 16) {
               if (elect_one_sync()) mbar_arrive(&full_b[b_stage]);
             } else if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&full_b[b_stage], k.b_stage_bytes);
-              bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, k.b_stage_bytes, &full_b[b_stage]);
+              mbar_arrive_expect_tx(&full_b[b_stage], bbytes);
+              bulk_g2s(b_ring + (size_t)b_stage * k.b_stage_bytes, wsrc, bbytes, &full_b[b_stage]);
             }
           }
           __syncwarp();
@@ -291,6 +305,11 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
         HRNB_TRACE(2, it, 0);
         const uint32_t d_base = tmem_base + (uint32_t)(as * acc_cols);
         uint32_t accumulate = 0;
+        int grp = 0, ntaps = k.taps;
+        if (k.ngroup > 1) {
+          grp = (tile % k.n_tiles_all) / k.n_tiles;
+          ntaps = k.grp_taps[grp];
+        }
         for (int c = 0; c < k.nchunks; ++c) {
           // one wait per chunk for the A halo (flat-shift) and for the weights of all taps: every wait / commit
           // stalls the tensor pipe (~100-140 cycles each, measured), so hand-offs are per chunk, not per tap
@@ -299,13 +318,14 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           tc_fence_after_sync();
           if (c == 0) HRNB_TRACE(2, it, 1);
           uint32_t b_lo_tap = b_lo_ring + (uint32_t)b_stage * b_stage16;
-          for (int t = 0; t < k.taps; ++t) {
+          for (int t = 0; t < ntaps; ++t) {
             if (GATHER) {
               mbar_wait(&full_a[a_stage], a_phase);
               tc_fence_after_sync();
             }
             // tap t reads input position p + dpos[t] of source src[t]: a row offset into the halo stage (host table)
-            const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + (GATHER ? 0u : (uint32_t)k.tap_off[t]);
+            const uint32_t toff = GATHER ? 0u : (uint32_t)(k.ngroup > 1 ? k.grp_tap_off[grp][t & 3] : k.tap_off[t]);
+            const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + toff;
             uint32_t d = d_base;
             uint32_t a_lo_mb = a_lo_tap;
             for (int mb = 0; mb < k.MB; ++mb) {
@@ -398,8 +418,15 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       const bool fuse_after = PH && (k.flags & HRNB_CONV_FUSE_AFTER_RELU) != 0;
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1, aph = (it >> 1) & 1;
-        const unsigned mg = k.n_tiles == 1 ? (unsigned)tile : fast_div((unsigned)tile, k.mNt, k.sNt);
-        const int ntile = tile - (int)mg * k.n_tiles;
+        const unsigned mg = k.n_tiles_all == 1 ? (unsigned)tile : fast_div((unsigned)tile, k.mNt, k.sNt);
+        int ntile = tile - (int)mg * k.n_tiles_all;
+        long long gout = 0, gres = 0;      // grouped launch: this tile's conv writes / accumulates into its own tensor
+        if (k.ngroup > 1) {
+          const int grp = ntile / k.n_tiles;
+          ntile -= grp * k.n_tiles;
+          gout = (long long)grp * k.grp_out_stride;
+          gres = (long long)grp * k.grp_res_stride;
+        }
         const unsigned p0 = mg * (unsigned)(k.MB * 128) + (unsigned)(q * 32 + lane);
         unsigned validm = 0, realm = 0;
         unsigned phoff[4] = {0u, 0u, 0u, 0u};   // phase-split copy / output: position of the row in 16-byte units, phase offset included
@@ -422,8 +449,8 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
           }
         }
         const int plane0 = ntile * (k.BN / 8);
-        __nv_bfloat16* const obase = outp + ((long long)plane0 * k.out_ps + p0) * 8;
-        const __nv_bfloat16* const rbase = k.res + ((long long)plane0 * k.res_ps + p0) * 8;
+        __nv_bfloat16* const obase = outp + gout + ((long long)plane0 * k.out_ps + p0) * 8;
+        const __nv_bfloat16* const rbase = k.res + gres + ((long long)plane0 * k.res_ps + p0) * 8;
         const float* const bias_t = bias_s + ntile * k.BN;
         // With 16 epilogue warps a warp owns <= 4 items of a tile (ROUNDS == 1); with 8 warps (two CTAs per SM) up to 8: a second
         // round over items 4..7, whose table entries are recomputed instead of being held in registers.
@@ -924,7 +951,15 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   k->trace = g_trace;
   if (k->nbias * 4 > kBiasBytes) return fail(HRNB_EINVAL, "conv: more than 768 (padded) output channels");
   const int mblocks = (k->P + 127) / 128;
-  k->num_tiles = ((mblocks + p->MB - 1) / p->MB) * k->n_tiles;
+  k->ngroup = p->ngroup > 1 ? p->ngroup : 1;
+  if (k->ngroup > 4) return fail(HRNB_EINVAL, "conv: ngroup must be <= 4");
+  if (k->ngroup > 1 && (gather || !custom || phases_in || nchw || p->out2 || p->stats_sums || p->nfuse > 0 ||
+                        (p->flags & HRNB_CONV_OUT_PHASES)))
+    return fail(HRNB_EINVAL, "conv: a grouped launch needs the flat-shift path with custom taps and a plain PF8 output");
+  k->n_tiles_all = k->n_tiles * k->ngroup;
+  k->num_tiles = ((mblocks + p->MB - 1) / p->MB) * k->n_tiles_all;
+  k->grp_out_stride = p->grp_out_stride;
+  k->grp_res_stride = p->grp_res_stride;
   k->tmem_cols = next_pow2_cols(2 * p->MB * p->BN);
   k->src_stride = p->in_phase_stride;
   for (int t = 0; t < 9; ++t) k->tap_off[t] = 0;
@@ -958,7 +993,7 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
   fast_magic((unsigned)k->Wp, &k->mWp, &k->sWp);
   fast_magic((unsigned)k->Hp, &k->mHp, &k->sHp);
   k->mNt = 0; k->sNt = 0;
-  if (k->n_tiles > 1) fast_magic((unsigned)k->n_tiles, &k->mNt, &k->sNt);
+  if (k->n_tiles_all > 1) fast_magic((unsigned)k->n_tiles_all, &k->mNt, &k->sNt);
   if (p->stats_sums != nullptr) {
     const int groups = p->BN / 16;
     if (!p->stats_ws || gather || nchw || k->n_tiles != 1 || (groups != 1 && groups != 2 && groups != 4) || p->res != nullptr ||
@@ -1000,14 +1035,32 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
       if (tdpos[t] < lo) lo = tdpos[t];
       if (tdpos[t] > hi) hi = tdpos[t];
     }
+    int max_taps = p->taps;
+    if (k->ngroup > 1) {      // one halo serves every conv of the group: union of their tap ranges
+      for (int g = 0; g < k->ngroup; ++g) {
+        if (p->grp_ntap[g] < 1 || p->grp_ntap[g] > 4 || !p->grp_wpk[g]) return fail(HRNB_EINVAL, "conv: grouped launch: 1..4 taps and packed weights per conv");
+        if (p->grp_ntap[g] > max_taps) max_taps = p->grp_ntap[g];
+        for (int t = 0; t < p->grp_ntap[g]; ++t) {
+          if (p->grp_tap_dpos[g][t] < lo) lo = p->grp_tap_dpos[g][t];
+          if (p->grp_tap_dpos[g][t] > hi) hi = p->grp_tap_dpos[g][t];
+        }
+      }
+      k->b_stage_bytes = (unsigned)(max_taps * p->KC * p->BN * 16);   // ring stage = the widest conv of the group
+    }
     if (-lo > HRNB_GUARD_LEAD(k->Wp) || hi > HRNB_GUARD_LEAD(k->Wp)) return fail(HRNB_EINVAL, "conv: tap offset exceeds the PF8 guard band");
     k->lead = -lo;
     k->halo = 128 * p->MB + hi - lo;
     for (int t = 0; t < p->taps; ++t) k->tap_off[t] = tsrc[t] * p->KC * k->halo + k->lead + tdpos[t];
+    for (int g = 0; g < 4; ++g) {
+      k->grp_taps[g] = g < k->ngroup && k->ngroup > 1 ? p->grp_ntap[g] : 0;
+      k->grp_wpk[g] = g < k->ngroup && k->ngroup > 1 ? (const __nv_bfloat16*)p->grp_wpk[g] : nullptr;
+      k->grp_b_bytes[g] = (unsigned)(k->grp_taps[g] * p->KC * p->BN * 16);
+      for (int t = 0; t < 4; ++t) k->grp_tap_off[g][t] = (k->ngroup > 1 && g < k->ngroup && t < p->grp_ntap[g]) ? k->lead + p->grp_tap_dpos[g][t] : 0;
+    }
     k->a_stage_bytes = (unsigned)(k->nsrc * p->KC * k->halo * 16);
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }
-  k->wres = (k->nchunks == 1 && k->n_tiles == 1) ? 1 : 0;   // measured in-trip against per-tile re-loads: +0.5 ... 1 % (inference)
+  k->wres = (k->nchunks == 1 && k->n_tiles_all == 1) ? 1 : 0;   // measured in-trip against per-tile re-loads: +0.5 ... 1 % (inference)
   // dual issue: two tiles in flight need two A stages, a third one is the prefetch; hrnb_debug_set(8, 1) turns it off (A/B)
   k->dual = 0;
   if (k->wres && !gather && g_debug[8] == 0 &&
@@ -1083,6 +1136,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if ((p->flags & HRNB_CONV_FUSE_AFTER_RELU) && (k.out2 == nullptr || !lean_ok))
     return fail(HRNB_EINVAL, "conv: HRNB_CONV_FUSE_AFTER_RELU needs out2 on the flat-shift path");
   if (k.nfuse > 0 && !lean_ok) return fail(HRNB_EINVAL, "conv: fuse sources need the lean epilogue (plain PF8 output)");
+  if (k.ngroup > 1 && (!lean_ok || g_debug[3] != 0 || g_debug[0] != 0)) return fail(HRNB_EINVAL, "conv: a grouped launch needs the lean epilogue");
   const bool lean = lean_ok && ((g_debug[3] == 0 && g_debug[0] == 0) || k.nfuse > 0);
 #define HRNB_PICK(KS, IDX)                                                                                   \
   if (ks == KS) {                                                                                            \

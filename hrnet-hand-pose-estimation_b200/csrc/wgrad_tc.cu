@@ -41,6 +41,10 @@ struct WgradK {
   // (copy i = rows [i*cpl*8, (i+1)*cpl*8)), so ONE MMA per kernel row r yields the taps (r, s0..s0+stack-1):
   //   dW[r,s][co,ci] = sum_q dY[q - s, co] * X[q + (r-1)*Wp - 1, ci]            (q = p + s)
   int stack, s0, cpl;   // stack == 0: plain mode
+  // tap groups (one per CTA): taps [grp_t0[g], grp_t0[g] + grp_tn[g]) read the X tensor at x + grp_x_off[g] elements -
+  // uniform groups of TG taps of one tensor, or one group per input phase of a stride-2 conv (hrnb_wgrad_params.tap_src)
+  int grp_t0[9], grp_tn[9];
+  long long grp_x_off[9];
 };
 
 constexpr int kWgThreads = 192;
@@ -109,8 +113,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradK k)
   const int ks = r / k.n_tg;
   const int c0 = (int)((long long)ks * k.nchunks / k.ksplit);
   const int c1 = (int)((long long)(ks + 1) * k.nchunks / k.ksplit);
-  const int t0 = tg * k.TG;
-  const int tn = (k.ntap - t0 < k.TG) ? (k.ntap - t0) : k.TG;
+  const int t0 = k.grp_t0[tg];
+  const int tn = k.grp_tn[tg];
+  const __nv_bfloat16* const xsrc = k.x + k.grp_x_off[tg];
   const int mt = (k.dy_planes - cot * 16 < 16) ? (k.dy_planes - cot * 16) : 16;
   const int nplanes_b = k.NT / 8;
 
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradK k)
           }
           for (int j = 0; j < nplanes_b; ++j)
             bulk_g2s(b_dst + (size_t)j * b_plane_bytes,
-                     k.x + ((long long)(cit * nplanes_b + j) * k.x_ps + pa - k.lead) * 8, b_plane_bytes, &full[stage]);
+                     xsrc + ((long long)(cit * nplanes_b + j) * k.x_ps + pa - k.lead) * 8, b_plane_bytes, &full[stage]);
         }
         __syncwarp();
         if (++stage == k.S) { stage = 0; phase ^= 1; }
@@ -299,6 +304,32 @@ static long long derive_wgrad(const hrnb_wgrad_params* p, WgradK* k, int* grid, 
   if (TG < 1 || TG * NT > 512) return fail(HRNB_EINVAL, "wgrad: TG*NT exceeds 512 TMEM columns");
   k->TG = TG;
   k->n_tg = (k->ntap + TG - 1) / TG;
+  for (int g = 0; g < 9; ++g) {
+    k->grp_t0[g] = g * TG;
+    k->grp_tn[g] = (k->ntap - g * TG < TG) ? (k->ntap - g * TG > 0 ? k->ntap - g * TG : 0) : TG;
+    k->grp_x_off[g] = 0;
+  }
+  if (p->x_src_stride != 0 && k->stack == 0) {
+    // one tap group per source tensor: consecutive taps with the same tap_src
+    int ng = 0, maxn = 0;
+    for (int t = 0; t < p->ntap;) {
+      int e = t;
+      while (e < p->ntap && p->tap_src[e] == p->tap_src[t]) ++e;
+      if (ng >= 9 || p->tap_src[t] < 0 || p->tap_src[t] > 3) return fail(HRNB_EINVAL, "wgrad: bad tap_src");
+      for (int g = 0; g < ng; ++g)
+        if (k->grp_x_off[g] == (long long)p->tap_src[t] * p->x_src_stride) return fail(HRNB_EINVAL, "wgrad: taps of one source must be consecutive");
+      k->grp_t0[ng] = t;
+      k->grp_tn[ng] = e - t;
+      k->grp_x_off[ng] = (long long)p->tap_src[t] * p->x_src_stride;
+      if (e - t > maxn) maxn = e - t;
+      ++ng;
+      t = e;
+    }
+    if (maxn * NT > 512) return fail(HRNB_EINVAL, "wgrad: taps of one source x NT exceed 512 TMEM columns (pass a smaller NT)");
+    k->TG = maxn;
+    k->n_tg = ng;
+    TG = maxn;
+  }
   int cols = 32;
   while (cols < TG * NT) cols <<= 1;
   k->tmem_cols = cols;

@@ -409,6 +409,38 @@ class ConvLayer:
         return out
 
 
+def grouped_conv_params(layers, x, outs, ress=None):
+    """ONE launch for len(layers) <= 4 custom-tap convs over the same input `x` (include/hrnb.h: ngroup) - the per-phase
+    data-gradient convs of a 3x3 stride-2 conv.  outs / ress: PF8 tensors (views) a constant stride apart."""
+    n = len(layers)
+    assert 2 <= n <= 4 and all(l.custom_taps is not None and l.cin == layers[0].cin and l.cout == layers[0].cout for l in layers)
+    lead = max(range(n), key=lambda i: layers[i].taps)           # the widest conv decides the tile shape
+    L = layers[lead]
+    H, W, P, mode, custom = L._geometry(x)
+    bn, mb, kc = pick_tile(P, W, L.cin, L.cout, L.taps, mode, ress is not None, L.fixed_kc, custom)
+    p = layers[0]._build_params(x, outs[0], ress[0] if ress is not None else None, None, bn, mb, kc)
+    p.ngroup = n
+    keep = []
+    for g, l in enumerate(layers):
+        wpk, _ = l.pack(bn, kc)
+        keep.append(wpk)
+        p.grp_wpk[g], p.grp_ntap[g] = wpk.data_ptr(), l.taps
+        for t, (src, dpos) in enumerate(l.custom_taps):
+            assert src == 0 and t < 4
+            p.grp_tap_dpos[g][t] = dpos
+    stride = (outs[1].ptr - outs[0].ptr) // 2
+    assert all((outs[g].ptr - outs[0].ptr) // 2 == g * stride and outs[g].ps == outs[0].ps for g in range(n))
+    p.grp_out_stride = stride
+    if ress is not None:
+        rstride = (ress[1].ptr - ress[0].ptr) // 2
+        assert all((ress[g].ptr - ress[0].ptr) // 2 == g * rstride and ress[g].ps == ress[0].ps for g in range(n))
+        p.grp_res_stride = rstride
+    p._keep_grp = keep
+    while p.MB > 1 and _lib.lib().hrnb_conv_smem_bytes(C.byref(p)) < 0:
+        p.MB //= 2
+    return p
+
+
 class Repacker:
     """Collects hrnb_pack_job records and (re)packs all of them with ONE launch of hrnb_pack_conv_weights_batch."""
 

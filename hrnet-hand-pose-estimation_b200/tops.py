@@ -48,16 +48,24 @@ def dgrad_taps_s2(Wp_half):
 
 
 # ---- wgrad ------------------------------------------------------------------------------------------------
-def wgrad_params(dy, x_ptr, x_ps, dw, cin, cout, taps, NT=0, TG=0, KP=0, ksplit=0):
+def wgrad_params(dy, x_ptr, x_ps, dw, cin, cout, taps, NT=0, TG=0, KP=0, ksplit=0, src_stride=0):
     """dy: PF8 gradient on the conv's output grid; x_ptr/x_ps: PF8 input tensor (or one phase of it) on the same grid;
-    dw: fp32 [taps_total, cin, cout] (accumulated); taps: [(dpos, tap_id)]."""
+    dw: fp32 [taps_total, cin, cout] (accumulated); taps: [(dpos, tap_id)] or, with src_stride (elements between the input
+    tensors, e.g. the phases of a PhasePF8), [(dpos, tap_id, source)] grouped by source."""
     p = WgradParams()
     p.dy, p.dy_ps, p.x, p.x_ps, p.dw = dy.ptr, dy.ps, x_ptr, x_ps, dw.data_ptr()
     p.N, p.H, p.W, p.cin, p.cout, p.ntap = dy.N, dy.H, dy.W, cin, cout, len(taps)
-    for t, (dpos, tid) in enumerate(taps):
-        p.tap_dpos[t], p.tap_id[t] = dpos, tid
-    p.NT, p.TG, p.KP, p.ksplit = NT, TG, KP, ksplit
+    for t, tap in enumerate(taps):
+        p.tap_dpos[t], p.tap_id[t] = tap[0], tap[1]
+        p.tap_src[t] = tap[2] if len(tap) > 2 else 0
+    p.NT, p.TG, p.KP, p.ksplit, p.x_src_stride = NT, TG, KP, ksplit, src_stride
     return p
+
+
+def fwd_taps_s2_merged(Wp_half):
+    """all nine taps of the 3x3 stride-2 conv over a phase-split input for ONE weight-gradient launch:
+    [(dpos, tap_id, phase)] grouped by phase"""
+    return [(dpos, tid, ph) for ph, taps in sorted(fwd_taps_s2(Wp_half).items()) for dpos, tid in taps]
 
 
 def wgrad(dy, x, dw, cin, cout, taps, **kw):
@@ -73,9 +81,8 @@ def wgrad_conv(dy, x, dw, k, stride):
         wgrad(dy, x, dw, cin, cout, fwd_taps_s1(k, dy.Wp))
     else:
         assert isinstance(x, PhasePF8) and k == 3
-        for ph, taps in fwd_taps_s2(dy.Wp).items():
-            p = wgrad_params(dy, x.ptr + ph * x.phase_stride * 2, x.ps, dw, cin, cout, taps)
-            _lib.check(_lib.lib().hrnb_wgrad(C.byref(p), _lib.stream_ptr()))
+        p = wgrad_params(dy, x.ptr, x.ps, dw, cin, cout, fwd_taps_s2_merged(dy.Wp), src_stride=x.phase_stride)
+        _lib.check(_lib.lib().hrnb_wgrad(C.byref(p), _lib.stream_ptr()))
     return dw
 
 

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib, arch as A, tops
 from .flat import FlatParams
-from .ops import ConvLayer, PF8, PhasePF8, Repacker, attach_stats
+from .ops import ConvLayer, PF8, PhasePF8, Repacker, attach_stats, grouped_conv_params
 
 
 class T:
@@ -138,8 +138,8 @@ class TrainPlan:
             return fn
         return fn, (want and attach_stats(p, stats))
 
-    def _wgrad_fn(self, dy, x_ptr, x_ps, dw, cin, cout, taps):
-        p = tops.wgrad_params(dy, x_ptr, x_ps, dw, cin, cout, taps)
+    def _wgrad_fn(self, dy, x_ptr, x_ps, dw, cin, cout, taps, src_stride=0):
+        p = tops.wgrad_params(dy, x_ptr, x_ps, dw, cin, cout, taps, src_stride=src_stride)
         self.keep.append(p)
         lib, ref = _lib.lib(), C.byref(p)
         return lambda: _lib.check(lib.hrnb_wgrad(ref, _lib.stream_ptr()))
@@ -282,14 +282,28 @@ class TrainPlan:
                 gx, mode = self._gw(x)
                 self._b(self._conv_fn(L["dgrad"], dc, gx, res=gx if mode == 2 else None), "dgrad:" + sp.key)
         else:
-            for ph, taps in tops.fwd_taps_s2(dc.Wp).items():
-                self._bw(self._wgrad_fn(dc, x.v.ptr + ph * x.v.phase_stride * 2, x.v.ps, dw, cin_g, sp.cout, taps), "wgrad:" + sp.key)
+            if os.environ.get("HRNB_S2_SPLIT", "0") == "1":       # A/B: one weight-gradient launch per input phase (round-2 first half)
+                for ph, taps in tops.fwd_taps_s2(dc.Wp).items():
+                    self._bw(self._wgrad_fn(dc, x.v.ptr + ph * x.v.phase_stride * 2, x.v.ps, dw, cin_g, sp.cout, taps), "wgrad:" + sp.key)
+            else:
+                self._bw(self._wgrad_fn(dc, x.v.ptr, x.v.ps, dw, cin_g, sp.cout, tops.fwd_taps_s2_merged(dc.Wp),
+                                        src_stride=x.v.phase_stride), "wgrad:" + sp.key)
             if need_dx:
                 gx, mode = self._gw(x)
-                for ph in range(4):
-                    out = _phase_view(gx, ph)
-                    self.keep.append(out)
-                    self._b(self._conv_fn(L["dgrad"][ph], dc, out, res=out if mode == 2 else None), "dgrad:" + sp.key)
+                outs = [_phase_view(gx, ph) for ph in range(4)]
+                self.keep.extend(outs)
+                if os.environ.get("HRNB_S2_SPLIT", "0") == "1":       # A/B: one data-gradient launch per input phase
+                    for ph in range(4):
+                        self._b(self._conv_fn(L["dgrad"][ph], dc, outs[ph], res=outs[ph] if mode == 2 else None), "dgrad:" + sp.key)
+                else:
+                    # the four per-phase convs (1, 2, 2 and 4 taps) as ONE grouped launch (include/hrnb.h: ngroup)
+                    layers = [L["dgrad"][ph] for ph in range(4)]
+                    for l in layers:
+                        l.no_pdl = not self.eng.pdl
+                    gp = grouped_conv_params(layers, dc, outs, outs if mode == 2 else None)
+                    self.keep.append(gp)
+                    lib, ref = _lib.lib(), C.byref(gp)
+                    self._b(lambda lib=lib, ref=ref: _lib.check(lib.hrnb_conv(ref, _lib.stream_ptr())), "dgrad:" + sp.key)
 
     def fuse(self, srcs, shifts, out_v=None, out_g=None):
         ch, (H, W) = srcs[0].v.C, (srcs[0].v.H << shifts[0], srcs[0].v.W << shifts[0])

@@ -29,7 +29,7 @@ extern "C" {
 #define HRNB_EINVAL (-1)  /* bad argument / unsupported shape */
 #define HRNB_ECUDA (-2)   /* CUDA runtime error (message in hrnb_last_error) */
 
-#define HRNB_ABI_VERSION 4
+#define HRNB_ABI_VERSION 5
 
 /* guard bands (in positions) a PF8 plane must carry around [0, P) */
 #define HRNB_GUARD_LEAD(Wp) ((((Wp) + 2) + 7) / 8 * 8)
@@ -111,7 +111,17 @@ typedef struct hrnb_conv_params {
    * how the fuse sum of the highest-resolution branch, which has no stride-2 chain of its own, gets a host convolution.
    * in_H / in_W are then H >> in_up_shift / W >> in_up_shift. */
   int32_t in_up_shift;
-  int32_t pad_;
+  /* ABI 5: GROUPED launch (flat-shift path, lean PF8 epilogue): ngroup (0 / 1 = off, else 2..4) convolutions over the SAME
+   * input with the same cin / cout / tile shape, each with its own custom tap table (<= 4 taps, source 0), packed weights
+   * and output (residual) tensor `out + g*grp_out_stride` (`res + g*grp_res_stride`) elements - the data gradient of a
+   * 3x3 stride-2 conv, whose four input phases each receive 1, 2, 2 and 4 taps, in ONE launch instead of four.  The bias
+   * vector is shared.  taps / ntap_custom / tap_* / wpk describe group 0 as for a single launch. */
+  int32_t ngroup;
+  int32_t grp_ntap[4];
+  int32_t grp_tap_dpos[4][4];
+  const void* grp_wpk[4];
+  int64_t grp_out_stride;
+  int64_t grp_res_stride;
 } hrnb_conv_params;
 
 int hrnb_conv(const hrnb_conv_params* p, void* stream);
@@ -226,7 +236,8 @@ int hrnb_loss_pose2d(const float* pred, const float* gt, const float* vis, int32
  * hrnb_adam_step / hrnb_grad_to_natural read it through hrnb_param_seg.  dy: PF8 with ceil(cout/8) planes on the
  * conv's OUTPUT grid [N,H,W] (zero padding / guards as always); x: PF8 input on the SAME grid: the conv input itself
  * for stride 1 (3x3: tap_dpos = (r-1)*(W+1) + (s-1)), one phase tensor of it for stride-2 convs (tap (r,s) of a
- * 3x3 stride-2 conv reads phase (r != 1, s != 1) at dpos = -(r == 0)*(W+1) - (s == 0): one launch per phase).
+ * 3x3 stride-2 conv reads phase (r != 1, s != 1) at dpos = -(r == 0)*(W+1) - (s == 0): one launch per phase, or one launch
+ * for all phases with tap_src / x_src_stride).
  * Replaces the weight-gradient half of nn.Conv2d's backward for lib/models/pose_hrnet.py:28-98,187-242,335-350,419-458. */
 typedef struct hrnb_wgrad_params {
   const void* dy;
@@ -241,6 +252,12 @@ typedef struct hrnb_wgrad_params {
   int32_t tap_dpos[9];
   int32_t tap_id[9];
   int32_t NT, TG, KP, ksplit; /* tile overrides: cin tile, taps per CTA, positions per stage, K splits; 0 = auto */
+  /* ABI 5: taps over several input tensors in ONE launch (3x3 stride-2 conv over a phase-split input: all four phases).
+   * Tap t reads the tensor at x + tap_src[t] * x_src_stride elements (plane stride x_ps for every source); taps of one source
+   * must be consecutive in the list and form one CTA tap group (<= 4 taps per source).  x_src_stride == 0: single source. */
+  int32_t tap_src[9];
+  int32_t pad_;
+  int64_t x_src_stride;
 } hrnb_wgrad_params;
 int hrnb_wgrad(const hrnb_wgrad_params* p, void* stream);
 int64_t hrnb_wgrad_smem_bytes(const hrnb_wgrad_params* p);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(_lib.EXPORTS) == set(names), set(_lib.EXPORTS) ^ set(names)
-    assert lib.hrnb_abi_version() == 4
+    assert lib.hrnb_abi_version() == 5
 
 
 def _params(**kw):

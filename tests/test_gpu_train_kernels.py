@@ -140,6 +140,40 @@ def test_dgrad_stride2_matches_autograd(N, H, W, cin, cout):
     assert torch.equal(dx2.to_nchw(), dph.to_nchw())
 
 
+@pytest.mark.parametrize("N,H,W,cin,cout,accumulate", [(2, 32, 32, 32, 64, False), (2, 64, 64, 64, 64, True), (3, 16, 24, 128, 256, False),
+                                                       (1, 16, 16, 256, 64, True), (64, 64, 64, 32, 32, True)])
+def test_grouped_dgrad_stride2_equals_per_phase_launches(N, H, W, cin, cout, accumulate):
+    """include/hrnb.h ngroup: the four per-phase data-gradient convs of a 3x3 stride-2 conv in ONE launch - equal to
+    the four separate launches, writing or accumulating"""
+    import ctypes as C
+    from hrnet_b200 import _lib, tops
+    from hrnet_b200.ops import ConvLayer, PF8, PhasePF8, grouped_conv_params
+    w = _bf16(_rand(cout, cin, 3, 3, seed=16, scale=1.0 / (cin * 9) ** 0.5)).contiguous()
+    dyp = PF8.from_nchw(_bf16(_rand(N, cout, H // 2, W // 2, seed=17)))
+    prev = _bf16(_rand(N, cin, H, W, seed=18))
+    ref, got = PhasePF8(N, cin, H, W), PhasePF8(N, cin, H, W)
+    if accumulate:
+        for d in (ref, got):
+            tops_src = PF8.from_nchw(prev)
+            from hrnet_b200.ops import phase_split
+            phase_split(tops_src, d)
+    layers, outs_ref, outs = [], [], []
+    for ph, (tap_ids, taps) in sorted(tops.dgrad_taps_s2(dyp.Wp).items()):
+        layers.append(ConvLayer(w, transpose=True, tap_ids=tap_ids, custom_taps=taps))
+        outs_ref.append(PF8(N, cin, H // 2, W // 2, buf=ref.buf[ph]))
+        outs.append(PF8(N, cin, H // 2, W // 2, buf=got.buf[ph]))
+    gp = grouped_conv_params(layers, dyp, outs, outs if accumulate else None)
+    for ph, layer in enumerate(layers):     # per-phase launches with the grouped launch's tile shape
+        layer(dyp, outs_ref[ph], outs_ref[ph] if accumulate else None, mb=gp.MB, bn=gp.BN)
+    _lib.check(_lib.lib().hrnb_conv(C.byref(gp), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert got.padding_is_zero()
+    assert _relerr(got.to_nchw(), ref.to_nchw()) < 2e-3      # K-chunk size may differ between the two forms: fp32 summation order
+    x = torch.zeros(N, cin, H, W, device="cuda", requires_grad=True)
+    F.conv2d(x, w, None, stride=2, padding=1).backward(dyp.to_nchw())
+    assert _relerr(got.to_nchw(), x.grad + (prev if accumulate else 0)) < 1.5e-2
+
+
 @pytest.mark.parametrize("N,C,H,W,relu,use_res", [(2, 32, 16, 16, True, True), (4, 64, 8, 12, True, False), (2, 256, 8, 8, False, False),
                                                   (64, 32, 64, 64, True, True), (64, 32, 64, 64, True, False)])
 def test_bn_train_forward_backward(N, C, H, W, relu, use_res):
