@@ -85,6 +85,7 @@ class BnParams(C.Structure):
         ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
         ("N", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("relu", C.c_int32),
         ("eps", C.c_float), ("momentum", C.c_float),
+        ("out2", C.c_void_p), ("out2_ps", C.c_int64), ("out2_phase_stride", C.c_int64),
     ]
 
 

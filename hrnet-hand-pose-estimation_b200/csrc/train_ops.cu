@@ -148,6 +148,7 @@ struct BnK {
   Geo g;
   int relu;
   float eps, momentum, count;
+  __nv_bfloat16* out2; long long out2_ps, out2_phase_stride;   // optional phase-split copy of out (hrnb_bn_params.out2)
 };
 
 // y = [relu]( gamma*(c-mean)*invstd + beta [+ res] ), zeros at padding; block (0, plane) also updates the running stats
@@ -201,6 +202,12 @@ __device__ __forceinline__ void bn_apply_body(const BnK& k, int plane, unsigned 
         for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
       }
       o = pack8(x);
+      if (k.out2 != nullptr) {       // phase (y & 1, x & 1) at (y >> 1, x >> 1) of the half-resolution grid
+        const int y = q.py - 1, xx = q.px - 1;
+        const long long qh = ((long long)q.n * (k.g.H / 2 + 1) + (y >> 1) + 1) * (k.g.W / 2 + 1) + (xx >> 1) + 1;
+        *reinterpret_cast<uint4*>(k.out2 + (long long)((y & 1) * 2 + (xx & 1)) * k.out2_phase_stride +
+                                  ((long long)plane * k.out2_ps + qh) * 8) = o;
+      }
     }
     *reinterpret_cast<uint4*>(k.out + ((long long)plane * k.out_ps + p) * 8) = o;
   }
@@ -772,19 +779,14 @@ extern "C" int hrnb_channel_sum(const void* c, int64_t c_ps, int32_t N, int32_t 
   return check_launch("copy_floats_kernel");
 }
 
+static int fill_bnk(const hrnb_bn_params* p, BnK* k);
+
 extern "C" int hrnb_bn_apply(const hrnb_bn_params* p, void* stream) {
   if (!p || !p->c || !p->sums || !p->gamma || !p->beta || !p->out || p->C % 8 || p->C <= 0)
     return fail(HRNB_EINVAL, "bn_apply: bad params");
   BnK k;
-  k.c = (const __nv_bfloat16*)p->c; k.c_ps = p->c_ps;
-  k.sums = p->sums; k.gamma = p->gamma; k.beta = p->beta;
-  k.res = (const __nv_bfloat16*)p->res; k.res_ps = p->res_ps;
-  k.out = (__nv_bfloat16*)p->out; k.out_ps = p->out_ps;
-  k.running_mean = p->running_mean; k.running_var = p->running_var;
-  if ((k.running_mean == nullptr) != (k.running_var == nullptr)) return fail(HRNB_EINVAL, "bn_apply: running stats must come in pairs");
-  k.g = make_geo(p->N, p->H, p->W);
-  k.relu = p->relu; k.eps = p->eps; k.momentum = p->momentum;
-  k.count = (float)((long long)p->N * p->H * p->W);
+  const int frc = fill_bnk(p, &k);
+  if (frc) return frc;
   dim3 grid(apply_blocks_host(k.g.P), p->C / 8);
   launch_pdl(bn_apply_kernel, grid, dim3(256), 0, (cudaStream_t)stream, k);
   count_launch();
@@ -840,6 +842,8 @@ static int fill_bnk(const hrnb_bn_params* p, BnK* k) {
   k->g = make_geo(p->N, p->H, p->W);
   k->relu = p->relu; k->eps = p->eps; k->momentum = p->momentum;
   k->count = (float)((long long)p->N * p->H * p->W);
+  k->out2 = (__nv_bfloat16*)p->out2; k->out2_ps = p->out2_ps; k->out2_phase_stride = p->out2_phase_stride;
+  if (p->out2 && ((p->H & 1) || (p->W & 1) || p->out2_phase_stride <= 0)) return fail(HRNB_EINVAL, "bn: out2 needs even H and W and a phase stride");
   return HRNB_OK;
 }
 

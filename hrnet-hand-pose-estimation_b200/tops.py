@@ -107,7 +107,7 @@ def bn_stats(c, sums, sid=0):
                                         reduce_ws(sums.device, sid).data_ptr(), _lib.stream_ptr()))
 
 
-def bn_params(c, sums, gamma, beta, out, res=None, relu=True, running_mean=None, running_var=None):
+def bn_params(c, sums, gamma, beta, out, res=None, relu=True, running_mean=None, running_var=None, out2=None):
     p = BnParams()
     p.c, p.c_ps, p.sums, p.gamma, p.beta = c.ptr, c.ps, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr()
     p.res, p.res_ps = (res.ptr, res.ps) if res is not None else (None, 0)
@@ -115,6 +115,9 @@ def bn_params(c, sums, gamma, beta, out, res=None, relu=True, running_mean=None,
     p.running_mean = running_mean.data_ptr() if running_mean is not None else None
     p.running_var = running_var.data_ptr() if running_var is not None else None
     p.N, p.C, p.H, p.W, p.relu, p.eps, p.momentum = c.N, c.C, c.H, c.W, int(relu), EPS, MOMENTUM
+    if out2 is not None:        # phase-split copy of `out` for a following stride-2 conv
+        assert isinstance(out2, PhasePF8) and (out2.N, out2.C, out2.H, out2.W) == (c.N, c.C, c.H, c.W)
+        p.out2, p.out2_ps, p.out2_phase_stride = out2.ptr, out2.ps, out2.phase_stride
     return p
 
 

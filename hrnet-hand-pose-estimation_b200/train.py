@@ -26,10 +26,11 @@ from .ops import ConvLayer, PF8, PhasePF8, Repacker, attach_stats, grouped_conv_
 
 class T:
     """activation node: value + (lazily allocated) gradient buffer"""
-    __slots__ = ("v", "g", "ginit", "g_sid")
+    __slots__ = ("v", "g", "ginit", "g_sid", "bp", "bp_sid")
 
     def __init__(self, v, g=None):
         self.v, self.g, self.ginit, self.g_sid = v, g, False, None
+        self.bp, self.bp_sid = None, None      # BatchNorm launch struct / stream of the unit that produced v (TrainPlan.unit)
 
 
 def _like(v, device):
@@ -151,8 +152,14 @@ class TrainPlan:
         self.act_bytes += ph.v.buf.numel() * 2
         self.all_bufs.append(ph.v)
         lib, s, d = _lib.lib(), x.v, ph.v
-        self._f(lambda: _lib.check(lib.hrnb_phase_split(s.ptr, s.ps, s.N, s.C, s.H, s.W, d.ptr, d.ps, d.phase_stride,
-                                                        _lib.stream_ptr())), "phase_split")
+        bp = getattr(x, "bp", None)
+        if bp is not None and not bp.out2 and getattr(x, "bp_sid", None) == self._sid and os.environ.get("HRNB_SPLIT_KERNEL", "0") != "1":
+            # x comes out of a unit's BatchNorm kernel on this stream: that kernel writes the phase-split copy as well
+            # (hrnb_bn_params.out2) - no separate pass over the tensor
+            bp.out2, bp.out2_ps, bp.out2_phase_stride = d.ptr, d.ps, d.phase_stride
+        else:
+            self._f(lambda: _lib.check(lib.hrnb_phase_split(s.ptr, s.ps, s.N, s.C, s.H, s.W, d.ptr, d.ps, d.phase_stride,
+                                                            _lib.stream_ptr())), "phase_split")
 
         sid = self._sid
 
@@ -188,6 +195,7 @@ class TrainPlan:
         if not fused:      # else: the conv's epilogue already reduced the batch statistics (conv_tc.cu, STATS variant)
             self._f(lambda: tops.bn_stats(c, sums, sid), "bn_stats:" + key)
         self._f(lambda: _lib.check(lib.hrnb_bn_apply(bref, _lib.stream_ptr())), "bn_apply:" + key)
+        y.bp, y.bp_sid = bp, sid          # split() may ask this launch for a phase-split copy of y
 
         def back():
             assert y.ginit, key

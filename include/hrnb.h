@@ -316,6 +316,11 @@ typedef struct hrnb_bn_params {
   int32_t N, C, H, W;
   int32_t relu;
   float eps, momentum;
+  /* ABI 5: optional second, phase-split copy of `out` (the input format of a following 3x3 stride-2 conv, see
+   * hrnb_conv_params): saves the hrnb_phase_split pass over the unit output.  NULL = off; H and W must be even. */
+  void* out2;
+  int64_t out2_ps;
+  int64_t out2_phase_stride;
 } hrnb_bn_params;
 int hrnb_bn_apply(const hrnb_bn_params* p, void* stream);
 /* Horizontally batched form: statistics (written to p[j].sums) + normalisation of n <= 4 independent tensors (the

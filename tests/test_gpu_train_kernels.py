@@ -140,6 +140,25 @@ def test_dgrad_stride2_matches_autograd(N, H, W, cin, cout):
     assert torch.equal(dx2.to_nchw(), dph.to_nchw())
 
 
+def test_bn_apply_writes_the_phase_split_copy():
+    """hrnb_bn_params.out2: the normalisation kernel also writes the unit output in the phase-split form the stride-2 convs
+    read - bit-identical to phase_split of the plain output, padding untouched"""
+    from hrnet_b200 import tops
+    from hrnet_b200.ops import PF8, PhasePF8, phase_split
+    for N, C_, H, W, use_res in ((2, 32, 16, 16, True), (3, 64, 8, 12, False), (64, 32, 64, 64, True)):
+        c = PF8.from_nchw(_bf16(_rand(N, C_, H, W, seed=30) * 1.5 + 0.3))
+        res = PF8.from_nchw(_bf16(_rand(N, C_, H, W, seed=31))) if use_res else None
+        gamma, beta = torch.rand(C_, device="cuda") + 0.5, torch.randn(C_, device="cuda") * 0.1
+        sums = torch.zeros(C_, 2, device="cuda")
+        tops.bn_stats(c, sums)
+        y, y2, ph, ref = PF8(N, C_, H, W), PF8(N, C_, H, W), PhasePF8(N, C_, H, W), PhasePF8(N, C_, H, W)
+        tops.bn_apply(c, sums, gamma, beta, y, res=res, relu=True)
+        tops.bn_apply(c, sums, gamma, beta, y2, res=res, relu=True, out2=ph)
+        phase_split(y, ref)
+        torch.cuda.synchronize()
+        assert torch.equal(y.buf, y2.buf) and torch.equal(ph.buf, ref.buf) and ph.padding_is_zero()
+
+
 @pytest.mark.parametrize("N,H,W,cin,cout,accumulate", [(2, 32, 32, 32, 64, False), (2, 64, 64, 64, 64, True), (3, 16, 24, 128, 256, False),
                                                        (1, 16, 16, 256, 64, True), (64, 64, 64, 32, 32, True)])
 def test_grouped_dgrad_stride2_equals_per_phase_launches(N, H, W, cin, cout, accumulate):
