@@ -139,6 +139,8 @@ _SIGS = {
     "hrnb_bn_bwd_reduce": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
     "hrnb_bn_bwd_apply": (C.c_int, [C.POINTER(BnBwdParams), _vp]),
     "hrnb_fuse_sum_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "hrnb_fuse_sum_bwd_batch": (C.c_int, [_vp, _i64, _vp, _i64, _i32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i32, _i32, _i32, _i32, _i32, _vp]),
     "hrnb_bilinear_up_bwd": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "hrnb_phase_merge": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hrnb_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -154,6 +154,23 @@ def fuse_sum_bwd(dy, y, dsrc, shift, relu=True, mode=1):
                                              _lib.stream_ptr()))
 
 
+def fuse_sum_bwd_batch_args(dy, y, dsrcs, shifts, modes, relu=True):
+    """-> argument tuple of hrnb_fuse_sum_bwd_batch (all sources of one fuse output in one launch); keep it alive"""
+    n = len(dsrcs)
+    assert 1 <= n <= 4 and all(d.H == dy.H >> s and d.W == dy.W >> s and d.C == dy.C for d, s in zip(dsrcs, shifts))
+    ptrs = (C.c_void_p * n)(*[d.ptr for d in dsrcs])
+    pss = (C.c_int64 * n)(*[d.ps for d in dsrcs])
+    sh = (C.c_int32 * n)(*shifts)
+    md = (C.c_int32 * n)(*modes)
+    return (dy.ptr, dy.ps, y.ptr if y is not None else None, y.ps if y is not None else 0, n, ptrs, pss, sh, md,
+            dy.N, dy.H, dy.W, dy.C, int(relu))
+
+
+def fuse_sum_bwd_batch(dy, y, dsrcs, shifts, modes, relu=True):
+    a = fuse_sum_bwd_batch_args(dy, y, dsrcs, shifts, modes, relu)
+    _lib.check(_lib.lib().hrnb_fuse_sum_bwd_batch(*a, _lib.stream_ptr()))
+
+
 def bilinear_up_bwd(d_dst, d_src, align_corners, mode=1):
     assert d_dst.C == d_src.C
     _lib.check(_lib.lib().hrnb_bilinear_up_bwd(d_dst.ptr, d_dst.ps, d_dst.N, d_dst.C, d_dst.H, d_dst.W, d_src.ptr, d_src.ps,

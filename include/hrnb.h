@@ -361,6 +361,11 @@ int hrnb_bn_backward_batch(const hrnb_bn_bwd_params* p, int32_t n, void* stream)
  * fused output grid [N,H,W], dsrc on [N, H>>shift, W>>shift]. */
 int hrnb_fuse_sum_bwd(const void* dy, int64_t dy_ps, const void* y, int64_t y_ps, void* dsrc, int64_t dsrc_ps, int32_t N,
                       int32_t H, int32_t W, int32_t C, int32_t shift, int32_t relu, int32_t mode, void* stream);
+/* ABI 5: the gradients of ALL n <= 4 sources of one fuse output in one launch (source j: dsrc[j] on the grid
+ * [N, H >> shift[j], W >> shift[j]], mode[j] 1 = write, 2 = accumulate); dsrc / dsrc_ps / shift / mode are HOST arrays. */
+int hrnb_fuse_sum_bwd_batch(const void* dy, int64_t dy_ps, const void* y, int64_t y_ps, int32_t n, void* const* dsrc,
+                            const int64_t* dsrc_ps, const int32_t* shift, const int32_t* mode, int32_t N, int32_t H, int32_t W,
+                            int32_t C, int32_t relu, void* stream);
 int hrnb_bilinear_up_bwd(const void* d_dst, int64_t d_dst_ps, int32_t N, int32_t C, int32_t dH, int32_t dW, void* d_src,
                          int64_t d_src_ps, int32_t sH, int32_t sW, int32_t align_corners, int32_t mode, void* stream);
 int hrnb_phase_merge(const void* src_phase00, int64_t src_ps, int64_t phase_stride, void* dst, int64_t dst_ps, int32_t N,

@@ -324,6 +324,17 @@ def test_fuse_sum_backward_matches_autograd():
         d2 = PF8(N, C, H >> s, W >> s)
         tops.fuse_sum_bwd(dyp, y, d2, s, relu=True, mode=1)
         assert _relerr(d2.to_nchw(), srcs[s].grad) < 1.5e-2 and d2.padding_is_zero()
+    # all four sources in one launch (hrnb_fuse_sum_bwd_batch), mixed write / accumulate: bit-identical to the single launches
+    prevs = [_bf16(_rand(N, C, H >> s, W >> s, seed=40 + s)) for s in range(4)]
+    one = [PF8.from_nchw(p) for p in prevs]
+    many = [PF8.from_nchw(p) for p in prevs]
+    modes = [2, 1, 2, 1]
+    for s in range(4):
+        tops.fuse_sum_bwd(dyp, y, one[s], s, relu=True, mode=modes[s])
+    tops.fuse_sum_bwd_batch(dyp, y, many, [0, 1, 2, 3], modes, relu=True)
+    torch.cuda.synchronize()
+    for a, b in zip(one, many):
+        assert torch.equal(a.buf, b.buf) and b.padding_is_zero()
 
 
 @pytest.mark.parametrize("align", [True, False])
