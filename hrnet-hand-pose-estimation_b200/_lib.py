@@ -183,6 +183,8 @@ def lib():
                 "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
         h = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGS.items():
+            if os.environ.get("HRNB_LIB_LAX", "0") == "1" and not hasattr(h, name):
+                continue           # A/B runs against libraries built from earlier commits (tools/gpu_trip21.sh)
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args

@@ -133,7 +133,9 @@ constexpr int kStatsMaxCtas = 320;
 // per warp and tile fully unrolled with all residual loads issued before the accumulator wait, packed fp32x2 adds.
 // PH (lean flat-shift launches whose output also / only exists in the phase-split form a following stride-2 conv reads):
 // kept out of the plain variant - the thin layers are bound by the epilogue's issue slots, every instruction there counts
-template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false, bool LEAN = false, bool PH = false>
+// GRP (grouped launch, hrnb_conv_params.ngroup > 1): its per-tile conv lookup likewise lives in its own instantiation - inside
+// the plain variant it cost 2.8 % (batch 256) / 7 % (batch 64) of the whole inference pass [in-trip A/B of library builds]
+template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false, bool LEAN = false, bool PH = false, bool GRP = false>
 __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ? 1 : kCtasPerSm) conv_tc_kernel(const ConvK k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
@@ -202,10 +204,10 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       const bool wres = k.wres != 0;
       if ((int)blockIdx.x < k.num_tiles && !(k.dbg & 16)) {   // first weight stage of the first tile, ahead of the wait
         const int na0 = (int)blockIdx.x % k.n_tiles_all;
-        const int g0 = k.ngroup > 1 ? na0 / k.n_tiles : 0;
+        const int g0 = GRP ? na0 / k.n_tiles : 0;
         const int nt0 = na0 - g0 * k.n_tiles;
-        const unsigned bytes0 = k.ngroup > 1 ? k.grp_b_bytes[g0] : k.b_stage_bytes;
-        const __nv_bfloat16* w0 = k.ngroup > 1 ? k.grp_wpk[g0] : k.wpk;
+        const unsigned bytes0 = GRP ? k.grp_b_bytes[g0] : k.b_stage_bytes;
+        const __nv_bfloat16* w0 = GRP ? k.grp_wpk[g0] : k.wpk;
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_b[0], bytes0);
           bulk_g2s(b_ring, w0 + (size_t)nt0 * k.nchunks * (bytes0 / 2), bytes0, &full_b[0]);
@@ -216,12 +218,12 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int tile = blockIdx.x; tile < k.num_tiles; tile += gridDim.x) {
         const int mg = tile / k.n_tiles_all, nall = tile - mg * k.n_tiles_all;
-        const int grp = k.ngroup > 1 ? nall / k.n_tiles : 0;
+        const int grp = GRP ? nall / k.n_tiles : 0;
         const int ntile = nall - grp * k.n_tiles;
         const long long pstart = (long long)mg * k.MB * 128 - k.lead;  // first halo position (may be < 0: guard band)
-        const unsigned bbytes = k.ngroup > 1 ? k.grp_b_bytes[grp] : k.b_stage_bytes;
+        const unsigned bbytes = GRP ? k.grp_b_bytes[grp] : k.b_stage_bytes;
         const size_t b_elems = bbytes / 2;
-        const __nv_bfloat16* wsrc = (k.ngroup > 1 ? k.grp_wpk[grp] : k.wpk) + (size_t)ntile * k.nchunks * b_elems;
+        const __nv_bfloat16* wsrc = (GRP ? k.grp_wpk[grp] : k.wpk) + (size_t)ntile * k.nchunks * b_elems;
         const int pit = (tile - (int)blockIdx.x) / (int)gridDim.x;
         HRNB_TRACE(0, pit, 0);
         for (int c = 0; c < k.nchunks; ++c) {
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
         const uint32_t d_base = tmem_base + (uint32_t)(as * acc_cols);
         uint32_t accumulate = 0;
         int grp = 0, ntaps = k.taps;
-        if (k.ngroup > 1) {
+        if constexpr (GRP) {
           grp = (tile % k.n_tiles_all) / k.n_tiles;
           ntaps = k.grp_taps[grp];
         }
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
               tc_fence_after_sync();
             }
             // tap t reads input position p + dpos[t] of source src[t]: a row offset into the halo stage (host table)
-            const uint32_t toff = GATHER ? 0u : (uint32_t)(k.ngroup > 1 ? k.grp_tap_off[grp][t & 3] : k.tap_off[t]);
+            const uint32_t toff = GATHER ? 0u : (uint32_t)(GRP ? k.grp_tap_off[grp][t & 3] : k.tap_off[t]);
             const uint32_t a_lo_tap = a_lo_ring + (uint32_t)a_stage * a_stage16 + toff;
             uint32_t d = d_base;
             uint32_t a_lo_mb = a_lo_tap;
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
         const unsigned mg = k.n_tiles_all == 1 ? (unsigned)tile : fast_div((unsigned)tile, k.mNt, k.sNt);
         int ntile = tile - (int)mg * k.n_tiles_all;
         long long gout = 0, gres = 0;      // grouped launch: this tile's conv writes / accumulates into its own tensor
-        if (k.ngroup > 1) {
+        if constexpr (GRP) {
           const int grp = ntile / k.n_tiles;
           ntile -= grp * k.n_tiles;
           gout = (long long)grp * k.grp_out_stride;
@@ -1118,7 +1120,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // per-device launch state: written once per (device, variant), read on every launch, possibly from one host thread per
   // GPU (nn.DataParallel calls forward that way, tools/train.py:254) -> atomics; cudaFuncSetAttribute itself is idempotent
-  static std::atomic<unsigned char> attr_set[64][56] = {};
+  static std::atomic<unsigned char> attr_set[64][64] = {};
   static std::atomic<int> sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1146,14 +1148,15 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
                 : (nchw_out ? (const void*)conv_tc_kernel<false, true, KS>                                   \
                             : (lean ? (stats ? (const void*)conv_tc_kernel<false, false, KS, true, true>     \
                                              : (phases ? (const void*)conv_tc_kernel<false, false, KS, false, true, true>   \
-                                                       : (const void*)conv_tc_kernel<false, false, KS, false, true>))   \
+                                                       : (k.ngroup > 1 ? (const void*)conv_tc_kernel<false, false, KS, false, true, false, true>   \
+                                                                       : (const void*)conv_tc_kernel<false, false, KS, false, true>)))   \
                                     : (stats ? (const void*)conv_tc_kernel<false, false, KS, true>           \
                                              : (const void*)conv_tc_kernel<false, false, KS>)));             \
   }
   HRNB_PICK(1, 0) HRNB_PICK(2, 1) HRNB_PICK(3, 2) HRNB_PICK(4, 3) HRNB_PICK(6, 4) HRNB_PICK(8, 5) HRNB_PICK(16, 6)
 #undef HRNB_PICK
   if (!fn) return fail(HRNB_EINVAL, "conv: KC must be one of 2, 4, 6, 8, 12, 16, 32");
-  const int variant = ksi * 8 + (gather ? (lean ? 6 : 2) : (nchw_out ? 1 : (lean && phases ? 5 : (stats ? 3 : 0) + (lean ? 4 : 0))));
+  const int variant = ksi * 9 + (gather ? (lean ? 6 : 2) : (nchw_out ? 1 : (lean && phases ? 5 : (k.ngroup > 1 ? 8 : (stats ? 3 : 0) + (lean ? 4 : 0)))));
   if (!attr_set[dev][variant].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "conv: cudaFuncSetAttribute");

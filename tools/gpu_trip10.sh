@@ -3,7 +3,7 @@
 # ncu launch lists (training step, inference pass) and `--set full` captures of the dominant kernels
 mkdir -p gpurun_out; cd "$(dirname "$0")/.."
 O=gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_train_network.py -m gpu -q > $O/t10_pytest.txt 2>&1; echo "train-network tests rc=$?"; tail -4 $O/t10_pytest.txt
+timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_multi.py > $O/t10_pytest.txt 2>&1; echo "suite rc=$?"; tail -4 $O/t10_pytest.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/t10_smoke.txt 2>&1; echo "smoke rc=$?"; tail -2 $O/t10_smoke.txt
 timeout 900 python bench.py > $O/t10_bench_default.json 2> $O/t10_bench_default.err; echo "bench default rc=$?"; cut -c1-600 $O/t10_bench_default.json
 timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > $O/t10_bench_reference.json 2> $O/t10_bench_reference.err; echo "bench ref rc=$?"; cut -c1-400 $O/t10_bench_reference.json
