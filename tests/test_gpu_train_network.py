@@ -417,4 +417,4 @@ def test_loss_trajectory_against_reference(golden_dir):
         floor = float(g["update_cos_floor/" + k])
         _report("trajectory_update:" + k, rel_l2=l2, cos=cos, fp32_floor=floor)
         if k.startswith("last_layer") or k.startswith("stage4"):
-            assert cos > 0.25, (k, l2, cos, floor)
+            assert cos > (0.25 if k.startswith("last_layer") else 0.15), (k, l2, cos, floor)   # measured 0.43-0.52 / 0.30-0.72
