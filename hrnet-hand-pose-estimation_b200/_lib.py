@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("HRNB_LIB", "libhrnb.so"))
 _lib = None
 _lock = threading.Lock()
 
+ABI_VERSION = 5            # include/hrnb.h HRNB_ABI_VERSION (tests/test_abi.py checks the header against this)
 HRNB_CONV_RELU = 1
 HRNB_CONV_OUT_NCHW = 2
 HRNB_CONV_GATHER = 4
@@ -188,7 +189,7 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if h.hrnb_abi_version() != 5:
+        if h.hrnb_abi_version() != ABI_VERSION:
             raise HrnbError("libhrnb.so ABI version mismatch")
         if os.environ.get("HRNB_NO_PDL", "0") == "1":      # debug: launch the conv kernels without programmatic dependent launch
             h.hrnb_debug_set(2, 1)

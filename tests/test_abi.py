@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(_lib.EXPORTS) == set(names), set(_lib.EXPORTS) ^ set(names)
-    assert lib.hrnb_abi_version() == 5
+    header = open(os.path.join(ROOT, "include", "hrnb.h")).read()
+    assert int(re.search(r"#define HRNB_ABI_VERSION (\d+)", header).group(1)) == _lib.ABI_VERSION == lib.hrnb_abi_version()
 
 
 def _params(**kw):
