@@ -22,12 +22,13 @@
 //   TMEM stages  (MMA       -> epilogue) : two accumulator buffers of MB*BN fp32 columns
 // so the loads of tile i+1 and the epilogue of tile i-1 overlap the MMAs of tile i.
 //
-// Warp roles:
-//   warp 0      : bulk-copy producer (A halo chunks, packed weight tiles)           [1 elected lane]
-//   warp 1      : TMEM allocator + tcgen05.mma issuer                                [1 elected lane]
-//   warps 2..5  : epilogue  (tcgen05.ld -> +bias -> +residual -> ReLU -> bf16 -> coalesced 16 B stores);
-//                 the residual of the next 16-channel group is prefetched while the current one is finished
-//   warps 6..9  : (GATHER only) cp.async gather producers, one thread per A row
+// Warp roles (16 epilogue warps in the default build, HRNB_EPI_WARPS):
+//   warp 0       : bulk-copy producer (A halo chunks, packed weight tiles)           [1 elected lane]
+//   warp 1       : TMEM allocator + tcgen05.mma issuer                                [1 elected lane]
+//   warps 2..17  : epilogue  (tcgen05.ld -> +bias -> +residual (+fuse sources) -> ReLU -> bf16 -> coalesced 16 B stores);
+//                  residuals are requested before the accumulator is waited for
+//   warp 18      : second tcgen05.mma issuer on alternate tiles (k.dual: resident-weight flat-shift launches), else idle
+//   warps 19..22 : (GATHER only) cp.async gather producers, one thread per A row
 #include <atomic>
 #include "ptx.cuh"
 #include "common.h"

@@ -70,7 +70,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Hang diagnostics (debug build only: nvcc -DHRNB_HANG_RECORDS): a mapped HOST buffer (hrnb_hang_init) that survives the
 // trap.  Every warp that times out leaves a record: word 0 = blockDim.x << 48 | gridDim.x << 32 | blockIdx.x << 8 | warp,
-// word 1 = barrier smem address << 8 | parity (blockDim.x tells the kernel: 576 conv, 704 conv gather, 192 wgrad; the
+// word 1 = barrier smem address << 8 | parity (blockDim.x tells the kernel: 608 conv, 736 conv gather, 192 wgrad; the
 // address tells the barrier).  Not in the default build: the extra operand set-up in front of every wait was measurable in
 // the wait-heavy wgrad kernel.
 static __device__ unsigned long long* g_hang_buf = nullptr;   // one copy per translation unit, bound by hrnb_hang_init
