@@ -237,7 +237,8 @@ class TrainPlan:
                                       relu=relu, running_mean=L["rm"], running_var=L["rv"]))
             Ls.append(L); cs.append(c); ys.append(y)
         arr = (_lib.BnParams * n)(*bps)
-        ws = tops.reduce_ws(self.dev, 0)
+        sid = self._sid
+        ws = tops.reduce_ws(self.dev, sid)
         self.keep += [arr, bps]
         self._f(lambda: _lib.check(lib.hrnb_bn_forward_batch(arr, n, ws.data_ptr(), have_stats, _lib.stream_ptr())),
                 "bn_fwd_batch:" + keys[0])
@@ -245,14 +246,14 @@ class TrainPlan:
             self.n_launch["fwd"] += 1       # statistics launch for the tensors the convs did not cover + normalisation launch
 
         def back():
-            self._ctx, self._sid = keys[0], 0
+            self._ctx, self._sid = keys[0], sid
             bbs = []
             for L, c, y, res in zip(Ls, cs, ys, ress):
                 assert y.ginit
                 self._gr(y)
                 dres, dmode = (None, 0) if res is None else self._gw(res)
                 bbs.append(tops.bn_bwd_params(y.g, y.v, c, L["sums"], L["gamma"], L["dsums"], y.g, L["dgamma"], L["dbeta"],
-                                              relu=relu, dres=dres, dres_mode=dmode, sid=0))
+                                              relu=relu, dres=dres, dres_mode=dmode, sid=sid))
             barr = (_lib.BnBwdParams * n)(*bbs)
             self.keep += [barr, bbs]
             self._b(lambda: _lib.check(lib.hrnb_bn_backward_batch(barr, n, _lib.stream_ptr())), "bn_bwd_batch:" + keys[0])
@@ -422,11 +423,19 @@ class TrainPlan:
                 for i in range(nb):
                     self.on(i)
                     srcs, shifts = [], []
+                    # the 1x1 convs from the lower-resolution branches are independent units on this stream; batching their
+                    # BatchNorm kernels horizontally (HRNB_FUSE_BN_BATCH=1: -39 launches) measured SLOWER in-trip (20.91 vs 20.75
+                    # ms/step): conv -> BN chains of separate units overlap through PDL, the batched form waits for all convs
+                    up_keys = ["%s.fuse_layers.%d.%d.0" % (pre, i, j) for j in range(i + 1, nb)]
+                    ups_ = None
+                    if len(up_keys) >= 2 and os.environ.get("HRNB_FUSE_BN_BATCH", "0") == "1":
+                        ups_ = self.units(up_keys, [xs[j] for j in range(i + 1, nb)], False)
                     for j in range(nb):
                         if j == i:
                             srcs.append(xs[j]); shifts.append(0)
                         elif j > i:
-                            srcs.append(self.unit("%s.fuse_layers.%d.%d.0" % (pre, i, j), xs[j], False))
+                            srcs.append(ups_[j - i - 1] if ups_ is not None else
+                                        self.unit("%s.fuse_layers.%d.%d.0" % (pre, i, j), xs[j], False))
                             shifts.append(j - i)
                         else:
                             t = splits[j]
