@@ -78,6 +78,7 @@ struct ConvK {
   int in_up_shift;        // gather 1x1: input read at (y >> s, x >> s)
   int wres;               // weights resident in shared memory for the whole CTA (one K chunk, one N tile)
   int dual;               // two MMA-issuing warps on alternate tiles (resident-weight flat-shift launches, SA >= 3)
+  int twin;               // host only: launch the 8-epilogue-warp instantiation with two CTAs per SM
   // grouped launch (hrnb_conv_params.ngroup): tile -> (M group, conv g, N tile); per conv: taps, tap offsets, weights, output
   int ngroup, n_tiles_all;
   int grp_taps[4];
@@ -136,8 +137,12 @@ constexpr int kStatsMaxCtas = 320;
 // kept out of the plain variant - the thin layers are bound by the epilogue's issue slots, every instruction there counts
 // GRP (grouped launch, hrnb_conv_params.ngroup > 1): its per-tile conv lookup likewise lives in its own instantiation - inside
 // the plain variant it cost 2.8 % (batch 256) / 7 % (batch 64) of the whole inference pass [in-trip A/B of library builds]
-template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false, bool LEAN = false, bool PH = false, bool GRP = false>
-__global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ? 1 : kCtasPerSm) conv_tc_kernel(const ConvK k) {
+// EW (epilogue warps): 16, or 8 in the TWO-CTAS-PER-SM instantiation of the plain lean variant used by the thin resident-weight
+// layers at large batch (hrnb_conv: `twin`): those layers are bound by HBM latency per SM (one halo + residual stream per CTA),
+// two co-resident CTAs keep twice the loads in flight [libhrnb_epi8.so experiment: -16 % on the 32-channel 64x64 layers, while
+// every HBM-bound layer with many epilogue items LOSES with 8 warps - hence per launch, not per build]
+template <bool GATHER, bool NCHW, int KSTEPS, bool STATS = false, bool LEAN = false, bool PH = false, bool GRP = false, int EW = kEpiWarps>
+__global__ void __launch_bounds__(GATHER ? kThreadsGather : 96 + 32 * EW, GATHER ? 1 : (EW <= 8 ? 2 : 1)) conv_tc_kernel(const ConvK k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_a = full_a + kMaxSA;
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1u);
-      mbar_init(&tmem_empty[i], (uint32_t)kEpiWarps);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], (uint32_t)EW);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -180,8 +185,8 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     tmem_alloc(tmem_ptr_smem, (uint32_t)k.tmem_cols);
     tmem_relinquish();
   }
-  if (warp >= 2 && warp < 2 + kEpiWarps) {
-    for (int i = threadIdx.x - 64; i < k.nbias; i += 32 * kEpiWarps) bias_s[i] = k.bias[i];
+  if (warp >= 2 && warp < 2 + EW) {
+    for (int i = threadIdx.x - 64; i < k.nbias; i += 32 * EW) bias_s[i] = k.bias[i];
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
         }
       }
     }
-  } else if (warp == 1 || (!GATHER && warp == 2 + kEpiWarps)) {
+  } else if (warp == 1 || (!GATHER && warp == 2 + EW)) {
     // =============================== MMA issuer(s) ===============================
     // Executed by the whole warp so that descriptors stay in uniform registers; one elected lane issues.
     // Per-MMA scalar work is two 32-bit adds: the 64-bit descriptors are (constant hi word, running lo word)
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
         __syncwarp();
       }
     }
-  } else if (warp < 2 + kEpiWarps) {
+  } else if (warp < 2 + EW) {
     // =============================== epilogue ===============================
     // The epilogue is HBM-latency bound (residual reads), so residuals are prefetched PD 16-channel groups ahead
     // into a register ring; the first PD groups of a tile are requested BEFORE waiting for its accumulator.
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int cs = (warp - 2) >> 2;     // which share of the column groups this warp takes
-    constexpr int CS = kEpiWarps / 4;   // warps per quarter
+    constexpr int CS = EW / 4;   // warps per quarter
     const bool relu = (k.flags & HRNB_CONV_RELU) != 0;
     constexpr bool nchw = NCHW;
     const bool has_res = !STATS && k.res != nullptr && !(k.dbg & 1);
@@ -753,9 +758,9 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
     }
   } else {
     // =============================== gather producers (GATHER only) ===============================
-    if (GATHER && warp >= 3 + kEpiWarps) {
+    if (GATHER && warp >= 3 + EW) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      const int g = threadIdx.x - kThreadsFS;  // A row handled by this thread (per M block)
+      const int g = threadIdx.x - (96 + 32 * EW);  // A row handled by this thread (per M block)
       const int LAG = k.lag;
       auto wait_lag = [&]() {   // cp.async.wait_group needs an immediate
         switch (LAG) {
@@ -837,7 +842,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : kThreadsFS, GATHER ?
       // column group g is drained by the warps with cs % groups == g (cs = epilogue warp index / 4), all four lane quarters
       const int g = t >> 5, i = t & 31;
       float s = 0.f;
-      for (int cs = g; cs < kEpiWarps / 4; cs += groups) {
+      for (int cs = g; cs < EW / 4; cs += groups) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) s += bias_s[256 + (cs * 4 + j) * 32 + i];
       }
@@ -1072,6 +1077,21 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     k->SA = 3;
     if (kSmemHeader + 4LL * k->a_stage_bytes + (long long)k->b_stage_bytes <= 200 * 1024) k->SA = 4;   // deeper halo prefetch
   }
+  // twin: two CTAs per SM (8 epilogue warps each, single issuer, two halo stages) for plain lean launches of resident-weight
+  // layers with enough tiles.  OPT-IN (hrnb_debug_set(9, n) / HRNB_TWIN_MIN=n: at least n tiles per CTA slot): next to the dual
+  // issuers and the 4-stage halo ring it measured no gain in-trip (batch 256: 21.8 - 22.0 k vs 22.1 - 22.2 k images/s)
+  k->twin = 0;
+  if (g_debug[9] > 0) {
+    const long long min_tiles = (long long)g_debug[9] * 2 * 148;
+    const bool plain = !gather && !nchw && p->out2 == nullptr && !(p->flags & HRNB_CONV_OUT_PHASES) && p->stats_sums == nullptr &&
+                       k->ngroup == 1 && g_debug[3] == 0 && g_debug[0] == 0;
+    if (k->wres && plain && k->tmem_cols <= 256 && k->num_tiles >= min_tiles &&
+        kSmemHeader + 2LL * k->a_stage_bytes + (long long)k->b_stage_bytes <= 110 * 1024) {
+      k->twin = 1;
+      k->dual = 0;
+      k->SA = 2;
+    }
+  }
   const long long limit = 200 * 1024;
   int SB = k->wres ? 1 : 3;   // resident weights: one stage
   auto total = [&](int sa, int sb) { return kSmemHeader + (long long)sa * k->a_stage_bytes + (long long)sb * k->b_stage_bytes; };
@@ -1121,7 +1141,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // per-device launch state: written once per (device, variant), read on every launch, possibly from one host thread per
   // GPU (nn.DataParallel calls forward that way, tools/train.py:254) -> atomics; cudaFuncSetAttribute itself is idempotent
-  static std::atomic<unsigned char> attr_set[64][64] = {};
+  static std::atomic<unsigned char> attr_set[64][72] = {};
   static std::atomic<int> sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1141,6 +1161,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (k.nfuse > 0 && !lean_ok) return fail(HRNB_EINVAL, "conv: fuse sources need the lean epilogue (plain PF8 output)");
   if (k.ngroup > 1 && (!lean_ok || g_debug[3] != 0 || g_debug[0] != 0)) return fail(HRNB_EINVAL, "conv: a grouped launch needs the lean epilogue");
   const bool lean = lean_ok && ((g_debug[3] == 0 && g_debug[0] == 0) || k.nfuse > 0);
+  const bool twin = k.twin != 0 && lean;
 #define HRNB_PICK(KS, IDX)                                                                                   \
   if (ks == KS) {                                                                                            \
     ksi = IDX;                                                                                               \
@@ -1156,8 +1177,15 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   }
   HRNB_PICK(1, 0) HRNB_PICK(2, 1) HRNB_PICK(3, 2) HRNB_PICK(4, 3) HRNB_PICK(6, 4) HRNB_PICK(8, 5) HRNB_PICK(16, 6)
 #undef HRNB_PICK
+  // two CTAs per SM with 8 epilogue warps each: plain lean launches of resident-weight layers (single issuer, two halo stages
+  // per CTA: derive() sized them for that) with at least g_debug[9] (default 4) tiles per CTA slot
+  if (twin) {
+#define HRNB_TWIN(KS) if (ks == KS) fn = (const void*)conv_tc_kernel<false, false, KS, false, true, false, false, 8>;
+    HRNB_TWIN(1) HRNB_TWIN(2) HRNB_TWIN(3) HRNB_TWIN(4) HRNB_TWIN(6) HRNB_TWIN(8) HRNB_TWIN(16)
+#undef HRNB_TWIN
+  }
   if (!fn) return fail(HRNB_EINVAL, "conv: KC must be one of 2, 4, 6, 8, 12, 16, 32");
-  const int variant = ksi * 9 + (gather ? (lean ? 6 : 2) : (nchw_out ? 1 : (lean && phases ? 5 : (k.ngroup > 1 ? 8 : (stats ? 3 : 0) + (lean ? 4 : 0)))));
+  const int variant = twin ? 64 + ksi : ksi * 9 + (gather ? (lean ? 6 : 2) : (nchw_out ? 1 : (lean && phases ? 5 : (k.ngroup > 1 ? 8 : (stats ? 3 : 0) + (lean ? 4 : 0)))));
   if (!attr_set[dev][variant].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(e, "conv: cudaFuncSetAttribute");
@@ -1169,7 +1197,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
     sm_count[dev].store(nsm, std::memory_order_relaxed);
   }
   // persistent grid: one or two CTAs per SM (two when shared memory and TMEM columns allow it)
-  int per_sm = (kCtasPerSm == 2 && !gather && smem <= 110 * 1024 && 2 * k.tmem_cols <= 512) ? 2 : 1;
+  int per_sm = ((kCtasPerSm == 2 || twin) && !gather && smem <= 110 * 1024 && 2 * k.tmem_cols <= 512) ? 2 : 1;
   if (g_debug[1] > 0) per_sm = g_debug[1] == 1 ? 1 : per_sm;   // debug: force one CTA per SM
   int grid = nsm * per_sm;
   if (grid > k.num_tiles) grid = k.num_tiles;
@@ -1178,7 +1206,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (stats && grid > kStatsMaxCtas) return fail(HRNB_EINVAL, "conv: fused statistics support at most 320 CTAs");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(gather ? (unsigned)kThreadsGather : (unsigned)kThreadsFS);
+  cfg.blockDim = dim3(gather ? (unsigned)kThreadsGather : (twin ? 96u + 32u * 8u : (unsigned)kThreadsFS));
   cfg.dynamicSmemBytes = (size_t)(per_sm == 1 && smem < kTmemExclusiveSmem && g_debug[6] == 0 ? kTmemExclusiveSmem : smem);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

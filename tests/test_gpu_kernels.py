@@ -424,6 +424,41 @@ def test_lean_epilogue_phase_copy_equals_plain_output():
         assert torch.equal(ph.to_nchw(), out.to_nchw()) and ph.padding_is_zero() and out.padding_is_zero()
 
 
+@pytest.mark.parametrize("N,C,H,W,use_res,nfuse", [(160, 32, 64, 64, True, 0), (160, 32, 64, 64, False, 0), (128, 48, 96, 72, True, 0),
+                                                   (160, 32, 64, 64, True, 2)])
+def test_two_ctas_per_sm_variant_equals_the_single_cta_launch(N, C, H, W, use_res, nfuse):
+    """conv_tc.cu `twin` (opt-in, hrnb_debug_set(9, n)): thin resident-weight layers with >= n tiles per CTA slot run the
+    8-epilogue-warp instantiation with two CTAs per SM - bit-identical to the 16-warp launch and right vs torch"""
+    from hrnet_b200 import _lib
+    from hrnet_b200.ops import ConvLayer, PF8
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(N, C, H, W, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5
+    shift = torch.randn(C, device="cuda", generator=g) * 0.1
+    res = PF8.from_nchw(torch.randn(N, C, H, W, device="cuda", generator=g)) if use_res else None
+    srcs = [torch.randn(N, C, H >> s, W >> s, device="cuda", generator=g) for s in range(1, nfuse + 1)]
+    fuse = [(PF8.from_nchw(t), s + 1) for s, t in enumerate(srcs)] or None
+    layer, xp = ConvLayer(w, None, shift, relu=True), PF8.from_nchw(x)
+    outs = []
+    for off in (0, 1):
+        _lib.check(_lib.lib().hrnb_debug_set(9, 0 if off else 2))
+        try:
+            o = PF8(N, C, H, W)
+            layer(xp, o, res, fuse=fuse)
+            torch.cuda.synchronize()
+            outs.append(o)
+        finally:
+            _lib.lib().hrnb_debug_set(9, 0)
+    assert torch.equal(outs[0].buf, outs[1].buf) and outs[0].padding_is_zero()
+    ref = F.conv2d(_bf16(x), _bf16(w), None, padding=1) + shift.view(1, -1, 1, 1)
+    if use_res:
+        ref = ref + res.to_nchw()
+    for s, t in enumerate(srcs):
+        ref = ref + F.interpolate(_bf16(t), scale_factor=2 ** (s + 1), mode="nearest")
+    ref = F.relu(ref)
+    assert (outs[0].to_nchw() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
 def test_fuse_in_epilogue_plan_equals_stand_alone_sum_plan():
     """whole network: the inference plans with the fuse sums inside conv epilogues (output 0 hosted by branch 0's last conv, or
     by the gathered 1x1 conv) against the plan with fuse_sum kernels"""
