@@ -133,6 +133,21 @@ class Plan:
             t = self._conv(i, L[fp], t, dst, name=fp)
         return t
 
+    def _up_tree(self, pre, i, nb, xs, ch, res_hw, sids):
+        """The up-path terms of fuse output i, sum_{j>i} up_{2^(j-i)}(f_ij(x_j)), as ONE tensor on branch i+1's grid: the 1x1 convs
+        run from the lowest resolution upwards and each adds the 2x up-sampled result of the previous one in its epilogue
+        (nearest up-sampling by powers of two composes exactly), so the full-resolution host conv reads one extra source
+        instead of up to three - its epilogue is issue-bound, every source costs ~65 instructions per item.  sids[j]: stream of
+        the conv from branch j.  None when i is the last branch."""
+        L, z = self.engine.layers, None
+        for j in range(nb - 1, i, -1):
+            fp = "%s.fuse_layers.%d.%d.0" % (pre, i, j)
+            if z is not None:
+                self._wait(sids[j], sids[j + 1])
+            z = self._conv(sids[j], L[fp], xs[j], self._buf(ch[i], *res_hw[j]), name=fp + ("+up" if z is not None else ""),
+                           fuse=[(z, 1)] if z is not None else None)
+        return z
+
     def _fuse_in_epilogue(self, pre, i, nb, xs, split, dst, ch, res_hw):
         """Fuse output i = ReLU(sum_j f_ij(x_j)) (lib/models/pose_hrnet.py:199-207,257-266) WITHOUT a separate sum pass: one
         of the output's own convolutions is the host of the sum - its epilogue adds the identity branch (residual input) and
@@ -141,8 +156,14 @@ class Plan:
         grid with its input up-sampled (1x1 conv and nearest up-sampling commute)."""
         L = self.engine.layers
         fuse = []
+        if self.engine.fuse_tree and i > 0:
+            z = self._up_tree(pre, i, nb, xs, ch, res_hw, [i] * nb)
+            if z is not None:
+                fuse.append((z, 1))
         for j in range(nb):
             if j > i and not (i == 0 and j == 1):
+                if self.engine.fuse_tree and i > 0:
+                    continue
                 fp = "%s.fuse_layers.%d.%d.0" % (pre, i, j)
                 fuse.append((self._conv(i, L[fp], xs[j], self._buf(ch[i], *res_hw[j]), name=fp), j - i))
             elif j < i - 1:
@@ -233,12 +254,16 @@ class Plan:
                     # f_0j run first (their inputs are ready long before branch 0's eighth conv), then branch 0's last conv adds
                     # them AFTER its own ReLU (HRNB_CONV_FUSE_AFTER_RELU) - x0 itself only leaves the SM as the phase-split
                     # copy the stride-2 chains read; the full-resolution sum never makes an extra trip through HBM.
-                    fuse0 = []
-                    for j in range(1, nb):
-                        fp = "%s.fuse_layers.0.%d.0" % (pre, j)
-                        fuse0.append((self._conv(j, L[fp], xs[j], self._buf(ch[0], *res_hw[j]), name=fp), j))
-                    for j in range(1, nb):
-                        self._wait(0, j)
+                    if e.fuse_tree:
+                        fuse0 = [(self._up_tree(pre, 0, nb, xs, ch, res_hw, list(range(nb))), 1)]
+                        self._wait(0, 1)
+                    else:
+                        fuse0 = []
+                        for j in range(1, nb):
+                            fp = "%s.fuse_layers.0.%d.0" % (pre, j)
+                            fuse0.append((self._conv(j, L[fp], xs[j], self._buf(ch[0], *res_hw[j]), name=fp), j))
+                        for j in range(1, nb):
+                            self._wait(0, j)
                     layer, y, res0, ph, name = host0
                     out0 = cat.view_planes(0, ch[0] // 8) if last_module else self._buf(ch[0], *res_hw[0])
                     self._conv(0, layer, y, out0, res=res0, name=name, out2=ph, fuse=fuse0, relu=True, fuse_after=True)
@@ -386,6 +411,10 @@ class HRNetEngine:
         # host of fuse output 0: "conv2" = the last conv of branch 0 (default), "gather" = the 1x1 conv from branch 1 evaluated
         # on the up-sampled grid (round-2 first form, 88 us instead of ~10 us extra at batch 256)
         self.fuse_host0 = os.environ.get("HRNB_FUSE_HOST0", "conv2")
+        # HRNB_FUSE_TREE=1: up-path terms of a fuse output pre-summed on the low-resolution grids (Plan._up_tree) instead of
+        # every 1x1 conv output being a separate source of the host conv.  Opt-in: +0.5 % at batch 256, -0.8 % at batch 64,
+        # -3 % at batch 8 in-trip (the chain of small convs is serial, the separate convs run side by side)
+        self.fuse_tree = os.environ.get("HRNB_FUSE_TREE", "0") == "1"
         with torch.cuda.device(self.device):
             _lib.hang_init()
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]

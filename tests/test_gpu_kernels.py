@@ -460,15 +460,16 @@ def test_two_ctas_per_sm_variant_equals_the_single_cta_launch(N, C, H, W, use_re
 
 
 def test_fuse_in_epilogue_plan_equals_stand_alone_sum_plan():
-    """whole network: the inference plans with the fuse sums inside conv epilogues (output 0 hosted by branch 0's last conv, or
-    by the gathered 1x1 conv) against the plan with fuse_sum kernels"""
+    """whole network: the inference plans with the fuse sums inside conv epilogues (output 0 hosted by branch 0's last conv - up-path
+    terms pre-summed on the low-resolution grids or as separate sources - or by the gathered 1x1 conv) against the plan with
+    fuse_sum kernels"""
     import os
     from oracle import fixtures
     from hrnet_b200.config import make_cfg
     from hrnet_b200.models import pose_hrnet_softmax
     outs = []
-    for flag, host0 in (("1", "conv2"), ("1", "gather"), ("0", "conv2")):
-        os.environ["HRNB_FUSE_EPILOGUE"], os.environ["HRNB_FUSE_HOST0"] = flag, host0
+    for flag, host0, tree in (("1", "conv2", "1"), ("1", "conv2", "0"), ("1", "gather", "1"), ("0", "conv2", "1")):
+        os.environ["HRNB_FUSE_EPILOGUE"], os.environ["HRNB_FUSE_HOST0"], os.environ["HRNB_FUSE_TREE"] = flag, host0, tree
         try:
             torch.manual_seed(0)
             m = pose_hrnet_softmax.get_pose_net(make_cfg(32), is_train=False)
@@ -479,7 +480,8 @@ def test_fuse_in_epilogue_plan_equals_stand_alone_sum_plan():
         finally:
             os.environ.pop("HRNB_FUSE_EPILOGUE", None)
             os.environ.pop("HRNB_FUSE_HOST0", None)
-    assert outs[0][2] < outs[2][2] and outs[1][2] < outs[2][2]      # the fuse_sum launches are gone
-    for a in outs[:2]:
-        assert (a[1] - outs[2][1]).abs().max().item() <= 4e-2 * outs[2][1].abs().max().item()
-        assert (a[0] - outs[2][0]).abs().max().item() <= 2e-2 * outs[2][0].abs().max().item()
+            os.environ.pop("HRNB_FUSE_TREE", None)
+    assert all(o[2] < outs[3][2] for o in outs[:3])                 # the fuse_sum launches are gone
+    for a in outs[:3]:
+        assert (a[1] - outs[3][1]).abs().max().item() <= 4e-2 * outs[3][1].abs().max().item()
+        assert (a[0] - outs[3][0]).abs().max().item() <= 2e-2 * outs[3][0].abs().max().item()
