@@ -195,6 +195,8 @@ def lib():
             h.hrnb_debug_set(2, 1)
         if os.environ.get("HRNB_TWIN_MIN"):                 # two-CTAs-per-SM variant: tiles per CTA slot it needs (huge = off)
             h.hrnb_debug_set(9, int(os.environ["HRNB_TWIN_MIN"]))
+        if os.environ.get("HRNB_SLAB", "0") == "1":        # opt-in: resident multi-chunk / multi-N-tile weight slabs (ops.py too)
+            h.hrnb_debug_set(10, 1)
         if os.environ.get("HRNB_NO_DUAL", "0") == "1":     # A/B: one MMA-issuing warp per CTA everywhere
             h.hrnb_debug_set(8, 1)
         if os.environ.get("HRNB_TMEM_SHARE", "0") == "1":  # debug: let TMEM-holding CTAs of different kernels share an SM (can deadlock)

@@ -99,10 +99,10 @@ __device__ __forceinline__ unsigned fast_div(unsigned n, unsigned m, unsigned s)
       k.trace[(role) * 64 + 2 * (iter) + (ev)] = clock64();                                           \
   } while (0)
 
-constexpr int kBarBytes = 256;    // mbarriers + tmem ptr
+constexpr int kBarBytes = 384;    // mbarriers (2*kMaxSA + 2*kMaxSB + 4) + tmem ptr + the STATS ticket at byte 320
 constexpr int kBiasBytes = 3072;  // up to 768 fp32 (whole padded bias vector)
 constexpr int kSmemHeader = kBarBytes + kBiasBytes;
-constexpr int kMaxSA = 8, kMaxSB = 4;
+constexpr int kMaxSA = 8, kMaxSB = 8;   // kMaxSB: also the most K chunks a resident weight slab may have
 
 #ifndef HRNB_EPI_WARPS
 #define HRNB_EPI_WARPS 16
@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : 96 + 32 * EW, GATHER
             if (++a_stage == k.SA) { a_stage = 0; a_phase ^= 1; }
           }
           // one weight stage per K chunk: all taps of the chunk in a single bulk copy (one hand-off per chunk)
+          if (wres) b_stage = c;     // resident slab: chunk c lives in stage c for the whole CTA
           if (b_prefetched) {
             // Stage 0 of the first tile is already in flight - and there is NOTHING to wait for: waiting here for the
             // "previous" phase of empty_b[0] (parity 1) is only a no-op while that barrier is still in phase 0.  The MMA
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : 96 + 32 * EW, GATHER
           // one wait per chunk for the A halo (flat-shift) and for the weights of all taps: every wait / commit
           // stalls the tensor pipe (~100-140 cycles each, measured), so hand-offs are per chunk, not per tap
           if (!GATHER) mbar_wait(&full_a[a_stage], a_phase);
+          if (wres) b_stage = c;     // resident slab: chunk c lives in stage c, filled once (first tile of this CTA)
           if (!wres || it == mw) mbar_wait(&full_b[b_stage], b_phase);
           tc_fence_after_sync();
           if (c == 0) HRNB_TRACE(2, it, 1);
@@ -835,9 +837,9 @@ __global__ void __launch_bounds__(GATHER ? kThreadsGather : 96 + 32 * EW, GATHER
     const int t = threadIdx.x;
     unsigned* counter = reinterpret_cast<unsigned*>(k.stats_ws);
     float* partials = k.stats_ws + 32;
-    // the ticket lives in the spare bytes of the barrier block (28 mbarriers + the TMEM pointer end at byte 228 of 256):
+    // the ticket lives in the spare bytes of the barrier block (36 mbarriers + the TMEM pointer end at byte 292 of 384):
     // a static __shared__ variable would push dynamic + static shared memory over the 227 KB opt-in limit
-    volatile unsigned& ticket_s = *reinterpret_cast<volatile unsigned*>(smem + 240);
+    volatile unsigned& ticket_s = *reinterpret_cast<volatile unsigned*>(smem + 320);
     if (t < nval) {
       // column group g is drained by the warps with cs % groups == g (cs = epilogue warp index / 4), all four lane quarters
       const int g = t >> 5, i = t & 31;
@@ -1068,10 +1070,19 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     k->a_stage_bytes = (unsigned)(k->nsrc * p->KC * k->halo * 16);
     k->SA = 2;  // next tile / next chunk is prefetched while the current one is multiplied
   }
-  k->wres = (k->nchunks == 1 && k->n_tiles_all == 1) ? 1 : 0;   // measured in-trip against per-tile re-loads: +0.5 ... 1 % (inference)
+  // resident weights: the weight slab of ONE N tile stays in shared memory for the life of the CTA.  Default: single-chunk,
+  // single-N-tile layers (+0.5 ... 1 % in-trip).  OPT-IN (hrnb_debug_set(10, 1) / HRNB_SLAB=1): multi-chunk slabs, one ring stage
+  // per K chunk, and several N tiles with the grid a multiple of n_tiles so that every CTA keeps to one N tile (the 480-channel
+  // head conv as 3 x 160).  Measured SLOWER in-trip: the head conv 787 vs 629 us at batch 256 - with 206 KB of the slab + two
+  // 24 KB halo stages only 49 KB of activations are in flight per SM, and the loads, not the re-streamed weights, set the pace.
+  k->wres = 0;
+  if (k->ngroup == 1 && k->nchunks <= kMaxSB && k->n_tiles <= 148 &&
+      (k->nchunks == 1 ? k->n_tiles == 1
+                       : !gather && g_debug[10] != 0 && kSmemHeader + 2LL * k->a_stage_bytes + (long long)k->nchunks * k->b_stage_bytes <= 216 * 1024))
+    k->wres = 1;
   // dual issue: two tiles in flight need two A stages, a third one is the prefetch; hrnb_debug_set(8, 1) turns it off (A/B)
   k->dual = 0;
-  if (k->wres && !gather && g_debug[8] == 0 &&
+  if (k->wres && k->nchunks == 1 && !gather && g_debug[8] == 0 &&
       kSmemHeader + 3LL * k->a_stage_bytes + (long long)k->b_stage_bytes <= 200 * 1024) {
     k->dual = 1;
     k->SA = 3;
@@ -1085,7 +1096,7 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     const long long min_tiles = (long long)g_debug[9] * 2 * 148;
     const bool plain = !gather && !nchw && p->out2 == nullptr && !(p->flags & HRNB_CONV_OUT_PHASES) && p->stats_sums == nullptr &&
                        k->ngroup == 1 && g_debug[3] == 0 && g_debug[0] == 0;
-    if (k->wres && plain && k->tmem_cols <= 256 && k->num_tiles >= min_tiles &&
+    if (k->wres && k->nchunks == 1 && plain && k->tmem_cols <= 256 && k->num_tiles >= min_tiles &&
         kSmemHeader + 2LL * k->a_stage_bytes + (long long)k->b_stage_bytes <= 110 * 1024) {
       k->twin = 1;
       k->dual = 0;
@@ -1093,9 +1104,9 @@ static long long derive(const hrnb_conv_params* p, ConvK* k) {
     }
   }
   const long long limit = 200 * 1024;
-  int SB = k->wres ? 1 : 3;   // resident weights: one stage
+  int SB = k->wres ? k->nchunks : 3;   // resident weights: one stage per K chunk
   auto total = [&](int sa, int sb) { return kSmemHeader + (long long)sa * k->a_stage_bytes + (long long)sb * k->b_stage_bytes; };
-  while (SB > 2 && total(k->SA, SB) > limit) --SB;
+  while (!k->wres && SB > 2 && total(k->SA, SB) > limit) --SB;
   while (gather && k->SA > 3 && total(k->SA, SB) > limit) --k->SA;
   k->lag = gather ? k->SA - 2 : 0;
   const long long smem = total(k->SA, SB);
@@ -1201,6 +1212,7 @@ extern "C" int hrnb_conv(const hrnb_conv_params* p, void* stream) {
   if (g_debug[1] > 0) per_sm = g_debug[1] == 1 ? 1 : per_sm;   // debug: force one CTA per SM
   int grid = nsm * per_sm;
   if (grid > k.num_tiles) grid = k.num_tiles;
+  if (k.wres && k.n_tiles_all > 1 && grid >= k.n_tiles_all) grid -= grid % k.n_tiles_all;   // every CTA keeps to one N tile
   if (stats && k.BN / 16 > kEpiWarps / 4 && k.BN / 16 != 1)
     return fail(HRNB_EINVAL, "conv: fused statistics need one fixed column group per epilogue warp (BN/16 <= epilogue warps / 4)");
   if (stats && grid > kStatsMaxCtas) return fail(HRNB_EINVAL, "conv: fused statistics support at most 320 CTAs");

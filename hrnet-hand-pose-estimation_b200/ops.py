@@ -50,7 +50,7 @@ def _smem_bytes(W, taps, mode, bn, mb, kc, custom=None, wres=False):
     a_stage = nsrc * kc * (128 * mb if gather else halo) * 16
     b_stage = taps * kc * bn * 16
     # wres (one K chunk, one N tile): the weights are loaded once per CTA into a single stage (conv_tc.cu)
-    return 3328 + (5 if gather else 2) * a_stage + (1 if wres else 2) * b_stage
+    return 3456 + (5 if gather else 2) * a_stage + (1 if wres else 2) * b_stage
 
 
 def _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kc, custom=None):
@@ -65,16 +65,24 @@ def _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kc, custom=None):
     # 22,032 images/s at batch 256, training 22.1 vs 21.8 ms/step) - fewer, fatter tiles win over resident weights there.
     wres = nchunks == 1 and cout == bn and os.environ.get("HRNB_PICK_WRES", "0") == "1"
     smem = _smem_bytes(W, taps, mode, bn, mb, kc, custom, wres)
-    if smem > 200 * 1024:
+    # opt-in (HRNB_SLAB=1, measured slower): 1x1 convs with several N tiles (the head conv) keep the whole weight slab of one
+    # N tile resident, every CTA keeps to one N tile (conv_tc.cu: k.wres with nchunks > 1)
+    n_tiles = cout // bn if cout % 16 == 0 else 1
+    slab = False
+    if not gather and taps == 1 and n_tiles > 1 and 1 < nchunks <= 8 and os.environ.get("HRNB_SLAB", "0") == "1":
+        a_st = (_smem_bytes(W, taps, mode, bn, mb, kc, custom) - 3456 - 2 * taps * kc * bn * 16) // 2
+        if 3456 + 2 * a_st + nchunks * taps * kc * bn * 16 <= 216 * 1024:
+            slab, smem = True, 3456 + 2 * a_st + nchunks * taps * kc * bn * 16
+    if smem > (216 if slab else 200) * 1024:
         return None
     ksteps = taps * cin // 16
     handoffs = nchunks * (taps if gather else 1)
     mma = ksteps * mb * max(bn / 2.0, (4096 + bn * 32) / 128.0) * 1.3 + 300.0 * handoffs + 400.0
     # dual issue (conv_tc.cu: k.dual): resident weights (one K chunk, one N tile) and room for three halo stages - the second
     # issuing warp hides the hand-off stalls and keeps the pipe fed
-    a_stage = (smem - 3328 - (1 if wres else 2) * taps * kc * bn * 16) // (5 if gather else 2)
+    a_stage = (smem - 3456 - (1 if wres else 2) * taps * kc * bn * 16) // (5 if gather else 2)
     if (not gather and wres and os.environ.get("HRNB_NO_DUAL", "0") != "1" and tiles >= 4 * NUM_SMS
-            and 3328 + 3 * a_stage + taps * kc * bn * 16 <= 200 * 1024):
+            and 3456 + 3 * a_stage + taps * kc * bn * 16 <= 200 * 1024):
         mma = (mma - 300.0 * handoffs - 400.0) * 0.85 + 200.0
     if custom is not None:
         a_bytes = custom[1] * (128 * mb + custom[0]) * cin * 2
@@ -84,7 +92,7 @@ def _tile_model(P, W, cin, cout, taps, mode, has_res, bn, mb, kc, custom=None):
         a_bytes = 128 * mb * taps * cin * 2 * 2        # 9 taps, half-used 32-byte sectors
     else:
         a_bytes = (128 * mb + (2 * (W + 2) if taps == 9 else 0)) * cin * 2
-    io = a_bytes + (0 if wres else bn * taps * cin * 2 * 0.5) + mb * 128 * bn * 2 * (2 if has_res else 1)
+    io = a_bytes + (0 if (wres or slab) else bn * taps * cin * 2 * 0.5) + mb * 128 * bn * 2 * (2 if has_res else 1)
     cost = max(mma, io / 23.0)
     rounds = -(-tiles // NUM_SMS)        # one persistent CTA per SM
     return rounds * cost + 4500.0
