@@ -15,6 +15,7 @@ kernel runs on which buffer and stream:
 """
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -23,6 +24,7 @@ from .ops import ConvLayer, PF8, PhasePF8
 from ._lib import FuseParams
 
 EPS = 1e-5
+_BUILD_LOCK = threading.RLock()    # engine / plan construction and graph capture: one thread at a time (nn.DataParallel replicas)
 
 
 def _fold(sd, bn_key, conv_bias=None, device=None):
@@ -383,14 +385,17 @@ class Plan:
         if self.graph is None:
             self.graph = {}
         if key not in self.graph:
-            # warm-up outside capture (sets function attributes, loads modules), then capture
-            self._run_steps(want_features, u8)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            # thread_local: nn.DataParallel threads capture / launch on other devices at the same time
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            # warm-up outside capture (sets function attributes, loads modules), then capture.  nn.DataParallel calls forward from
+            # one thread per GPU: building (device synchronisation, allocation) and capturing are serialised across threads -
+            # a cudaDeviceSynchronize of one replica thread while another one captured failed with
+            # cudaErrorStreamCaptureUnsupported about one run in three, thread-local capture mode notwithstanding
+            with _BUILD_LOCK:
                 self._run_steps(want_features, u8)
-            self.graph[key] = g
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._run_steps(want_features, u8)
+                self.graph[key] = g
         self.graph[key].replay()
         return self.out
 
@@ -415,7 +420,7 @@ class HRNetEngine:
         # every 1x1 conv output being a separate source of the host conv.  Opt-in: +0.5 % at batch 256, -0.8 % at batch 64,
         # -3 % at batch 8 in-trip (the chain of small convs is serial, the separate convs run side by side)
         self.fuse_tree = os.environ.get("HRNB_FUSE_TREE", "0") == "1"
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _BUILD_LOCK:
             _lib.hang_init()
             self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
             self._pack(sd)
@@ -465,8 +470,9 @@ class HRNetEngine:
     def plan(self, B, H, W):
         key = (B, H, W)
         if key not in self.plans:
-            with torch.cuda.device(self.device):
-                self.plans[key] = Plan(self, B, H, W)
+            with torch.cuda.device(self.device), _BUILD_LOCK:
+                if key not in self.plans:
+                    self.plans[key] = Plan(self, B, H, W)
         return self.plans[key]
 
     def forward_u8(self, images, mean, std, want_features=True):
