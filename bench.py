@@ -752,7 +752,8 @@ def run_b200_mhp(args):
 CONFIGS = {
     1: dict(mode="infer", variant="raw", width=32, height=256, img_width=256, batch=8),
     2: dict(mode="train", variant="softmax", width=32, height=256, img_width=256, batch=64, loss="hm+pose2d"),
-    3: dict(mode="infer", variant="softmax", width=48, height=384, img_width=288, batch=64, trainable_temp=True),
+    3: dict(mode="infer", variant="softmax", width=48, height=384, img_width=288, batch=256, trainable_temp=True,
+            sweep="1,2,4,8,16,32,64,128,256"),       # BASELINE: "batch sweep 1-256"; the headline value is the last (largest) batch
     4: dict(mode="mhp", variant="softmax", width=32, height=256, img_width=256, batch=16, trainable_temp=True),
     5: dict(mode="train", variant="raw", width=48, height=256, img_width=256, batch=32, loss="hm"),
 }
@@ -787,9 +788,12 @@ def main():
     ap.add_argument("--detail", default=None, help="write per-launch timings (json) here")
     args = ap.parse_args()
     preset = CONFIGS[args.config or 2]
+    user_batch = args.batch is not None
     for k, v in dict(dict(loss="hm+pose2d", trainable_temp=False), **preset).items():
         if getattr(args, k, None) is None:
             setattr(args, k, v)
+    if user_batch and "sweep" in preset and "--sweep" not in sys.argv:
+        args.sweep = None                             # an explicit --batch asks for that one batch, not for the preset's sweep
     if args.variant == "raw":
         args.loss = "hm"
     if args.impl == "reference":
